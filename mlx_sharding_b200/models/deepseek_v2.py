@@ -1,0 +1,121 @@
+"""Sharded DeepSeek-V2 (MLA attention + MoE).
+
+Reference: ``shard/server/model/deepseek_v2.py`` (layer-range wrapper, expert stacking at :101-111,
+tuple ``head_dim`` = (192, 128) at :120-125) + upstream ``DeepseekV2DecoderLayer``.
+
+B200 design notes:
+* ``q_proj`` and ``kv_a_proj_with_mqa`` are concatenated at load into one GEMM when the
+  model has no q-LoRA (DeepSeek-V2-Lite);
+* the KV cache keeps the reference's *decompressed* layout (K 192 / V 128 per head) so results are
+  bit-comparable with the reference pipeline; the MLA append kernel assembles ``[k_nope | k_pe]``
+  straight into the paged pool;
+* MoE = router kernel (fp32 softmax + top-k) -> token permutation -> grouped swap-AB tcgen05 GEMMs over
+  the stacked ``switch_mlp`` weights -> weighted combine fused with shared-expert output + residual.
+"""
+from __future__ import annotations
+
+import re
+from typing import Dict
+
+import torch
+
+from ..ops import BatchMeta, LinearWeight
+from .base import StageModel, deepseek_rope_spec
+
+_EXPERT_RE = re.compile(r"^(model\.layers\.\d+\.mlp)\.experts\.(\d+)\.(gate_proj|up_proj|down_proj)\.(weight|scales|biases)$")
+
+
+class DeepseekV2Stage(StageModel):
+    arch = "deepseek_v2"
+
+    @property
+    def head_dim(self):
+        # reference deepseek_v2.py:120-125 returns the (qk, v) tuple
+        return (self.cfg.qk_nope_head_dim + self.cfg.qk_rope_head_dim, self.cfg.v_head_dim)
+
+    def _make_rope(self):
+        return deepseek_rope_spec(self.cfg)
+
+    def sanitize(self, sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        sd = super().sanitize(sd)
+        # stack per-expert HF weights into switch_mlp.* (reference deepseek_v2.py:101-111)
+        groups: Dict[tuple, Dict[int, torch.Tensor]] = {}
+        for k in list(sd):
+            m = _EXPERT_RE.match(k)
+            if m:
+                groups.setdefault((m.group(1), m.group(3), m.group(4)), {})[int(m.group(2))] = sd.pop(k)
+        for (prefix, proj, kind), d in groups.items():
+            n = self.cfg.n_routed_experts
+            if sorted(d) != list(range(n)):
+                raise ValueError(f"{prefix}.experts.*.{proj}.{kind}: expected {n} experts, found {len(d)}")
+            sd[f"{prefix}.switch_mlp.{proj}.{kind}"] = torch.stack([d[e] for e in range(n)])
+        return sd
+
+    def _load_layer(self, sd, i) -> dict:
+        c = self.cfg
+        p = f"model.layers.{i}"
+        a = p + ".self_attn"
+        w = dict(
+            in_ln=self._vec(sd, p + ".input_layernorm.weight"),
+            post_ln=self._vec(sd, p + ".post_attention_layernorm.weight"),
+            kv_a_ln=self._vec(sd, a + ".kv_a_layernorm.weight"),
+            kv_b=self._lin(sd, a + ".kv_b_proj"),
+            o=self._lin(sd, a + ".o_proj"),
+        )
+        kv_a = self._lin(sd, a + ".kv_a_proj_with_mqa")
+        if c.q_lora_rank is None:
+            w["qkv_a"] = LinearWeight.concat([self._lin(sd, a + ".q_proj"), kv_a])
+        else:
+            w["q_a_kv_a"] = LinearWeight.concat([self._lin(sd, a + ".q_a_proj"), kv_a])
+            w["q_a_ln"] = self._vec(sd, a + ".q_a_layernorm.weight")
+            w["q_b"] = self._lin(sd, a + ".q_b_proj")
+        m = p + ".mlp"
+        if c.is_moe_layer(i):
+            w["router"] = sd.pop(m + ".gate.weight").to(device=self.device, dtype=self.dtype)
+            for n in ("gate", "up", "down"):
+                w["e_" + n] = self._lin(sd, f"{m}.switch_mlp.{n}_proj")
+            if c.n_shared_experts:
+                for n in ("gate", "up", "down"):
+                    w["s_" + n] = self._lin(sd, f"{m}.shared_experts.{n}_proj")
+        else:
+            for n in ("gate", "up", "down"):
+                w[n] = self._lin(sd, f"{m}.{n}_proj")
+        return w
+
+    def layer_forward(self, i, h, meta: BatchMeta, kpool, vpool):
+        O, c, w = self.ops, self.cfg, self.layer_weights[i]
+        T = h.shape[0]
+        nh, nope, rd, vd, lr = (c.num_attention_heads, c.qk_nope_head_dim, c.qk_rope_head_dim,
+                                c.v_head_dim, c.kv_lora_rank)
+        qd = nope + rd
+        normed = O.rmsnorm(h, w["in_ln"], c.rms_norm_eps)
+        if "qkv_a" in w:
+            qkv = O.linear(normed, w["qkv_a"])
+            q = qkv[:, : nh * qd]
+            ckv = qkv[:, nh * qd: nh * qd + lr]
+            k_pe = qkv[:, nh * qd + lr:]
+        else:
+            qa = O.linear(normed, w["q_a_kv_a"])
+            ql = c.q_lora_rank
+            q = O.linear(O.rmsnorm(qa[:, :ql], w["q_a_ln"], c.rms_norm_eps), w["q_b"])
+            ckv, k_pe = qa[:, ql: ql + lr], qa[:, ql + lr:]
+        q = q.view(T, nh, qd) if q.is_contiguous() else q.unflatten(1, (nh, qd))
+        k_pe = k_pe.unflatten(1, (1, rd))
+        O.rope_(q, meta.positions, self.rope, nope)
+        O.rope_(k_pe, meta.positions, self.rope, 0)
+        kv = O.linear(O.rmsnorm(ckv, w["kv_a_ln"], c.rms_norm_eps), w["kv_b"]).view(T, nh, nope + vd)
+        O.kv_write_mla(kv, k_pe.squeeze(1), kpool, vpool, meta.slot_mapping, nope, vd)
+        attn = O.paged_attention(q, kpool, vpool, meta, c.attn_scale, 0.0)
+        h = O.linear(attn.reshape(T, nh * vd), w["o"], residual=h)
+        normed = O.rmsnorm(h, w["post_ln"], c.rms_norm_eps)
+        if "router" in w:
+            idx, wts = O.moe_route(normed, w["router"], c.num_experts_per_tok, c.topk_method,
+                                   c.n_group or 1, c.topk_group or 1, c.routed_scaling_factor,
+                                   c.norm_topk_prob)
+            if "s_gate" in w:
+                h = O.linear(O.gated_up(normed, w["s_gate"], w["s_up"], "silu"), w["s_down"], residual=h)
+            return O.moe_experts(normed, idx, wts, w["e_gate"], w["e_up"], w["e_down"], "silu", residual=h)
+        return O.linear(O.gated_up(normed, w["gate"], w["up"], "silu"), w["down"], residual=h)
+
+
+Model = DeepseekV2Stage
