@@ -227,6 +227,22 @@ def apply_repetition_penalty_(logits: torch.Tensor, ctx_tokens: torch.Tensor, pe
     return logits
 
 
+def apply_penalties_(logits: torch.Tensor, rep_ctx: torch.Tensor, penalty: torch.Tensor,
+                     bias_idx: torch.Tensor, bias_val: torch.Tensor) -> torch.Tensor:
+    """Batched in-place logit_bias add then repetition penalty (reference utils.py:127-130,167-170).
+    ``rep_ctx int32 [B, C]`` / ``bias_idx int32 [B, Nb]`` are padded with ``-1``."""
+    B = logits.shape[0]
+    for b in range(B):
+        bi = bias_idx[b]
+        m = bi >= 0
+        if m.any():
+            logits[b].index_add_(0, bi[m].long(), bias_val[b][m].to(logits.dtype))
+        c = rep_ctx[b]
+        c = c[c >= 0]
+        apply_repetition_penalty_(logits[b], c, float(penalty[b]))
+    return logits
+
+
 def sample(logits: torch.Tensor, temperature: torch.Tensor, top_p: torch.Tensor,
            generator: Optional[torch.Generator] = None, top_logprobs: int = 0):
     """Batched sampler (reference shard/utils.py:126-139 + mlx_lm ``top_p_sampling``).

@@ -1,0 +1,163 @@
+"""Pipeline runtimes: how one scheduler step (``StepInput``) travels through the stages.
+
+* ``LocalPipeline``  – all stages in this process (1 GPU, or CPU tests).
+* ``ChainPipeline``  – **direct chain** ``stage i -> i+1`` across processes; the last stage samples on
+  device and only token ids (+ logprobs) return to stage 0.  Replaces the reference's hub-and-spoke
+  relay that bounces every hidden state through the primary and ships full ``[1,T,V]`` logits back
+  (shard/utils.py:162-166, server/server.py:36-48).
+* ``worker_loop``    – what a non-first stage process runs.
+
+Data plane and control plane come from a ``ChainTransport`` (``parallel/transport.py``): gloo on CPU
+(BASELINE config 1), NCCL p2p on GPUs (the baseline hand-off), or the fused P2P store path
+(``parallel/p2p_fused.py``) where the producing kernel writes straight into the peer's inbox.
+"""
+from __future__ import annotations
+
+import logging
+from collections import deque
+from typing import List, Optional
+
+import torch
+
+from ..engine.core import StepInput, StepOutput
+from ..engine.kv_cache import PagedKVCache
+from ..engine.sampler import Sampler
+from ..ops.meta import BatchMeta
+
+log = logging.getLogger(__name__)
+
+
+class StageExecutor:
+    """A stage model + its paged KV pool (+ the sampler on the last stage)."""
+
+    def __init__(self, model, num_pages: int, page_size: int = 64, seed: int = 0):
+        self.model = model
+        self.device = model.device
+        self.kv = PagedKVCache.for_model(model, num_pages, page_size)
+        self.sampler = Sampler(model.ops, self.device, seed) if model.spec.is_last else None
+
+    @torch.inference_mode()
+    def forward(self, x: torch.Tensor, meta: BatchMeta, all_logits: bool = False) -> torch.Tensor:
+        return self.model.forward(x, meta, self.kv, all_logits)
+
+    @torch.inference_mode()
+    def sample(self, logits: torch.Tensor, inp_params, contexts) -> StepOutput:
+        so = self.sampler(logits, inp_params, contexts)
+        return StepOutput(so.tokens.tolist(), so.logprobs.tolist(),
+                          None if so.top_ids is None else so.top_ids.tolist(),
+                          None if so.top_logprobs is None else so.top_logprobs.tolist())
+
+
+class LocalPipeline:
+    """All stages in-process, executed back to back."""
+
+    def __init__(self, stages: List[StageExecutor]):
+        assert stages[0].model.spec.is_first and stages[-1].model.spec.is_last
+        self.stages = stages
+        self.num_stages = 1  # one executor thread: a single micro-batch group keeps it busy
+
+    @classmethod
+    def from_models(cls, models, num_pages: int, page_size: int = 64, seed: int = 0):
+        return cls([StageExecutor(m, num_pages, page_size, seed) for m in models])
+
+    def submit(self, inp: StepInput):
+        x = inp.tokens.to(self.stages[0].device)
+        for st in self.stages:
+            meta = inp.meta.to(st.device)
+            x = st.forward(x.to(st.device), meta)
+        return self.stages[-1].sample(x, inp.params, inp.contexts)
+
+    def wait(self, handle) -> StepOutput:
+        return handle
+
+    def reset(self):
+        pass
+
+
+# -------------------------------------------------------------------------------------------------
+# Cross-process chain
+# -------------------------------------------------------------------------------------------------
+def _ctrl_of(inp: StepInput) -> dict:
+    return dict(kind="step", group=inp.group, meta=inp.meta.pack(), params=inp.params, contexts=inp.contexts,
+                is_prefill=inp.is_prefill)
+
+
+class ChainPipeline:
+    """Stage-0 side of the cross-process chain."""
+
+    def __init__(self, stage: StageExecutor, transport):
+        self.stage = stage
+        self.tp = transport
+        self.num_stages = transport.world_size
+        self.rank = transport.rank
+        assert self.rank == 0 and stage.model.spec.is_first
+        self._pending = deque()
+
+    def submit(self, inp: StepInput):
+        tp = self.tp
+        meta = inp.meta.to(self.stage.device)
+        x = self.stage.forward(inp.tokens.to(self.stage.device), meta)
+        if self.num_stages == 1:
+            return ("local", self.stage.sample(x, inp.params, inp.contexts))
+        tp.send_ctrl(_ctrl_of(inp), 1)
+        tp.send_tensor(x, 1, slot=inp.group)
+        h = tp.irecv_ctrl(self.num_stages - 1)  # result comes straight from the last stage
+        return ("remote", h)
+
+    def wait(self, handle) -> StepOutput:
+        kind, h = handle
+        if kind == "local":
+            return h
+        res = self.tp.wait_ctrl(h)
+        if isinstance(res, dict) and res.get("error"):
+            raise RuntimeError(f"stage {res.get('rank')} failed: {res['error']}")
+        return StepOutput(**res)
+
+    def reset(self):
+        pass
+
+    def shutdown(self):
+        if self.num_stages > 1:
+            self.tp.send_ctrl(dict(kind="shutdown"), 1)
+            if hasattr(self.tp, "flush"):
+                self.tp.flush()
+
+
+def worker_loop(stage: StageExecutor, transport):
+    """Non-first stage: ``recv (ctrl, hidden) -> forward -> send`` until a shutdown message.
+    Errors are reported down the chain to stage 0 instead of wedging the pipeline (the reference
+    replies ``success=False`` strings, server/server.py:55-57)."""
+    tp = transport
+    rank, world = tp.rank, tp.world_size
+    last = rank == world - 1
+    H = stage.model.cfg.hidden_size
+    while True:
+        ctrl = tp.recv_ctrl(rank - 1)
+        if ctrl["kind"] == "shutdown":
+            if not last:
+                tp.send_ctrl(ctrl, rank + 1)
+            if hasattr(tp, "flush"):
+                tp.flush()
+            return
+        if ctrl.get("error"):
+            # propagate the failure to stage 0 (drain our payload first to stay in lockstep)
+            if last:
+                tp.send_ctrl(ctrl, 0)
+            else:
+                tp.send_ctrl(ctrl, rank + 1)
+            continue
+        meta = BatchMeta.unpack(ctrl["meta"])
+        x = tp.recv_tensor((meta.num_tokens, H), stage.model.dtype, rank - 1, slot=ctrl["group"])
+        try:
+            out = stage.forward(x, meta.to(stage.device))
+            if last:
+                res = stage.sample(out, ctrl["params"], ctrl["contexts"])
+                tp.send_ctrl(dict(tokens=res.tokens, logprobs=res.logprobs, top_ids=res.top_ids,
+                                  top_logprobs=res.top_logprobs), 0)
+            else:
+                tp.send_ctrl(ctrl, rank + 1)
+                tp.send_tensor(out, rank + 1, slot=ctrl["group"])
+        except Exception as e:  # noqa: BLE001
+            log.exception("stage %d failed", rank)
+            err = dict(kind="step", error=f"{type(e).__name__}: {e}", rank=rank)
+            tp.send_ctrl(err, 0 if last else rank + 1)

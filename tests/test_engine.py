@@ -1,0 +1,97 @@
+"""Engine / scheduler tests on the CPU reference path (tiny Llama)."""
+import torch
+
+from helpers import TINY_DSV2, TINY_LLAMA, run_sequence
+from mlx_sharding_b200.config import ModelConfig
+from mlx_sharding_b200.engine.core import LLMEngine, stopping_criteria
+from mlx_sharding_b200.engine.sampler import SamplingParams
+from mlx_sharding_b200.models import build_stage
+from mlx_sharding_b200.parallel.pipeline import LocalPipeline
+from mlx_sharding_b200.utils.checkpoint import random_state_dict
+
+
+def _engine(C=TINY_LLAMA, ranges=None, **kw):
+    cfg = ModelConfig.from_dict(C)
+    sd = dict(random_state_dict(cfg, dtype=torch.float32))
+    ranges = ranges or [(0, cfg.num_hidden_layers)]
+    models = [build_stage(cfg, cfg.shard(s, e), torch.float32).load_state(sd) for s, e in ranges]
+    pipe = LocalPipeline.from_models(models, num_pages=64, page_size=16)
+    return models, LLMEngine(pipe, num_pages=64, page_size=16, **kw)
+
+
+def _greedy_oracle(models, prompt, n):
+    outs = run_sequence(models, prompt, n - 1)
+    return [int(o.argmax()) for o in outs]
+
+
+def test_greedy_matches_single_sequence_oracle():
+    models, eng = _engine()
+    prompt = [3, 9, 27, 81, 243, 11]
+    assert eng.generate(prompt, SamplingParams(temperature=0.0), max_tokens=6) == _greedy_oracle(models, prompt, 6)
+
+
+def test_batch_invariance_and_chunked_prefill():
+    """n concurrent sequences through the micro-batch scheduler == n sequential runs."""
+    models, eng = _engine(TINY_DSV2, ranges=[(0, 2), (2, 4)], num_groups=2, max_prefill_tokens=5)
+    prompts = [[5, 6, 7, 8, 9, 10, 11], [100, 50], [1, 2, 3], [42] * 9, [7, 300, 12, 13]]
+    reqs = [eng.submit(p, SamplingParams(), max_tokens=5) for p in prompts]
+    eng.drain()
+    for p, r in zip(prompts, reqs):
+        assert r.finished and r.finish_reason == "length"
+        assert r.output == _greedy_oracle(models, p, 5), p
+    assert eng.table.alloc.num_free == 63  # every page returned
+
+
+def test_stop_conditions():
+    models, eng = _engine()
+    prompt = [3, 9, 27]
+    ref = _greedy_oracle(models, prompt, 8)
+    k = next(i for i in range(1, 8) if ref[i] not in ref[:i])
+    r = eng.submit(prompt, SamplingParams(), max_tokens=8, eos_token_id=ref[k])
+    eng.drain()
+    assert r.finish_reason == "stop" and r.output == ref[:k + 1]
+    j = next(i for i in range(2, 8) if all(ref[m:m + 2] != ref[i - 1:i + 1] for m in range(i - 1)))
+    r = eng.submit(prompt, SamplingParams(), max_tokens=8, stop_id_sequences=[ref[j - 1:j + 1]])
+    eng.drain()
+    assert r.finish_reason == "stop" and r.output == ref[:j + 1]
+    assert stopping_criteria([1, 2, 3], [[2, 3]], None) == (True, 2)
+    assert stopping_criteria([1, 2, 3], [[9]], 3) == (True, 1)
+    assert stopping_criteria([1, 2, 3], [], None) == (False, 0)
+
+
+def test_threaded_engine_streams_events():
+    models, eng = _engine()
+    eng.start()
+    try:
+        r = eng.submit([4, 5, 6], SamplingParams(logprobs=3), max_tokens=4)
+        evs = list(r)
+        assert len(evs) == 4 and evs[-1].finished and evs[-1].finish_reason == "length"
+        assert all(len(e.top) == 3 for e in evs)
+        assert all(e.logprob <= 0 for e in evs)
+        # the chosen greedy token is the top-1 logprob entry
+        assert all(abs(max(e.top.values()) - e.logprob) < 1e-5 for e in evs)
+        assert r.ttft is not None and r.ttft > 0
+    finally:
+        eng.shutdown()
+
+
+def test_sampling_params_affect_output():
+    models, eng = _engine()
+    prompt = [3, 9, 27]
+    greedy = eng.generate(prompt, SamplingParams(), max_tokens=6)
+    biased = eng.generate(prompt, SamplingParams(logit_bias={7: 100.0}), max_tokens=3)
+    assert biased == [7, 7, 7]
+    pen = eng.generate(prompt, SamplingParams(logit_bias={7: 5.0}, repetition_penalty=50.0,
+                                              repetition_context_size=20), max_tokens=6)
+    assert pen.count(7) <= 1 or pen != [7] * 6
+    torch.manual_seed(0)
+    hot = eng.generate(prompt, SamplingParams(temperature=5.0, top_p=0.95, seed=1), max_tokens=12)
+    assert hot != greedy[:12] or True  # sampling path executes; distribution checked in test_sampler
+    assert len(hot) == 12
+
+
+def test_oversized_request_rejected():
+    models, eng = _engine()
+    r = eng.submit(list(range(1, 200)), SamplingParams(), max_tokens=2000)
+    eng.drain()
+    assert isinstance(r.error, MemoryError)
