@@ -1,0 +1,276 @@
+// Memory-bound helper kernels of a decoder layer: embedding gather
+// with in-kernel MLX-affine dequant, RMSNorm (+Gemma variant, + post-norm residual), rotary embedding
+// (half-split and interleaved/YaRN), paged KV-cache append (plain and MLA-assembling).
+// The reference gets all of these from MLX Metal kernels (mx.fast.rms_norm / mx.fast.rope / Embedding /
+// KVCache.update_and_fetch via mlx_lm blocks); these are from-scratch sm_100a kernels: 128-bit
+// vectorised accesses, one warp-shuffle reduction tree, no shared-memory round trips beyond one exchange.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { f[2 * j] = bf16_lo(w[j]); f[2 * j + 1] = bf16_hi(w[j]); }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+  return o;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ RMSNorm
+// One CTA per row; each thread keeps up to MAXV 16-byte vectors of the row in registers (H <= 256*8*MAXV).
+constexpr int kNormThreads = 256;
+constexpr int kNormMaxV = 8;
+
+__global__ void __launch_bounds__(kNormThreads)
+rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv_bfloat16* __restrict__ w,
+               const __nv_bfloat16* __restrict__ residual, long long ld_res, __nv_bfloat16* __restrict__ out,
+               long long ld_out, int H, float eps, int gemma) {
+  const int row = blockIdx.x;
+  const int nvec = H / 8;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * ld_x);
+  uint4 regs[kNormMaxV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kNormMaxV; ++i) {
+    const int v = threadIdx.x + i * kNormThreads;
+    if (v < nvec) {
+      regs[i] = xr[v];
+      float f[8];
+      unpack8(regs[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+    }
+  }
+  __shared__ float red[kNormThreads / 32];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < kNormThreads / 32; ++i) tot += red[i];
+  const float inv = rsqrtf(tot / (float)H + eps);
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  uint4* orow = reinterpret_cast<uint4*>(out + (size_t)row * ld_out);
+#pragma unroll
+  for (int i = 0; i < kNormMaxV; ++i) {
+    const int v = threadIdx.x + i * kNormThreads;
+    if (v < nvec) {
+      float f[8], g[8];
+      unpack8(regs[i], f);
+      unpack8(wr[v], g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gg = gemma ? (1.0f + g[j]) : g[j];
+        // match the unfused graph: the normalised value is rounded to bf16 before the optional residual add
+        f[j] = f[j] * inv * gg;
+      }
+      if (residual != nullptr) {
+        float r[8];
+        unpack8(reinterpret_cast<const uint4*>(residual + (size_t)row * ld_res)[v], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __bfloat162float(__float2bfloat16_rn(f[j])) + r[j];
+      }
+      orow[v] = pack8(f);
+    }
+  }
+}
+
+cudaError_t rmsnorm_launch(const void* x, long long ld_x, const void* w, const void* residual, long long ld_res,
+                           void* out, long long ld_out, int rows, int H, float eps, bool gemma, cudaStream_t s) {
+  if (H % 8 != 0 || H > kNormThreads * 8 * kNormMaxV || (ld_x % 8) || (ld_out % 8)) return cudaErrorInvalidValue;
+  if (rows == 0) return cudaSuccess;
+  rmsnorm_kernel<<<rows, kNormThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ld_x,
+                                                 static_cast<const __nv_bfloat16*>(w),
+                                                 static_cast<const __nv_bfloat16*>(residual), ld_res,
+                                                 static_cast<__nv_bfloat16*>(out), ld_out, H, eps, gemma ? 1 : 0);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ RoPE
+// In place on x[T, heads, D] (token stride ld_t, head stride ld_h) over dims [rot_off, rot_off + rot_dim).
+// One thread per rotated pair; angle = position * inv_freq[i], computed with full-range sincosf.
+__global__ void rope_kernel(__nv_bfloat16* __restrict__ x, long long ld_t, long long ld_h, int heads,
+                            const int* __restrict__ positions, const float* __restrict__ inv_freq, int rot_off,
+                            int rot_dim, int interleaved, float mscale, int T) {
+  const int half = rot_dim / 2;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total = (long long)T * heads * half;
+  if (idx >= total) return;
+  const int i = idx % half;
+  const int h = (idx / half) % heads;
+  const int t = idx / ((long long)half * heads);
+  float sn, cs;
+  sincosf((float)positions[t] * inv_freq[i], &sn, &cs);
+  __nv_bfloat16* base = x + (size_t)t * ld_t + (size_t)h * ld_h + rot_off;
+  const int i1 = interleaved ? 2 * i : i;
+  const int i2 = interleaved ? 2 * i + 1 : i + half;
+  const float a = __bfloat162float(base[i1]) * mscale, b = __bfloat162float(base[i2]) * mscale;
+  base[i1] = __float2bfloat16_rn(a * cs - b * sn);
+  base[i2] = __float2bfloat16_rn(interleaved ? (a * sn + b * cs) : (b * cs + a * sn));
+}
+
+cudaError_t rope_launch(void* x, long long ld_t, long long ld_h, int heads, const int* positions, const float* inv_freq,
+                        int rot_off, int rot_dim, bool interleaved, float mscale, int T, cudaStream_t s) {
+  const long long total = (long long)T * heads * (rot_dim / 2);
+  if (total == 0) return cudaSuccess;
+  rope_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(static_cast<__nv_bfloat16*>(x), ld_t, ld_h, heads, positions,
+                                                              inv_freq, rot_off, rot_dim, interleaved ? 1 : 0, mscale, T);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ Embedding
+// out[t, :] = table[ids[t], :] * scale; quantised tables are dequantised on the fly:
+// w = scales * q + biases, group size g, codes packed LSB-first in uint32 words (MLX affine layout).
+__global__ void embed_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
+                             __nv_bfloat16* __restrict__ out, int H, float scale, int T) {
+  const int nvec = H / 8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)T * nvec) return;
+  const int t = idx / nvec, v = idx % nvec;
+  uint4 r = reinterpret_cast<const uint4*>(table + (size_t)ids[t] * H)[v];
+  if (scale != 1.0f) {
+    float f[8];
+    unpack8(r, f);
+    const float sc = __bfloat162float(__float2bfloat16_rn(scale));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= sc;
+    r = pack8(f);
+  }
+  reinterpret_cast<uint4*>(out + (size_t)t * H)[v] = r;
+}
+
+template <int BITS>
+__global__ void embed_quant_kernel(const long long* __restrict__ ids, const uint32_t* __restrict__ wq,
+                                   const __nv_bfloat16* __restrict__ scales, const __nv_bfloat16* __restrict__ biases,
+                                   __nv_bfloat16* __restrict__ out, int H, int group, float scale, int T) {
+  constexpr int PER = 32 / BITS;  // codes per word
+  const int words = H / PER;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)T * words) return;
+  const int t = idx / words, wi = idx % words;
+  const long long row = ids[t];
+  const uint32_t word = wq[(size_t)row * words + wi];
+  const int col0 = wi * PER;
+  const int ng = H / group;
+  const float s = __bfloat162float(scales[(size_t)row * ng + col0 / group]);
+  const float b = __bfloat162float(biases[(size_t)row * ng + col0 / group]);
+  const float sc = (scale != 1.0f) ? __bfloat162float(__float2bfloat16_rn(scale)) : 1.0f;
+  __nv_bfloat16* o = out + (size_t)t * H + col0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const float q = (float)((word >> (j * BITS)) & ((1u << BITS) - 1u));
+    float val = s * q + b;
+    if (scale != 1.0f) val = __bfloat162float(__float2bfloat16_rn(val)) * sc;
+    o[j] = __float2bfloat16_rn(val);
+  }
+}
+
+cudaError_t embed_launch(const long long* ids, const void* table, const void* scales, const void* biases, int bits, int group,
+                         void* out, int H, float scale, int T, cudaStream_t s) {
+  if (T == 0) return cudaSuccess;
+  if (bits == 0) {
+    if (H % 8) return cudaErrorInvalidValue;
+    const long long n = (long long)T * (H / 8);
+    embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ids, static_cast<const __nv_bfloat16*>(table),
+                                                              static_cast<__nv_bfloat16*>(out), H, scale, T);
+  } else {
+    const int per = 32 / bits;
+    const long long n = (long long)T * (H / per);
+    auto sc = static_cast<const __nv_bfloat16*>(scales);
+    auto bi = static_cast<const __nv_bfloat16*>(biases);
+    auto wq = static_cast<const uint32_t*>(table);
+    auto o = static_cast<__nv_bfloat16*>(out);
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (bits == 4) embed_quant_kernel<4><<<grid, 256, 0, s>>>(ids, wq, sc, bi, o, H, group, scale, T);
+    else if (bits == 8) embed_quant_kernel<8><<<grid, 256, 0, s>>>(ids, wq, sc, bi, o, H, group, scale, T);
+    else if (bits == 2) embed_quant_kernel<2><<<grid, 256, 0, s>>>(ids, wq, sc, bi, o, H, group, scale, T);
+    else return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ KV append
+// pools are [pages, kv_heads, page_size, D]; slot = page * page_size + offset.
+__global__ void kv_write_kernel(const __nv_bfloat16* __restrict__ k, long long k_ld_t, long long k_ld_h,
+                                const __nv_bfloat16* __restrict__ v, long long v_ld_t, long long v_ld_h,
+                                __nv_bfloat16* __restrict__ kpool, __nv_bfloat16* __restrict__ vpool,
+                                const int* __restrict__ slots, int heads, int dk, int dv, int page, int T) {
+  const int vk = dk / 8, vv = dv / 8, per = vk + vv;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)T * heads * per) return;
+  const int c = idx % per;
+  const int h = (idx / per) % heads;
+  const int t = idx / ((long long)per * heads);
+  const int slot = slots[t];
+  const size_t pg = slot / page, off = slot % page;
+  if (c < vk) {
+    const uint4 r = reinterpret_cast<const uint4*>(k + (size_t)t * k_ld_t + (size_t)h * k_ld_h)[c];
+    reinterpret_cast<uint4*>(kpool + ((pg * heads + h) * page + off) * dk)[c] = r;
+  } else {
+    const uint4 r = reinterpret_cast<const uint4*>(v + (size_t)t * v_ld_t + (size_t)h * v_ld_h)[c - vk];
+    reinterpret_cast<uint4*>(vpool + ((pg * heads + h) * page + off) * dv)[c - vk] = r;
+  }
+}
+
+cudaError_t kv_write_launch(const void* k, long long k_ld_t, long long k_ld_h, const void* v, long long v_ld_t,
+                            long long v_ld_h, void* kpool, void* vpool, const int* slots, int heads, int dk, int dv,
+                            int page, int T, cudaStream_t s) {
+  if (T == 0) return cudaSuccess;
+  if ((dk % 8) || (dv % 8) || (k_ld_t % 8) || (k_ld_h % 8) || (v_ld_t % 8) || (v_ld_h % 8)) return cudaErrorInvalidValue;
+  const long long n = (long long)T * heads * (dk / 8 + dv / 8);
+  kv_write_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(k), k_ld_t, k_ld_h, static_cast<const __nv_bfloat16*>(v), v_ld_t, v_ld_h,
+      static_cast<__nv_bfloat16*>(kpool), static_cast<__nv_bfloat16*>(vpool), slots, heads, dk, dv, page, T);
+  return cudaGetLastError();
+}
+
+// MLA append (reference layout, deepseek_v2.py:120-125): kv[T, heads, nope + vd] from kv_b_proj, k_pe[T, rd]
+// shared by all heads -> K row = [k_nope | k_pe], V row = v.
+__global__ void kv_write_mla_kernel(const __nv_bfloat16* __restrict__ kv, long long kv_ld_t,
+                                    const __nv_bfloat16* __restrict__ kpe, long long pe_ld_t,
+                                    __nv_bfloat16* __restrict__ kpool, __nv_bfloat16* __restrict__ vpool,
+                                    const int* __restrict__ slots, int heads, int nope, int rd, int vd, int page, int T) {
+  const int vn = nope / 8, vr = rd / 8, vvv = vd / 8, per = vn + vr + vvv;
+  const int dk = nope + rd;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)T * heads * per) return;
+  const int c = idx % per;
+  const int h = (idx / per) % heads;
+  const int t = idx / ((long long)per * heads);
+  const int slot = slots[t];
+  const size_t pg = slot / page, off = slot % page;
+  const __nv_bfloat16* src = kv + (size_t)t * kv_ld_t + (size_t)h * (nope + vd);
+  __nv_bfloat16* krow = kpool + ((pg * heads + h) * page + off) * dk;
+  __nv_bfloat16* vrow = vpool + ((pg * heads + h) * page + off) * vd;
+  if (c < vn) reinterpret_cast<uint4*>(krow)[c] = reinterpret_cast<const uint4*>(src)[c];
+  else if (c < vn + vr) reinterpret_cast<uint4*>(krow + nope)[c - vn] = reinterpret_cast<const uint4*>(kpe + (size_t)t * pe_ld_t)[c - vn];
+  else reinterpret_cast<uint4*>(vrow)[c - vn - vr] = reinterpret_cast<const uint4*>(src + nope)[c - vn - vr];
+}
+
+cudaError_t kv_write_mla_launch(const void* kv, long long kv_ld_t, const void* kpe, long long pe_ld_t, void* kpool,
+                                void* vpool, const int* slots, int heads, int nope, int rd, int vd, int page, int T,
+                                cudaStream_t s) {
+  if (T == 0) return cudaSuccess;
+  if ((nope % 8) || (rd % 8) || (vd % 8) || (kv_ld_t % 8) || (pe_ld_t % 8)) return cudaErrorInvalidValue;
+  const long long n = (long long)T * heads * ((nope + rd + vd) / 8);
+  kv_write_mla_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(kv), kv_ld_t, static_cast<const __nv_bfloat16*>(kpe), pe_ld_t,
+      static_cast<__nv_bfloat16*>(kpool), static_cast<__nv_bfloat16*>(vpool), slots, heads, nope, rd, vd, page, T);
+  return cudaGetLastError();
+}
+
+}  // namespace b200

@@ -1,0 +1,453 @@
+// Swap-AB tcgen05 GEMM for LLM inference on sm_100a:  Y[tokens, N] = X[tokens, K] · W[N, K]^T
+//
+// Implements SURVEY §2.6 K3/K4/K5/K8/K9/K11/K12 (all projection GEMMs, the SwiGLU/GeGLU pair, the MoE
+// grouped GEMMs and the LM head) — ops the reference delegates to MLX Metal matmul / gather_qmm
+// (shard/server/model/*.py via mlx_lm blocks).
+//
+// Design (B200-first, not a translation of anything):
+//  * The *weight* tile is the 128-row MMA "A" operand (UMMA_M = 128 output features) and the *token*
+//    tile is the "B" operand (UMMA_N = BN in {16..256} tokens).  Decode batches are skinny (1..64
+//    tokens) so the tensor-core tile is always full along M and the kernel is a pure HBM weight
+//    stream; prefill uses BN = 256 and gets the same 128x256 tile as a conventional layout.
+//  * TMA (cp.async.bulk.tensor, 128B swizzle) feeds a STAGES-deep shared-memory ring; one elected
+//    thread issues tcgen05.mma with fp32 accumulators in TMEM; 4 epilogue warps read TMEM with
+//    tcgen05.ld, apply the fused epilogue, transpose through shared memory and write coalesced rows.
+//  * DUAL mode streams two weight matrices (gate, up) against the same token tile into two TMEM
+//    accumulators and writes act(gate)*up — the SwiGLU intermediate never touches HBM un-fused.
+//  * Grouped mode (MoE): blockIdx.y = expert, rows come from a permuted token buffer via per-expert
+//    offsets; experts with no tokens exit immediately.
+//  * split-K (decode, few output tiles): partial tiles go to an fp32 workspace; the last-arriving CTA of a
+//    tile (global atomic ticket) reduces them in split order (deterministic) and runs the epilogue.
+//  * Fused stage boundary: `out` may be a peer-mapped pointer (next pipeline stage's inbox over
+//    NVLink); when `signal_flag` is set the last CTA of the grid publishes it with st.release.sys
+//    after a system-scope fence — GEMM + P2P hand-off in one kernel, no NCCL call, no host hop.
+#include "gemm_tcgen05.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int kTileM = 128;      // output features per CTA (UMMA M)
+constexpr int kBlockK = 64;      // bf16 elements per k-block = one 128B swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kNumThreads = 192;  // warp0: TMA, warp1: MMA + TMEM alloc, warps 2..5: epilogue
+constexpr int kEpiThreads = 128;
+constexpr int kATileBytes = kTileM * kBlockK * 2;  // 16 KB
+
+__host__ __device__ constexpr int stage_bytes(int BN, bool dual) {
+  return kATileBytes * (dual ? 2 : 1) + BN * kBlockK * 2;
+}
+__host__ __device__ constexpr int num_stages(int BN, bool dual, int out_bytes) {
+  // leave room for barriers; the epilogue staging buffer aliases the (by then idle) stage ring
+  int s = (200 * 1024) / stage_bytes(BN, dual);
+  s = s > 8 ? 8 : s;
+  // the ring must be at least as large as the epilogue staging tile
+  while (s * stage_bytes(BN, dual) < BN * kTileM * out_bytes) ++s;
+  return s;
+}
+__host__ __device__ constexpr uint32_t tmem_cols(int BN, bool dual) {
+  int c = BN * (dual ? 2 : 1);
+  return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512;
+}
+
+__device__ __forceinline__ float apply_act(int act, float g) {
+  if (act == kActSilu) return g / (1.0f + __expf(-g));
+  if (act == kActGeluTanh) {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    float u = k0 * (g + k1 * g * g * g);
+    float t = 1.0f - 2.0f / (1.0f + __expf(2.0f * u));  // tanh(u)
+    return 0.5f * g * (1.0f + t);
+  }
+  return g;
+}
+
+template <typename OutT>
+__device__ __forceinline__ void stage_store(OutT* p, float v);
+template <>
+__device__ __forceinline__ void stage_store<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ void stage_store<float>(float* p, float v) { *p = v; }
+
+}  // namespace
+
+template <int BN, bool DUAL, typename OutT>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_w2,
+                   const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
+  constexpr int STAGES = num_stages(BN, DUAL, sizeof(OutT));
+  constexpr int STAGE_BYTES = stage_bytes(BN, DUAL);
+  constexpr uint32_t TMEM_COLS = tmem_cols(BN, DUAL);
+  constexpr uint32_t IDESC = umma_idesc_bf16(kTileM, BN);
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024B alignment is required by the 128B swizzle atom (8 rows x 128 B)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint32_t* flag_smem = tmem_base_smem + 1;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---------------------------------------------------------------- tile coordinates
+  const int n0 = blockIdx.x * kTileM;
+  const int expert = blockIdx.y;
+  const int split = blockIdx.z % p.splits;
+  const int mt = blockIdx.z / p.splits;
+  int row_base = 0, rows_valid = p.m;
+  if (p.expert_offsets != nullptr) {
+    const int lo = p.expert_offsets[expert], hi = p.expert_offsets[expert + 1];
+    row_base = lo;
+    rows_valid = hi - lo;
+  }
+  rows_valid -= mt * BN;
+  row_base += mt * BN;
+  if (rows_valid <= 0) return;  // uniform across the CTA: nothing allocated yet
+  if (rows_valid > BN) rows_valid = BN;
+  const int w_row = expert * p.n + n0;
+
+  const int kb_total = (p.k + kBlockK - 1) / kBlockK;
+  const int kb_per = (kb_total + p.splits - 1) / p.splits;
+  const int kb_begin = split * kb_per;
+  int kb_end = kb_begin + kb_per;
+  if (kb_end > kb_total) kb_end = kb_total;
+  const int num_kb = kb_end - kb_begin;  // may be 0 for a trailing split: contributes zeros
+
+  // ---------------------------------------------------------------- one-time setup
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_x);
+    if (DUAL) tma_prefetch_desc(&tmap_w2);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ============================================================== TMA producer
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        const int kc = (kb_begin + i) * kBlockK;
+        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        // weights are streamed exactly once per launch: evict-first; activations are re-read by every
+        // feature tile: evict-last
+        tma_load_2d(st, &tmap_w, &full_bar[s], kc, w_row, kEvictFirst);
+        if (DUAL) tma_load_2d(st + kATileBytes, &tmap_w2, &full_bar[s], kc, w_row, kEvictFirst);
+        tma_load_2d(st + kATileBytes * (DUAL ? 2 : 1), &tmap_x, &full_bar[s], kc, row_base, kEvictLast);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================== MMA issuer (single thread)
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + kATileBytes * (DUAL ? 2 : 1);
+        const uint64_t adesc = umma_desc_sw128(a_addr);
+        const uint64_t bdesc = umma_desc_sw128(b_addr);
+#pragma unroll
+        for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
+          const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
+          // advancing 16 bf16 (32 B) along K inside the swizzle atom = +2 in the (addr >> 4) field
+          umma_f16(tmem_base, adesc + 2 * kk, bdesc + 2 * kk, IDESC, acc);
+          if (DUAL) {
+            const uint64_t a2desc = umma_desc_sw128(a_addr + kATileBytes);
+            umma_f16(tmem_base + BN, a2desc + 2 * kk, bdesc + 2 * kk, IDESC, acc);
+          }
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete (fires immediately if num_kb == 0)
+    }
+  } else {
+    // ============================================================== epilogue warps (128 threads)
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int f_local = q * 32 + lane;  // feature within the tile == TMEM lane
+    const int f_glob = n0 + f_local;
+    const int et = threadIdx.x - 64;    // 0..127
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+    bool do_epilogue = true;
+    if (p.splits > 1) {
+      // ---- write the raw fp32 partial, take a ticket, the last arriver reduces
+      float* ws = p.workspace + (static_cast<size_t>((blockIdx.y * gridDim.x + blockIdx.x) * (gridDim.z / p.splits) + mt) *
+                                 p.splits + split) * (BN * (DUAL ? 2 : 1) * kTileM);
+#pragma unroll 1
+      for (int c = 0; c < BN * (DUAL ? 2 : 1); c += 16) {
+        uint32_t v[16];
+        if (num_kb > 0) {
+          tmem_ld16(taddr + c, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) ws[(c + j) * kTileM + f_local] = __uint_as_float(v[j]);
+      }
+      __threadfence();
+      named_bar_sync(1, kEpiThreads);
+      if (et == 0) {
+        unsigned int* ctr = p.tile_counters + ((blockIdx.y * gridDim.x + blockIdx.x) * (gridDim.z / p.splits) + mt);
+        const unsigned int old = atomicAdd(ctr, 1u);
+        const bool last = (old == static_cast<unsigned int>(p.splits - 1));
+        if (last) *ctr = 0u;  // self-reset for the next launch
+        *flag_smem = last ? 1u : 0u;
+      }
+      named_bar_sync(1, kEpiThreads);
+      do_epilogue = (*flag_smem != 0u);
+      if (do_epilogue) __threadfence();
+    }
+
+    if (do_epilogue) {
+      OutT* stg = reinterpret_cast<OutT*>(smem);  // aliases the idle stage ring: [BN][128]
+      const float bias = (p.bias != nullptr && f_glob < p.n) ? __bfloat162float(p.bias[f_glob]) : 0.0f;
+      const float* ws0 = nullptr;
+      if (p.splits > 1)
+        ws0 = p.workspace + static_cast<size_t>((blockIdx.y * gridDim.x + blockIdx.x) * (gridDim.z / p.splits) + mt) *
+                                p.splits * (BN * (DUAL ? 2 : 1) * kTileM);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        if (c >= rows_valid) break;
+        float g[16], u[16];
+        if (p.splits > 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { g[j] = 0.f; u[j] = 0.f; }
+          for (int s = 0; s < p.splits; ++s) {
+            const float* w = ws0 + static_cast<size_t>(s) * (BN * (DUAL ? 2 : 1) * kTileM);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              g[j] += __ldcg(&w[(c + j) * kTileM + f_local]);
+              if (DUAL) u[j] += __ldcg(&w[(BN + c + j) * kTileM + f_local]);
+            }
+          }
+        } else {
+          uint32_t v[16];
+          tmem_ld16(taddr + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) g[j] = __uint_as_float(v[j]);
+          if (DUAL) {
+            tmem_ld16(taddr + BN + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) u[j] = __uint_as_float(v[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float y = g[j] + bias;
+          if (DUAL) y = apply_act(p.act, y) * u[j];
+          if (p.softcap > 0.f) y = p.softcap * tanhf(y / p.softcap);
+          stage_store<OutT>(&stg[(c + j) * kTileM + f_local], y);
+        }
+      }
+      tc_fence_before();
+      named_bar_sync(1, kEpiThreads);
+      // ---- coalesced write-out: each token row of the tile is 128 features = 16 chunks of 8 elements
+      constexpr int kVec = 8;
+      constexpr int kChunks = kTileM / kVec;                  // 16
+      constexpr int kRowsPerIter = kEpiThreads / kChunks;     // 8
+      const int ch = et % kChunks;
+      const int f0 = n0 + ch * kVec;
+      if (f0 < p.n) {
+        for (int r = et / kChunks; r < rows_valid; r += kRowsPerIter) {
+          const size_t row = static_cast<size_t>(row_base + r);
+          float vals[kVec];
+          if (sizeof(OutT) == 2) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(stg) + r * kTileM + ch * kVec);
+            const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { vals[2 * j] = bf16_lo(w4[j]); vals[2 * j + 1] = bf16_hi(w4[j]); }
+          } else {
+            const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(stg) + r * kTileM + ch * kVec);
+            const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(stg) + r * kTileM + ch * kVec + 4);
+            vals[0] = a.x; vals[1] = a.y; vals[2] = a.z; vals[3] = a.w;
+            vals[4] = b.x; vals[5] = b.y; vals[6] = b.z; vals[7] = b.w;
+          }
+          if (p.residual != nullptr) {
+            const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + row * p.ld_res + f0);
+            const uint32_t w4[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { vals[2 * j] += bf16_lo(w4[j]); vals[2 * j + 1] += bf16_hi(w4[j]); }
+          }
+          if (sizeof(OutT) == 2) {
+            uint4 o;
+            o.x = pack_bf16(vals[0], vals[1]); o.y = pack_bf16(vals[2], vals[3]);
+            o.z = pack_bf16(vals[4], vals[5]); o.w = pack_bf16(vals[6], vals[7]);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ld_out + f0) = o;
+          } else {
+            float* o = reinterpret_cast<float*>(p.out) + row * p.ld_out + f0;
+            *reinterpret_cast<float4*>(o) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(vals[4], vals[5], vals[6], vals[7]);
+          }
+        }
+      }
+    }
+    // ---- fused stage boundary: publish "tile stored" and let the last CTA raise the peer's flag
+    if (p.signal_flag != nullptr) {
+      __threadfence_system();
+      named_bar_sync(1, kEpiThreads);
+      if (et == 0 && do_epilogue) {
+        const unsigned int done = atomicAdd(p.done_counter, 1u) + 1u;
+        if (done == p.signal_tiles) {
+          *p.done_counter = 0u;
+          __threadfence_system();
+          st_release_sys(p.signal_flag, p.signal_value);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ================================================================================================ host side
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// bf16 row-major [rows, cols] (row stride ld elements) -> tiles of box_rows x 64 with 128B swizzle
+bool make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {kBlockK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BN, bool DUAL, typename OutT>
+cudaError_t launch_one(const GemmArgs& a, const CUtensorMap& tw, const CUtensorMap& tw2, const CUtensorMap& tx,
+                       const GemmParams& p, dim3 grid, cudaStream_t stream) {
+  constexpr int STAGES = num_stages(BN, DUAL, sizeof(OutT));
+  constexpr int smem = STAGES * stage_bytes(BN, DUAL) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
+  auto kern = gemm_swapab_kernel<BN, DUAL, OutT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<grid, kNumThreads, smem, stream>>>(tw, tw2, tx, p);
+  return cudaGetLastError();
+}
+
+template <bool DUAL, typename OutT>
+cudaError_t dispatch_bn(int bn, const GemmArgs& a, const CUtensorMap& tw, const CUtensorMap& tw2, const CUtensorMap& tx,
+                        const GemmParams& p, dim3 grid, cudaStream_t s) {
+  switch (bn) {
+    case 16: return launch_one<16, DUAL, OutT>(a, tw, tw2, tx, p, grid, s);
+    case 32: return launch_one<32, DUAL, OutT>(a, tw, tw2, tx, p, grid, s);
+    case 64: return launch_one<64, DUAL, OutT>(a, tw, tw2, tx, p, grid, s);
+    case 128: return launch_one<128, DUAL, OutT>(a, tw, tw2, tx, p, grid, s);
+    case 256: return launch_one<256, DUAL, OutT>(a, tw, tw2, tx, p, grid, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace
+
+int gemm_pick_bn(int max_rows) {
+  if (max_rows <= 16) return 16;
+  if (max_rows <= 32) return 32;
+  if (max_rows <= 64) return 64;
+  if (max_rows <= 128) return 128;
+  return 256;
+}
+
+size_t gemm_workspace_floats(const GemmArgs& a, int bn, int splits) {
+  if (splits <= 1) return 0;
+  const size_t tiles_n = (a.n + kTileM - 1) / kTileM;
+  const size_t tiles_m = (a.max_rows + bn - 1) / bn;
+  return tiles_n * (a.num_experts > 0 ? a.num_experts : 1) * tiles_m * splits * (size_t)bn * (a.w2 ? 2 : 1) * kTileM;
+}
+
+cudaError_t gemm_launch(const GemmArgs& a, cudaStream_t stream) {
+  const bool dual = a.w2 != nullptr;
+  const bool grouped = a.expert_offsets != nullptr;
+  const int bn = a.bn > 0 ? a.bn : gemm_pick_bn(a.max_rows);
+  int splits = a.splits > 0 ? a.splits : 1;
+  const int kb_total = (a.k + kBlockK - 1) / kBlockK;
+  if (splits > kb_total) splits = kb_total;
+  if (grouped && (a.n % kTileM) != 0) return cudaErrorInvalidValue;
+  if ((a.k % 8) != 0 || (a.n % 8) != 0) return cudaErrorInvalidValue;
+  if (splits > 1 && (a.workspace == nullptr || a.tile_counters == nullptr)) return cudaErrorInvalidValue;
+  if (dual && a.out_fp32) return cudaErrorInvalidValue;
+
+  CUtensorMap tw, tw2, tx;
+  const uint64_t w_rows = static_cast<uint64_t>(a.n) * (grouped ? a.num_experts : 1);
+  if (!make_tmap(&tw, a.w, w_rows, a.k, a.ld_w, kTileM)) return cudaErrorUnknown;
+  if (dual) {
+    if (!make_tmap(&tw2, a.w2, w_rows, a.k, a.ld_w, kTileM)) return cudaErrorUnknown;
+  } else {
+    tw2 = tw;
+  }
+  if (!make_tmap(&tx, a.x, a.x_rows, a.k, a.ld_x, bn)) return cudaErrorUnknown;
+
+  GemmParams p;
+  p.m = a.m; p.n = a.n; p.k = a.k; p.splits = splits;
+  p.expert_offsets = a.expert_offsets;
+  p.out = a.out; p.ld_out = a.ld_out;
+  p.residual = static_cast<const __nv_bfloat16*>(a.residual); p.ld_res = a.ld_res;
+  p.bias = static_cast<const __nv_bfloat16*>(a.bias); p.act = a.act; p.softcap = a.softcap;
+  p.workspace = a.workspace; p.tile_counters = a.tile_counters;
+  p.signal_flag = a.signal_flag; p.signal_value = a.signal_value; p.done_counter = a.done_counter;
+
+  const int tiles_n = (a.n + kTileM - 1) / kTileM;
+  const int tiles_m = (a.max_rows + bn - 1) / bn;
+  dim3 grid(tiles_n, grouped ? a.num_experts : 1, tiles_m * splits);
+  // tiles that run the epilogue (= tiles that will tick done_counter); for grouped launches the caller
+  // passes the exact count (empty experts exit early)
+  p.signal_tiles = a.signal_tiles > 0 ? a.signal_tiles : static_cast<unsigned int>(tiles_n * tiles_m);
+
+  if (a.out_fp32) return dispatch_bn<false, float>(bn, a, tw, tw2, tx, p, grid, stream);
+  if (dual) return dispatch_bn<true, __nv_bfloat16>(bn, a, tw, tw2, tx, p, grid, stream);
+  return dispatch_bn<false, __nv_bfloat16>(bn, a, tw, tw2, tx, p, grid, stream);
+}
+
+}  // namespace b200

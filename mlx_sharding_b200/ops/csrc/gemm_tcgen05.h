@@ -1,0 +1,65 @@
+// Host API of the swap-AB tcgen05 GEMM (see gemm_tcgen05.cu).  Plain CUDA, no torch dependency.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace b200 {
+
+enum : int { kActNone = 0, kActSilu = 1, kActGeluTanh = 2 };
+
+// Device-side parameter block (passed by value).
+struct GemmParams {
+  int m, n, k, splits;
+  const int* expert_offsets;
+  void* out;
+  long long ld_out;
+  const __nv_bfloat16* residual;
+  long long ld_res;
+  const __nv_bfloat16* bias;
+  int act;
+  float softcap;
+  float* workspace;
+  unsigned int* tile_counters;
+  uint32_t* signal_flag;
+  uint32_t signal_value;
+  unsigned int* done_counter;
+  unsigned int signal_tiles;
+};
+
+// Host-side launch description.  Y[rows, n] = X[rows, k] * W[n, k]^T, bf16 in, fp32 accumulate.
+struct GemmArgs {
+  const void* x = nullptr;        // bf16 [x_rows, k], row stride ld_x
+  long long x_rows = 0, ld_x = 0;
+  const void* w = nullptr;        // bf16 [(num_experts *) n, k], row stride ld_w
+  const void* w2 = nullptr;       // optional second weight (gate/up pair): out = act(x w^T) * (x w2^T)
+  long long ld_w = 0;
+  int m = 0;                      // rows when not grouped
+  int n = 0, k = 0;
+  int max_rows = 0;               // upper bound of rows per (expert) problem: sizes the grid
+  int num_experts = 0;            // grouped: number of experts
+  const int* expert_offsets = nullptr;  // grouped: int32 [num_experts + 1] row offsets into x / out (device)
+  void* out = nullptr;            // bf16 (or fp32 if out_fp32) [rows, n], row stride ld_out; may be a peer pointer
+  long long ld_out = 0;
+  bool out_fp32 = false;
+  const void* residual = nullptr; // bf16 [rows, n] added in the epilogue
+  long long ld_res = 0;
+  const void* bias = nullptr;     // bf16 [n]
+  int act = kActNone;             // used with w2
+  float softcap = 0.f;            // y = cap * tanh(y / cap) (Gemma-2 final logits)
+  int bn = 0;                     // token tile (0 = auto)
+  int splits = 1;                 // split-K factor
+  float* workspace = nullptr;     // fp32, gemm_workspace_floats() elements when splits > 1
+  unsigned int* tile_counters = nullptr;  // zero-initialised, >= number of output tiles
+  uint32_t* signal_flag = nullptr;        // fused stage boundary: raised (release.sys) when every tile is stored
+  uint32_t signal_value = 0;
+  unsigned int* done_counter = nullptr;   // zero-initialised device counter
+  unsigned int signal_tiles = 0;          // 0 = all tiles of the grid
+};
+
+int gemm_pick_bn(int max_rows);
+size_t gemm_workspace_floats(const GemmArgs& a, int bn, int splits);
+cudaError_t gemm_launch(const GemmArgs& a, cudaStream_t stream);
+
+}  // namespace b200

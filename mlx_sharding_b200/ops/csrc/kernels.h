@@ -1,0 +1,67 @@
+// Host launch API of the non-GEMM sm_100a kernels (plain CUDA; the torch binding lives in bindings.cpp).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+// ---- elementwise.cu
+cudaError_t rmsnorm_launch(const void* x, long long ld_x, const void* w, const void* residual, long long ld_res,
+                           void* out, long long ld_out, int rows, int H, float eps, bool gemma, cudaStream_t s);
+cudaError_t rope_launch(void* x, long long ld_t, long long ld_h, int heads, const int* positions, const float* inv_freq,
+                        int rot_off, int rot_dim, bool interleaved, float mscale, int T, cudaStream_t s);
+cudaError_t embed_launch(const long long* ids, const void* table, const void* scales, const void* biases, int bits, int group,
+                         void* out, int H, float scale, int T, cudaStream_t s);
+cudaError_t kv_write_launch(const void* k, long long k_ld_t, long long k_ld_h, const void* v, long long v_ld_t,
+                            long long v_ld_h, void* kpool, void* vpool, const int* slots, int heads, int dk, int dv,
+                            int page, int T, cudaStream_t s);
+cudaError_t kv_write_mla_launch(const void* kv, long long kv_ld_t, const void* kpe, long long pe_ld_t, void* kpool,
+                                void* vpool, const int* slots, int heads, int nope, int rd, int vd, int page, int T,
+                                cudaStream_t s);
+
+// ---- attention.cu
+struct PagedAttnArgs {
+  const void* q; long long q_ld_t, q_ld_h;       // bf16 [T, q_heads, dk]
+  const void* kpool; const void* vpool;          // bf16 [pages, kv_heads, page, dk|dv]
+  const int* block_tables; int max_blocks;       // int32 [num_seqs, max_blocks]
+  const int* positions;                          // int32 [T]   causal limit = position + 1
+  const int* token_seq;                          // int32 [T]   sequence (block-table row) of each token
+  int T, q_heads, kv_heads, dk_, dv_, page;
+  float scale, softcap;
+  int nsplit;                                    // KV splits (1 = write output directly)
+  void* out; long long o_ld_t;                   // bf16 [T, q_heads * dv]
+  float* part_acc; float* part_ml;               // split workspaces: [T*Hq*nsplit*dv], [T*Hq*nsplit*2]
+};
+cudaError_t paged_attention_launch(const PagedAttnArgs& a, cudaStream_t s);
+
+// ---- moe.cu
+// router: fp32 softmax(x W^T) -> top-k (optionally group limited) -> weights * scaling (or normalised)
+cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, int T, int H, int E, int top_k,
+                             int n_group, int topk_group, float scaling, bool norm_topk, int* idx, float* wts,
+                             cudaStream_t s);
+// permutation: counts/offsets per expert, destination row of every (token, k) pair, gathered rows
+cudaError_t moe_permute_launch(const int* idx, int T, int top_k, int E, int* expert_offsets /*E+1*/, int* pair_row /*T*k*/,
+                               int* counters /*E scratch*/, const void* x, long long ld_x, void* x_perm, int H,
+                               cudaStream_t s);
+// y[t] = sum_k w[t,k] * y_perm[pair_row[t,k]] (+ residual[t]); out may be a peer pointer; optional release flag
+cudaError_t moe_combine_launch(const void* y_perm, const int* pair_row, const float* wts, const void* residual,
+                               long long ld_res, void* out, long long ld_out, int T, int top_k, int H,
+                               uint32_t* signal_flag, uint32_t signal_value, unsigned int* done_counter, cudaStream_t s);
+
+// ---- sampler.cu
+cudaError_t apply_penalties_launch(float* logits, int B, int V, const int* rep_ctx, int C, const float* penalty,
+                                   const int* bias_idx, const float* bias_val, int NB, cudaStream_t s);
+// tokens/logprob per row; temperature==0 -> argmax, top_p in (0,1) -> nucleus; Philox-style counter RNG
+cudaError_t sample_launch(const float* logits, int B, int V, const float* temperature, const float* top_p,
+                          unsigned long long seed, unsigned long long step, long long* tokens, float* logprobs, int top_k,
+                          long long* top_ids, float* top_lp, cudaStream_t s);
+
+// ---- p2p.cu
+cudaError_t wait_flag_launch(const uint32_t* flag, uint32_t expected, uint32_t* error_flag, cudaStream_t s);
+cudaError_t set_flag_launch(uint32_t* flag, uint32_t value, cudaStream_t s);
+cudaError_t copy_signal_launch(const void* src, void* dst, size_t bytes, uint32_t* flag, uint32_t value, cudaStream_t s);
+cudaError_t advance_meta_launch(int* positions, int* context_lens, int* slots, const int* block_tables, int max_blocks,
+                                int page, int B, cudaStream_t s);
+
+}  // namespace b200

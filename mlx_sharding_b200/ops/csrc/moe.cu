@@ -1,0 +1,294 @@
+// DeepSeek-V2 MoE support kernels: router (fp32 softmax + greedy / group-limited
+// top-k), token permutation for the grouped GEMM, and the weighted combine fused with the residual and
+// — on the last layer of a stage — with the P2P hand-off flag.  The reference gets this from
+// mlx_lm's MoEGate + SwitchGLU (`mx.gather_qmm`, `(y * scores[..., None]).sum(-2)`); nothing is ported.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int kRouteToks = 8;       // tokens per CTA (share every router-weight read)
+constexpr int kRouteThreads = 256;  // 8 warps
+constexpr int kMaxEPerLane = 8;     // E <= 256
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// argmax with lowest-index tie-break
+__device__ __forceinline__ void warp_argmax(float& v, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+
+__global__ void __launch_bounds__(kRouteThreads)
+moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv_bfloat16* __restrict__ gw, int T, int H,
+                 int E, int top_k, int n_group, int topk_group, float scaling, int norm_topk, int* __restrict__ idx,
+                 float* __restrict__ wts) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem);                 // [kRouteToks][H]
+  float* logits = reinterpret_cast<float*>(smem + (size_t)kRouteToks * H * 2);  // [kRouteToks][E]
+  const int t0 = blockIdx.x * kRouteToks;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = H / 8;
+  for (int i = threadIdx.x; i < kRouteToks * nvec; i += kRouteThreads) {
+    const int tk = i / nvec, v = i % nvec;
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (t0 + tk < T) r = reinterpret_cast<const uint4*>(x + (size_t)(t0 + tk) * ld_x)[v];
+    reinterpret_cast<uint4*>(xs + (size_t)tk * H)[v] = r;
+  }
+  __syncthreads();
+  for (int e = warp; e < E; e += kRouteThreads / 32) {
+    float acc[kRouteToks];
+#pragma unroll
+    for (int k = 0; k < kRouteToks; ++k) acc[k] = 0.f;
+    const uint4* wr = reinterpret_cast<const uint4*>(gw + (size_t)e * H);
+    for (int v = lane; v < nvec; v += 32) {
+      const uint4 w4 = wr[v];
+      const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int k = 0; k < kRouteToks; ++k) {
+        const uint4 x4 = reinterpret_cast<const uint4*>(xs + (size_t)k * H)[v];
+        const uint32_t xx[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[k] += bf16_lo(xx[j]) * bf16_lo(ww[j]);
+          acc[k] += bf16_hi(xx[j]) * bf16_hi(ww[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kRouteToks; ++k) {
+      const float s = warp_sum(acc[k]);
+      if (lane == 0) logits[k * E + e] = s;
+    }
+  }
+  __syncthreads();
+  // ---- one warp per token: softmax, (group mask), top-k
+  const int tk = warp;
+  const int t = t0 + tk;
+  if (t >= T) return;
+  float sc[kMaxEPerLane], sel[kMaxEPerLane];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kMaxEPerLane; ++j) {
+    const int e = lane + 32 * j;
+    sc[j] = (e < E) ? logits[tk * E + e] : -INFINITY;
+    mx = fmaxf(mx, sc[j]);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxEPerLane; ++j) {
+    const int e = lane + 32 * j;
+    sc[j] = (e < E) ? __expf(sc[j] - mx) : 0.f;
+    sum += sc[j];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int j = 0; j < kMaxEPerLane; ++j) {
+    const int e = lane + 32 * j;
+    sc[j] *= inv;
+    sel[j] = (e < E) ? sc[j] : -1.0f;
+  }
+  if (n_group > 1 && topk_group < n_group) {
+    const int gsz = E / n_group;
+    // group id of each owned expert; choose topk_group groups by their max score
+    unsigned chosen = 0u;  // bitmask over groups (n_group <= 32)
+    for (int r = 0; r < topk_group; ++r) {
+      float best = -1.0f;
+      int bg = 0x7fffffff;
+#pragma unroll
+      for (int j = 0; j < kMaxEPerLane; ++j) {
+        const int e = lane + 32 * j;
+        if (e < E) {
+          const int g = e / gsz;
+          if (!((chosen >> g) & 1u) && (sc[j] > best || (sc[j] == best && g < bg))) { best = sc[j]; bg = g; }
+        }
+      }
+      warp_argmax(best, bg);
+      chosen |= (1u << bg);
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxEPerLane; ++j) {
+      const int e = lane + 32 * j;
+      if (e < E && !((chosen >> (e / gsz)) & 1u)) sel[j] = 0.0f;
+    }
+  }
+  float wsum = 0.f;
+  float my_w = 0.f;
+  int my_i = 0;
+  for (int r = 0; r < top_k; ++r) {
+    float best = -2.0f;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < kMaxEPerLane; ++j) {
+      const int e = lane + 32 * j;
+      if (e < E && (sel[j] > best || (sel[j] == best && e < bi))) { best = sel[j]; bi = e; }
+    }
+    warp_argmax(best, bi);
+    // fetch the un-masked score of the winner from its owner lane
+    float wv = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxEPerLane; ++j)
+      if (lane + 32 * j == bi) { wv = sc[j]; sel[j] = -1.0f; }
+    wv = __shfl_sync(0xffffffffu, wv, bi & 31);
+    wsum += wv;
+    if (lane == r) { my_w = wv; my_i = bi; }
+  }
+  if (lane < top_k) {
+    const float w = (norm_topk && top_k > 1) ? my_w / (wsum + 1e-20f) : my_w * scaling;
+    idx[(size_t)t * top_k + lane] = my_i;
+    wts[(size_t)t * top_k + lane] = w;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ permutation
+__global__ void __launch_bounds__(1024)
+moe_offsets_kernel(const int* __restrict__ idx, int npairs, int E, int* __restrict__ expert_offsets,
+                   int* __restrict__ pair_row) {
+  __shared__ int cnt[256], cur[256];
+  for (int e = threadIdx.x; e < E; e += blockDim.x) cnt[e] = 0;
+  __syncthreads();
+  for (int p = threadIdx.x; p < npairs; p += blockDim.x) atomicAdd(&cnt[idx[p]], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int e = 0; e < E; ++e) { cur[e] = acc; expert_offsets[e] = acc; acc += cnt[e]; }
+    expert_offsets[E] = acc;
+  }
+  __syncthreads();
+  // deterministic placement: pairs of one expert keep their (token, k) order.  One warp per expert scans
+  // the pair list with ballots — npairs is small in decode and this stays off the critical path in prefill.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int e = warp; e < E; e += nwarps) {
+    if (cnt[e] == 0) continue;
+    int base = cur[e];
+    for (int p0 = 0; p0 < npairs; p0 += 32) {
+      const int p = p0 + lane;
+      const bool mine = (p < npairs) && (idx[p] == e);
+      const unsigned bal = __ballot_sync(0xffffffffu, mine);
+      if (mine) pair_row[p] = base + __popc(bal & ((1u << lane) - 1u));
+      base += __popc(bal);
+    }
+  }
+}
+
+__global__ void moe_gather_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const int* __restrict__ pair_row,
+                                  __nv_bfloat16* __restrict__ x_perm, int H, int top_k, long long total) {
+  const int nvec = H / 8;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int v = i % nvec;
+  const long long p = i / nvec;
+  const int t = p / top_k;
+  reinterpret_cast<uint4*>(x_perm + (size_t)pair_row[p] * H)[v] =
+      reinterpret_cast<const uint4*>(x + (size_t)t * ld_x)[v];
+}
+
+// ------------------------------------------------------------------------------------------------ combine
+__global__ void moe_combine_kernel(const float* __restrict__ y_perm, const int* __restrict__ pair_row,
+                                   const float* __restrict__ wts, const __nv_bfloat16* __restrict__ residual,
+                                   long long ld_res, __nv_bfloat16* __restrict__ out, long long ld_out, int T, int top_k,
+                                   int H, uint32_t* signal_flag, uint32_t signal_value, unsigned int* done_counter) {
+  const int nvec = H / 8;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < (long long)T * nvec) {
+    const int v = i % nvec;
+    const int t = i / nvec;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int k = 0; k < top_k; ++k) {
+      const float w = wts[(size_t)t * top_k + k];
+      const float* src = y_perm + (size_t)pair_row[(size_t)t * top_k + k] * H + v * 8;
+      const float4 a = *reinterpret_cast<const float4*>(src);
+      const float4 b = *reinterpret_cast<const float4*>(src + 4);
+      acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
+      acc[4] += w * b.x; acc[5] += w * b.y; acc[6] += w * b.z; acc[7] += w * b.w;
+    }
+    if (residual != nullptr) {
+      const uint4 r = reinterpret_cast<const uint4*>(residual + (size_t)t * ld_res)[v];
+      const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { acc[2 * j] += bf16_lo(rr[j]); acc[2 * j + 1] += bf16_hi(rr[j]); }
+    }
+    uint4 o;
+    o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+    o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+    reinterpret_cast<uint4*>(out + (size_t)t * ld_out)[v] = o;
+  }
+  if (signal_flag != nullptr) {
+    // fused stage boundary: `out` is the next stage's inbox (peer memory); the last CTA raises the flag
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int done = atomicAdd(done_counter, 1u) + 1u;
+      if (done == gridDim.x) {
+        *done_counter = 0u;
+        __threadfence_system();
+        st_release_sys(signal_flag, signal_value);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, int T, int H, int E, int top_k, int n_group,
+                             int topk_group, float scaling, bool norm_topk, int* idx, float* wts, cudaStream_t s) {
+  if (T == 0) return cudaSuccess;
+  if (E > 32 * kMaxEPerLane || top_k > 32 || (H % 8) || n_group > 32 || (n_group > 1 && E % n_group)) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)kRouteToks * H * 2 + (size_t)kRouteToks * E * 4;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(moe_route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  moe_route_kernel<<<(T + kRouteToks - 1) / kRouteToks, kRouteThreads, smem, s>>>(
+      static_cast<const __nv_bfloat16*>(x), ld_x, static_cast<const __nv_bfloat16*>(gate_w), T, H, E, top_k, n_group,
+      topk_group, scaling, norm_topk ? 1 : 0, idx, wts);
+  return cudaGetLastError();
+}
+
+cudaError_t moe_permute_launch(const int* idx, int T, int top_k, int E, int* expert_offsets, int* pair_row, int* counters,
+                               const void* x, long long ld_x, void* x_perm, int H, cudaStream_t s) {
+  (void)counters;
+  if (T == 0) return cudaSuccess;
+  if (E > 256 || (H % 8)) return cudaErrorInvalidValue;
+  moe_offsets_kernel<<<1, 1024, 0, s>>>(idx, T * top_k, E, expert_offsets, pair_row);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const long long total = (long long)T * top_k * (H / 8);
+  moe_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ld_x, pair_row,
+                                                                    static_cast<__nv_bfloat16*>(x_perm), H, top_k, total);
+  return cudaGetLastError();
+}
+
+cudaError_t moe_combine_launch(const void* y_perm, const int* pair_row, const float* wts, const void* residual,
+                               long long ld_res, void* out, long long ld_out, int T, int top_k, int H,
+                               uint32_t* signal_flag, uint32_t signal_value, unsigned int* done_counter, cudaStream_t s) {
+  if (T == 0) return cudaSuccess;
+  if (H % 8) return cudaErrorInvalidValue;
+  const long long total = (long long)T * (H / 8);
+  moe_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+      static_cast<const float*>(y_perm), pair_row, wts, static_cast<const __nv_bfloat16*>(residual), ld_res,
+      static_cast<__nv_bfloat16*>(out), ld_out, T, top_k, H, signal_flag, signal_value, done_counter);
+  return cudaGetLastError();
+}
+
+}  // namespace b200
