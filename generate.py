@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""Greedy CLI generator that drives a sharded model (reference ``generate.py``).
+
+Same flags as the reference (``generate.py:12-20``): ``--model`` (the first shard), ``--prompt``,
+``--max_tokens`` (512), ``--server_address`` (comma list of the remaining stages, in pipeline order),
+``--start_layer`` / ``--end_layer``.  Differences: remote stages are optional (a single process holding
+every layer works — the reference raises without at least one stub, generate.py:72-80); under
+``torchrun`` the remaining stages are the other ranks (native chain, no gRPC).
+
+Prints the generated text as it streams, then ``Prompt: X tokens-per-sec`` and
+``Generation: Y tokens-per-sec`` like the reference (generate.py:114-122).
+"""
+import argparse
+import os
+import sys
+import time
+
+from mlx_sharding_b200.engine.core import LLMEngine
+from mlx_sharding_b200.engine.sampler import SamplingParams
+from mlx_sharding_b200.engine.tokenizer import load_tokenizer
+
+
+def build_engine(model, server_address, num_pages=None, page_size=64):
+    from mlx_sharding_b200.parallel.pipeline import ChainPipeline, LocalPipeline, StageExecutor
+
+    num_pages = num_pages or 1024
+    stage = StageExecutor(model, num_pages, page_size)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        from mlx_sharding_b200.parallel.transport import TorchDistTransport
+
+        return LLMEngine(ChainPipeline(stage, TorchDistTransport(model.device)), num_pages, page_size, num_groups=1)
+    if not model.spec.is_last:
+        from mlx_sharding_b200.parallel.grpc_compat import GrpcRelayPipeline, connect_stubs
+
+        stubs = connect_stubs(server_address)
+        if not stubs:
+            raise ValueError("No gRPC stubs provided but the local model does not hold the last layer")
+        for s in stubs:
+            s.reset_cache()
+        return LLMEngine(GrpcRelayPipeline(stage, stubs), num_pages, page_size, num_groups=1, max_seqs_per_group=1)
+    return LLMEngine(LocalPipeline([stage]), num_pages, page_size, num_groups=1)
+
+
+def stream_generate(engine, tokenizer, prompt: str, max_tokens: int):
+    """Yield text segments; prints prompt / generation tokens-per-sec at the end (reference :90-122)."""
+    ids = tokenizer.encode(prompt)
+    detok = tokenizer.new_detokenizer()
+    tic = time.perf_counter()
+    req = engine.submit(ids, SamplingParams(temperature=0.0), max_tokens=max_tokens,
+                        eos_token_id=tokenizer.eos_token_id)
+    n, prompt_time = 0, None
+    while not req.finished:
+        engine.step()
+        while not req.events.empty():
+            ev = req.events.get()
+            if ev is None or ev.token < 0:
+                break
+            if n == 0:
+                prompt_time = time.perf_counter() - tic
+                tic = time.perf_counter()
+            n += 1
+            if ev.finished and ev.finish_reason == "stop":
+                break
+            detok.add_token(ev.token)
+            yield detok.last_segment
+    if req.error:
+        raise req.error
+    detok.finalize()
+    yield detok.last_segment
+    gen_time = time.perf_counter() - tic
+    print("\n" + "=" * 10)
+    if n == 0:
+        print("No tokens generated for this prompt")
+        return
+    print(f"Prompt: {len(ids) / max(prompt_time, 1e-9):.3f} tokens-per-sec")
+    print(f"Generation: {(n - 1) / max(gen_time, 1e-9):.3f} tokens-per-sec")
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser(description="Generate text with a sharded model")
+    parser.add_argument("--model", type=str, default="shard_0", help="Path to the (first shard of the) model")
+    parser.add_argument("--prompt", type=str, default="Hello, how are you?", help="Input prompt")
+    parser.add_argument("--max_tokens", type=int, default=512, help="Maximum number of tokens to generate")
+    parser.add_argument("--server_address", type=str, default="localhost:50051",
+                        help="Comma-separated addresses of the remaining pipeline stages")
+    parser.add_argument("--start_layer", type=int, default=None, help="Start layer index")
+    parser.add_argument("--end_layer", type=int, default=None, help="End layer index")
+    parser.add_argument("--device", type=str, default=None)
+    parser.add_argument("--no_chat_template", action="store_true", help="feed the raw prompt")
+    args = parser.parse_args(argv)
+
+    from mlx_sharding_b200.utils.checkpoint import get_model_path
+    from mlx_sharding_b200.utils.loader import load_model
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        from mlx_sharding_b200.parallel.transport import init_distributed
+
+        rank, _ = init_distributed(device=args.device)
+        if rank != 0:
+            from mlx_sharding_b200.server.shard_server import serve_chain
+
+            return serve_chain(args.model, args.start_layer, args.end_layer, args.device)
+        if args.start_layer is None and args.end_layer is None:
+            from mlx_sharding_b200.config import ModelConfig, ShardSpec
+
+            cfg = ModelConfig.from_path(get_model_path(args.model))
+            if cfg.start_layer is None:
+                spec = ShardSpec.even_split(cfg.num_hidden_layers, world)[0]
+                args.start_layer, args.end_layer = spec.start_layer, spec.end_layer
+    tokenizer = load_tokenizer(get_model_path(args.model))
+    model = load_model(args.model, args.start_layer, args.end_layer, device=args.device)
+    prompt = args.prompt
+    if not args.no_chat_template and getattr(tokenizer, "chat_template", None):
+        prompt = tokenizer.apply_chat_template([{"role": "user", "content": args.prompt}], tokenize=False,
+                                               add_generation_prompt=True)
+    engine = build_engine(model, args.server_address)
+    for seg in stream_generate(engine, tokenizer, prompt, args.max_tokens):
+        print(seg, end="", flush=True)
+    if hasattr(engine.pipe, "shutdown"):
+        engine.pipe.shutdown()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

@@ -1,0 +1,177 @@
+"""``b200`` op backend: the hand-written sm_100a kernels behind the same API as ``ops.reference``.
+
+Loading is strict: if the extension is missing (or is not loadable) on a box with a GPU this raises —
+there is no silent PyTorch fallback on the hot path.  The only non-kernel code here is argument
+plumbing (views, dtype checks) and the token->sequence map derived from the step metadata.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+from typing import Optional, Tuple
+
+import torch
+
+from .meta import BatchMeta
+from .weights import LinearWeight, RopeSpec
+
+NAME = "b200"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_b200_C.so")
+_C = None
+
+ACT_IDS = {"none": 0, "silu": 1, "gelu_tanh": 2, "gelu_pytorch_tanh": 2, "gelu_approx": 2}
+
+
+def load_extension(build_if_missing: bool = False):
+    """Import the in-tree ``_b200_C.so`` (optionally building it first with ``ops/build.py``)."""
+    global _C
+    if _C is not None:
+        return _C
+    if not os.path.exists(_SO):
+        if build_if_missing:
+            from .build import build
+
+            build()
+        else:
+            raise ImportError(
+                f"{_SO} not found: build the sm_100a extension with `python -m mlx_sharding_b200.ops.build` "
+                "(or __graft_entry__.build())")
+    spec = importlib.util.spec_from_file_location("_b200_C", _SO)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _C = mod
+    return _C
+
+
+def C():
+    return load_extension()
+
+
+def is_available() -> bool:
+    return os.path.exists(_SO) and torch.cuda.is_available()
+
+
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.bfloat16:
+        raise TypeError(f"b200 backend runs bf16 activations/weights, got {t.dtype}")
+    return t
+
+
+def _dense(W: LinearWeight) -> torch.Tensor:
+    """bf16 ``[.., N, K]`` view of a weight.  Quantised weights are expanded once at first use
+    (load-time dequant; the int4 payload stays the on-disk format)."""
+    if W.is_quantized:
+        if W.weight is None:
+            W.weight = W.dense(torch.bfloat16).contiguous()
+        return W.weight
+    return _bf16(W.weight)
+
+
+# ------------------------------------------------------------------------------------------------ ops
+def embed(ids: torch.Tensor, emb: LinearWeight, scale: float = 1.0, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    ids = ids.to(torch.int64).contiguous()
+    if emb.is_quantized:
+        return C().embed(ids, emb.wq, emb.scales, emb.biases, emb.bits, emb.group_size, float(scale))
+    return C().embed(ids, _bf16(emb.weight), None, None, 0, 64, float(scale))
+
+
+def rmsnorm(x, w, eps: float, gemma: bool = False, residual: Optional[torch.Tensor] = None):
+    return C().rmsnorm(x, w, float(eps), bool(gemma), residual)
+
+
+def add_rmsnorm(x, residual, w, eps, gemma=False):
+    h = x + residual
+    return rmsnorm(h, w, eps, gemma), h
+
+
+def linear(x: torch.Tensor, W: LinearWeight, residual: Optional[torch.Tensor] = None,
+           out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None,
+           signal: Optional[Tuple[int, int]] = None, softcap: float = 0.0) -> torch.Tensor:
+    fp32 = out_dtype == torch.float32
+    flag, val = signal if signal is not None else (0, 0)
+    return C().linear(x, _dense(W), None, residual, W.bias, 0, float(softcap), fp32, out, 0, int(flag), int(val))
+
+
+def gated_up(x: torch.Tensor, Wg: LinearWeight, Wu: LinearWeight, act: str = "silu") -> torch.Tensor:
+    if Wg.bias is not None or Wu.bias is not None:
+        raise NotImplementedError("gated MLP with bias")
+    return C().linear(x, _dense(Wg), _dense(Wu), None, None, ACT_IDS[act], 0.0, False, None, 0, 0, 0)
+
+
+def rope_(x: torch.Tensor, positions: torch.Tensor, spec: RopeSpec, rot_offset: int = 0) -> torch.Tensor:
+    C().rope_(x, positions, spec.inv_freq, int(rot_offset), int(spec.rot_dim), bool(spec.interleaved), float(spec.mscale))
+    return x
+
+
+def kv_write(k, v, kpool, vpool, slot_mapping):
+    C().kv_write(k, v, kpool, vpool, slot_mapping)
+
+
+def kv_write_mla(kv, k_pe, kpool, vpool, slot_mapping, nope: int, vdim: int):
+    C().kv_write_mla(kv, k_pe, kpool, vpool, slot_mapping, int(nope), int(vdim))
+
+
+def _token_seq(meta: BatchMeta) -> torch.Tensor:
+    ts = getattr(meta, "_token_seq", None)
+    if ts is None:
+        if meta.num_tokens == meta.num_seqs:
+            ts = torch.arange(meta.num_seqs, dtype=torch.int32, device=meta.positions.device)
+        else:
+            lens = (meta.cu_seqlens[1:] - meta.cu_seqlens[:-1]).long()
+            ts = torch.repeat_interleave(torch.arange(meta.num_seqs, device=lens.device), lens).to(torch.int32)
+        meta._token_seq = ts
+    return ts
+
+
+def paged_attention(q, kpool, vpool, meta: BatchMeta, scale: float, softcap: float = 0.0):
+    return C().paged_attention(q, kpool, vpool, meta.block_tables, meta.positions, _token_seq(meta), float(scale),
+                               float(softcap or 0.0), int(meta.max_ctx_len))
+
+
+def moe_route(x, gate_w, top_k: int, method: str = "greedy", n_group: int = 1, topk_group: int = 1,
+              scaling: float = 1.0, norm_topk: bool = False):
+    if method != "group_limited_greedy":
+        n_group, topk_group = 1, 1
+    idx, w = C().moe_route(x, _bf16(gate_w), int(top_k), int(n_group), int(topk_group), float(scaling), bool(norm_topk))
+    return idx, w
+
+
+def moe_experts(x, idx, w, Wg: LinearWeight, Wu: LinearWeight, Wd: LinearWeight, act: str = "silu",
+                extra: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None, signal: Optional[Tuple[int, int]] = None):
+    """router output -> permute -> grouped dual GEMM (act(gate)*up) -> grouped down GEMM (fp32) ->
+    weighted combine (+ residual [+ P2P store & flag])."""
+    c = C()
+    T, k = idx.shape
+    wg, wu, wd = _dense(Wg), _dense(Wu), _dense(Wd)
+    E = wg.shape[0]
+    offs, pair_row, xp = c.moe_permute(idx, x, E)
+    h = c.grouped_linear(xp, wg, wu, offs, T, ACT_IDS[act], False)
+    y = c.grouped_linear(h, wd, None, offs, T, 0, True)
+    if extra is not None:
+        residual = extra if residual is None else residual + extra
+    flag, val = signal if signal is not None else (0, 0)
+    return c.moe_combine(y, pair_row, w, residual, out, int(k), int(flag), int(val))
+
+
+def softcap_(logits, cap: float):
+    return torch.tanh(logits / cap) * cap
+
+
+def apply_penalties_(logits, rep_ctx, penalty, bias_idx, bias_val):
+    C().apply_penalties_(logits, rep_ctx.contiguous(), penalty, bias_idx.contiguous(), bias_val.contiguous())
+    return logits
+
+
+_step = [0]
+
+
+def sample(logits, temperature, top_p, generator: Optional[torch.Generator] = None, top_logprobs: int = 0):
+    seed = generator.initial_seed() if generator is not None else 0
+    _step[0] += 1
+    toks, lp, ti, tl = C().sample(logits.contiguous(), temperature, top_p, int(seed) & 0x7FFFFFFFFFFFFFFF, _step[0],
+                                  int(top_logprobs))
+    if top_logprobs > 0:
+        return toks, lp, ti, tl
+    return toks, lp, None, None

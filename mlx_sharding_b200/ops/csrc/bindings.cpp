@@ -1,0 +1,379 @@
+// PyTorch bindings for the sm_100a kernels.  Everything launches on the current torch CUDA stream so
+// the ops compose with torch.cuda.CUDAGraph capture; scratch buffers are process-lifetime (never freed,
+// never moved once handed to a kernel) so captured graphs stay valid.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <string>
+#include <vector>
+
+#include "gemm_tcgen05.h"
+#include "kernels.h"
+
+namespace py = pybind11;
+using torch::Tensor;
+
+namespace {
+
+#define CUDA_OK(expr)                                                                             \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    TORCH_CHECK(e__ == cudaSuccess, #expr, " failed: ", cudaGetErrorString(e__));                 \
+  } while (0)
+
+cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+void check_bf16(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.scalar_type() == torch::kBFloat16, name, " must be bfloat16");
+}
+void check_rows(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.dim() == 2 && t.stride(1) == 1, name, " must be 2-D with a contiguous last dim");
+}
+
+// ---- persistent scratch -----------------------------------------------------------------------------------------
+struct Scratch {
+  std::vector<Tensor> keep;  // every buffer ever handed out stays alive (graph safety)
+  Tensor ws;                 // fp32 split-K / attention-split workspace
+  Tensor counters;           // uint32 tile tickets (self-resetting) + done counters
+  Tensor get_ws(int64_t floats, const torch::Device& dev) {
+    if (!ws.defined() || ws.numel() < floats) {
+      int64_t n = std::max<int64_t>(floats, 16 << 20);
+      ws = torch::empty({n}, torch::dtype(torch::kFloat32).device(dev));
+      keep.push_back(ws);
+    }
+    return ws;
+  }
+  Tensor get_counters(const torch::Device& dev) {
+    if (!counters.defined()) {
+      counters = torch::zeros({1 << 16}, torch::dtype(torch::kInt32).device(dev));
+      keep.push_back(counters);
+    }
+    return counters;
+  }
+};
+Scratch& scratch() {
+  static Scratch s;
+  return s;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) n = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  return n;
+}
+
+int auto_splits(int rows, int n, int k, bool grouped) {
+  if (grouped || rows > 256) return 1;
+  const int tiles = (n + 127) / 128;
+  const int kb = (k + 63) / 64;
+  int s = 1;
+  // fill ~one wave of SMs while keeping >= 4 k-blocks per split
+  while (tiles * (s * 2) <= sm_count() && kb / (s * 2) >= 4) s *= 2;
+  return s;
+}
+
+// ---- GEMM -------------------------------------------------------------------------------------------------------
+Tensor linear(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& w2, const c10::optional<Tensor>& residual,
+              const c10::optional<Tensor>& bias, int64_t act, double softcap, bool out_fp32, const c10::optional<Tensor>& out_,
+              int64_t splits, int64_t signal_flag_ptr, int64_t signal_value) {
+  check_bf16(x, "x"); check_bf16(w, "w"); check_rows(x, "x"); check_rows(w, "w");
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int64_t T = x.size(0), K = x.size(1), N = w.size(0);
+  TORCH_CHECK(w.size(1) == K, "x/w inner dims differ");
+  Tensor out = out_.has_value() ? *out_ : torch::empty({T, N}, x.options().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16));
+  TORCH_CHECK(out.dim() == 2 && out.stride(1) == 1 && out.size(0) >= T && out.size(1) == N, "bad out tensor");
+  if (T == 0) return out;
+  b200::GemmArgs a;
+  a.x = x.data_ptr(); a.x_rows = T; a.ld_x = x.stride(0);
+  a.w = w.data_ptr(); a.ld_w = w.stride(0);
+  if (w2.has_value()) { check_bf16(*w2, "w2"); TORCH_CHECK(w2->sizes() == w.sizes() && w2->stride(0) == w.stride(0)); a.w2 = w2->data_ptr(); }
+  a.m = (int)T; a.n = (int)N; a.k = (int)K; a.max_rows = (int)T;
+  a.out = out.data_ptr(); a.ld_out = out.stride(0); a.out_fp32 = out.scalar_type() == torch::kFloat32;
+  if (residual.has_value()) { check_bf16(*residual, "residual"); check_rows(*residual, "residual"); a.residual = residual->data_ptr(); a.ld_res = residual->stride(0); }
+  if (bias.has_value()) { check_bf16(*bias, "bias"); a.bias = bias->data_ptr(); }
+  a.act = (int)act; a.softcap = (float)softcap;
+  int sp = splits > 0 ? (int)splits : auto_splits((int)T, (int)N, (int)K, false);
+  a.splits = sp;
+  auto& sc = scratch();
+  Tensor ctr = sc.get_counters(x.device());
+  if (sp > 1) {
+    const int bn = b200::gemm_pick_bn((int)T);
+    Tensor ws = sc.get_ws((int64_t)b200::gemm_workspace_floats(a, bn, sp), x.device());
+    a.workspace = ws.data_ptr<float>();
+    a.tile_counters = reinterpret_cast<unsigned int*>(ctr.data_ptr<int>());
+  }
+  if (signal_flag_ptr != 0) {
+    a.signal_flag = reinterpret_cast<uint32_t*>(signal_flag_ptr);
+    a.signal_value = (uint32_t)signal_value;
+    a.done_counter = reinterpret_cast<unsigned int*>(ctr.data_ptr<int>()) + 65535;
+  }
+  CUDA_OK(b200::gemm_launch(a, cur_stream()));
+  return out;
+}
+
+Tensor grouped_linear(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& w2, const Tensor& expert_offsets,
+                      int64_t max_rows, int64_t act, bool out_fp32) {
+  check_bf16(x, "x"); check_bf16(w, "w"); check_rows(x, "x");
+  TORCH_CHECK(w.dim() == 3 && w.is_contiguous(), "w must be contiguous [E, N, K]");
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int64_t R = x.size(0), K = x.size(1), E = w.size(0), N = w.size(1);
+  TORCH_CHECK(w.size(2) == K && expert_offsets.numel() == E + 1 && expert_offsets.scalar_type() == torch::kInt32);
+  Tensor out = torch::empty({R, N}, x.options().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16));
+  if (R == 0) return out;
+  b200::GemmArgs a;
+  a.x = x.data_ptr(); a.x_rows = R; a.ld_x = x.stride(0);
+  a.w = w.data_ptr(); a.ld_w = K;
+  if (w2.has_value()) { check_bf16(*w2, "w2"); TORCH_CHECK(w2->is_contiguous() && w2->sizes() == w.sizes()); a.w2 = w2->data_ptr(); }
+  a.m = (int)R; a.n = (int)N; a.k = (int)K; a.max_rows = (int)std::min<int64_t>(max_rows, R);
+  a.num_experts = (int)E; a.expert_offsets = expert_offsets.data_ptr<int>();
+  a.out = out.data_ptr(); a.ld_out = N; a.out_fp32 = out_fp32; a.act = (int)act; a.splits = 1;
+  CUDA_OK(b200::gemm_launch(a, cur_stream()));
+  return out;
+}
+
+// ---- elementwise ------------------------------------------------------------------------------------------------
+Tensor rmsnorm(const Tensor& x, const Tensor& w, double eps, bool gemma, const c10::optional<Tensor>& residual) {
+  check_bf16(x, "x"); check_bf16(w, "w"); check_rows(x, "x");
+  const c10::cuda::CUDAGuard guard(x.device());
+  Tensor out = torch::empty({x.size(0), x.size(1)}, x.options());
+  const void* res = nullptr; long long ldr = 0;
+  if (residual.has_value()) { check_bf16(*residual, "residual"); check_rows(*residual, "residual"); res = residual->data_ptr(); ldr = residual->stride(0); }
+  CUDA_OK(b200::rmsnorm_launch(x.data_ptr(), x.stride(0), w.data_ptr(), res, ldr, out.data_ptr(), out.stride(0), (int)x.size(0),
+                               (int)x.size(1), (float)eps, gemma, cur_stream()));
+  return out;
+}
+
+void rope_(Tensor x, const Tensor& positions, const Tensor& inv_freq, int64_t rot_off, int64_t rot_dim, bool interleaved, double mscale) {
+  check_bf16(x, "x");
+  TORCH_CHECK(x.dim() == 3 && x.stride(2) == 1, "x must be [T, heads, D] with contiguous D");
+  TORCH_CHECK(positions.scalar_type() == torch::kInt32 && inv_freq.scalar_type() == torch::kFloat32 && inv_freq.is_cuda());
+  const c10::cuda::CUDAGuard guard(x.device());
+  CUDA_OK(b200::rope_launch(x.data_ptr(), x.stride(0), x.stride(1), (int)x.size(1), positions.data_ptr<int>(), inv_freq.data_ptr<float>(),
+                            (int)rot_off, (int)rot_dim, interleaved, (float)mscale, (int)x.size(0), cur_stream()));
+}
+
+Tensor embed(const Tensor& ids, const Tensor& table, const c10::optional<Tensor>& scales, const c10::optional<Tensor>& biases,
+             int64_t bits, int64_t group, double scale) {
+  TORCH_CHECK(ids.is_cuda() && ids.scalar_type() == torch::kInt64 && ids.is_contiguous(), "ids must be contiguous int64 CUDA");
+  const c10::cuda::CUDAGuard guard(ids.device());
+  const int64_t T = ids.numel();
+  int64_t H;
+  if (bits == 0) { check_bf16(table, "table"); H = table.size(1); }
+  else { TORCH_CHECK(table.scalar_type() == torch::kInt32 && scales.has_value() && biases.has_value()); check_bf16(*scales, "scales"); check_bf16(*biases, "biases"); H = table.size(1) * (32 / bits); }
+  TORCH_CHECK(table.is_contiguous());
+  Tensor out = torch::empty({T, H}, torch::dtype(torch::kBFloat16).device(ids.device()));
+  CUDA_OK(b200::embed_launch(reinterpret_cast<const long long*>(ids.data_ptr<int64_t>()), table.data_ptr(),
+                             scales.has_value() ? scales->data_ptr() : nullptr, biases.has_value() ? biases->data_ptr() : nullptr,
+                             (int)bits, (int)group, out.data_ptr(), (int)H, (float)scale, (int)T, cur_stream()));
+  return out;
+}
+
+void kv_write(const Tensor& k, const Tensor& v, Tensor kpool, Tensor vpool, const Tensor& slots) {
+  check_bf16(k, "k"); check_bf16(v, "v"); check_bf16(kpool, "kpool"); check_bf16(vpool, "vpool");
+  TORCH_CHECK(k.dim() == 3 && v.dim() == 3 && k.stride(2) == 1 && v.stride(2) == 1 && kpool.is_contiguous() && vpool.is_contiguous());
+  TORCH_CHECK(slots.scalar_type() == torch::kInt32);
+  const c10::cuda::CUDAGuard guard(k.device());
+  CUDA_OK(b200::kv_write_launch(k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(), v.stride(0), v.stride(1), kpool.data_ptr(),
+                                vpool.data_ptr(), slots.data_ptr<int>(), (int)k.size(1), (int)k.size(2), (int)v.size(2),
+                                (int)kpool.size(2), (int)k.size(0), cur_stream()));
+}
+
+void kv_write_mla(const Tensor& kv, const Tensor& kpe, Tensor kpool, Tensor vpool, const Tensor& slots, int64_t nope, int64_t vd) {
+  check_bf16(kv, "kv"); check_bf16(kpe, "kpe");
+  TORCH_CHECK(kv.dim() == 3 && kv.stride(2) == 1 && kv.stride(1) == kv.size(2) && kpe.dim() == 2 && kpe.stride(1) == 1);
+  TORCH_CHECK(kpool.is_contiguous() && vpool.is_contiguous() && slots.scalar_type() == torch::kInt32);
+  const c10::cuda::CUDAGuard guard(kv.device());
+  CUDA_OK(b200::kv_write_mla_launch(kv.data_ptr(), kv.stride(0), kpe.data_ptr(), kpe.stride(0), kpool.data_ptr(), vpool.data_ptr(),
+                                    slots.data_ptr<int>(), (int)kv.size(1), (int)nope, (int)kpe.size(1), (int)vd, (int)kpool.size(2),
+                                    (int)kv.size(0), cur_stream()));
+}
+
+// ---- attention --------------------------------------------------------------------------------------------------
+Tensor paged_attention(const Tensor& q, const Tensor& kpool, const Tensor& vpool, const Tensor& block_tables, const Tensor& positions,
+                       const Tensor& token_seq, double scale, double softcap, int64_t max_ctx) {
+  check_bf16(q, "q"); check_bf16(kpool, "kpool"); check_bf16(vpool, "vpool");
+  TORCH_CHECK(q.dim() == 3 && q.stride(2) == 1 && kpool.is_contiguous() && vpool.is_contiguous());
+  TORCH_CHECK(block_tables.scalar_type() == torch::kInt32 && block_tables.is_contiguous() && positions.scalar_type() == torch::kInt32 &&
+              token_seq.scalar_type() == torch::kInt32);
+  const c10::cuda::CUDAGuard guard(q.device());
+  const int T = (int)q.size(0), Hq = (int)q.size(1), Hk = (int)kpool.size(1), dv = (int)vpool.size(3);
+  Tensor out = torch::empty({T, Hq, dv}, q.options());
+  if (T == 0) return out;
+  b200::PagedAttnArgs a;
+  a.q = q.data_ptr(); a.q_ld_t = q.stride(0); a.q_ld_h = q.stride(1);
+  a.kpool = kpool.data_ptr(); a.vpool = vpool.data_ptr();
+  a.block_tables = block_tables.data_ptr<int>(); a.max_blocks = (int)block_tables.size(1);
+  a.positions = positions.data_ptr<int>(); a.token_seq = token_seq.data_ptr<int>();
+  a.T = T; a.q_heads = Hq; a.kv_heads = Hk; a.dk_ = (int)kpool.size(3); a.dv_ = dv; a.page = (int)kpool.size(2);
+  a.scale = (float)scale; a.softcap = (float)softcap;
+  // split the KV range until ~2 waves of CTAs exist, keeping >= 256 positions per split
+  int nsplit = 1;
+  const int ctas = T * Hk;
+  while (ctas * nsplit < 2 * sm_count() && max_ctx / (nsplit * 2) >= 256 && nsplit < 32) nsplit *= 2;
+  a.nsplit = nsplit;
+  a.out = out.data_ptr(); a.o_ld_t = (long long)Hq * dv;
+  a.part_acc = nullptr; a.part_ml = nullptr;
+  if (nsplit > 1) {
+    const int64_t n_acc = (int64_t)T * Hq * nsplit * dv, n_ml = (int64_t)T * Hq * nsplit * 2;
+    Tensor ws = scratch().get_ws(n_acc + n_ml, q.device());
+    a.part_acc = ws.data_ptr<float>();
+    a.part_ml = ws.data_ptr<float>() + n_acc;
+  }
+  CUDA_OK(b200::paged_attention_launch(a, cur_stream()));
+  return out;
+}
+
+// ---- MoE --------------------------------------------------------------------------------------------------------
+std::vector<Tensor> moe_route(const Tensor& x, const Tensor& gate_w, int64_t top_k, int64_t n_group, int64_t topk_group, double scaling,
+                              bool norm_topk) {
+  check_bf16(x, "x"); check_bf16(gate_w, "gate_w"); check_rows(x, "x");
+  TORCH_CHECK(gate_w.is_contiguous());
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int T = (int)x.size(0);
+  Tensor idx = torch::empty({T, top_k}, torch::dtype(torch::kInt32).device(x.device()));
+  Tensor w = torch::empty({T, top_k}, torch::dtype(torch::kFloat32).device(x.device()));
+  CUDA_OK(b200::moe_route_launch(x.data_ptr(), x.stride(0), gate_w.data_ptr(), T, (int)x.size(1), (int)gate_w.size(0), (int)top_k,
+                                 (int)n_group, (int)topk_group, (float)scaling, norm_topk, idx.data_ptr<int>(), w.data_ptr<float>(),
+                                 cur_stream()));
+  return {idx, w};
+}
+
+std::vector<Tensor> moe_permute(const Tensor& idx, const Tensor& x, int64_t E) {
+  check_bf16(x, "x"); check_rows(x, "x");
+  TORCH_CHECK(idx.scalar_type() == torch::kInt32 && idx.is_contiguous());
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int T = (int)idx.size(0), k = (int)idx.size(1), H = (int)x.size(1);
+  auto io = torch::dtype(torch::kInt32).device(x.device());
+  Tensor offs = torch::empty({E + 1}, io), pair_row = torch::empty({T * k}, io);
+  Tensor xp = torch::empty({(int64_t)T * k, H}, x.options());
+  CUDA_OK(b200::moe_permute_launch(idx.data_ptr<int>(), T, k, (int)E, offs.data_ptr<int>(), pair_row.data_ptr<int>(), nullptr,
+                                   x.data_ptr(), x.stride(0), xp.data_ptr(), H, cur_stream()));
+  return {offs, pair_row, xp};
+}
+
+Tensor moe_combine(const Tensor& y_perm, const Tensor& pair_row, const Tensor& wts, const c10::optional<Tensor>& residual,
+                   const c10::optional<Tensor>& out_, int64_t top_k, int64_t signal_flag_ptr, int64_t signal_value) {
+  TORCH_CHECK(y_perm.is_cuda() && y_perm.scalar_type() == torch::kFloat32 && y_perm.is_contiguous());
+  TORCH_CHECK(wts.scalar_type() == torch::kFloat32 && wts.is_contiguous() && pair_row.scalar_type() == torch::kInt32);
+  const c10::cuda::CUDAGuard guard(y_perm.device());
+  const int H = (int)y_perm.size(1), T = (int)(pair_row.numel() / top_k);
+  Tensor out = out_.has_value() ? *out_ : torch::empty({T, H}, y_perm.options().dtype(torch::kBFloat16));
+  TORCH_CHECK(out.scalar_type() == torch::kBFloat16 && out.stride(1) == 1);
+  const void* res = nullptr; long long ldr = 0;
+  if (residual.has_value()) { check_bf16(*residual, "residual"); check_rows(*residual, "residual"); res = residual->data_ptr(); ldr = residual->stride(0); }
+  unsigned int* done = nullptr;
+  if (signal_flag_ptr != 0) done = reinterpret_cast<unsigned int*>(scratch().get_counters(y_perm.device()).data_ptr<int>()) + 65534;
+  CUDA_OK(b200::moe_combine_launch(y_perm.data_ptr(), pair_row.data_ptr<int>(), wts.data_ptr<float>(), res, ldr, out.data_ptr(),
+                                   out.stride(0), T, (int)top_k, H, reinterpret_cast<uint32_t*>(signal_flag_ptr), (uint32_t)signal_value,
+                                   done, cur_stream()));
+  return out;
+}
+
+// ---- sampler ----------------------------------------------------------------------------------------------------
+void apply_penalties_(Tensor logits, const Tensor& rep_ctx, const Tensor& penalty, const Tensor& bias_idx, const Tensor& bias_val) {
+  TORCH_CHECK(logits.is_cuda() && logits.scalar_type() == torch::kFloat32 && logits.is_contiguous());
+  TORCH_CHECK(rep_ctx.scalar_type() == torch::kInt32 && bias_idx.scalar_type() == torch::kInt32 && rep_ctx.is_contiguous() && bias_idx.is_contiguous());
+  const c10::cuda::CUDAGuard guard(logits.device());
+  CUDA_OK(b200::apply_penalties_launch(logits.data_ptr<float>(), (int)logits.size(0), (int)logits.size(1), rep_ctx.data_ptr<int>(),
+                                       (int)rep_ctx.size(1), penalty.data_ptr<float>(), bias_idx.data_ptr<int>(), bias_val.data_ptr<float>(),
+                                       (int)bias_idx.size(1), cur_stream()));
+}
+
+std::vector<Tensor> sample(const Tensor& logits, const Tensor& temperature, const Tensor& top_p, int64_t seed, int64_t step, int64_t top_k) {
+  TORCH_CHECK(logits.is_cuda() && logits.scalar_type() == torch::kFloat32 && logits.is_contiguous());
+  const c10::cuda::CUDAGuard guard(logits.device());
+  const int B = (int)logits.size(0);
+  auto dev = logits.device();
+  Tensor tokens = torch::empty({B}, torch::dtype(torch::kInt64).device(dev));
+  Tensor lp = torch::empty({B}, torch::dtype(torch::kFloat32).device(dev));
+  Tensor top_ids = torch::empty({B, top_k}, torch::dtype(torch::kInt64).device(dev));
+  Tensor top_lp = torch::empty({B, top_k}, torch::dtype(torch::kFloat32).device(dev));
+  CUDA_OK(b200::sample_launch(logits.data_ptr<float>(), B, (int)logits.size(1), temperature.data_ptr<float>(), top_p.data_ptr<float>(),
+                              (unsigned long long)seed, (unsigned long long)step, reinterpret_cast<long long*>(tokens.data_ptr<int64_t>()),
+                              lp.data_ptr<float>(), (int)top_k, reinterpret_cast<long long*>(top_ids.data_ptr<int64_t>()),
+                              top_lp.data_ptr<float>(), cur_stream()));
+  return {tokens, lp, top_ids, top_lp};
+}
+
+// ---- P2P / IPC --------------------------------------------------------------------------------------------------
+py::tuple ipc_alloc(int64_t nbytes) {
+  void* p = nullptr;
+  CUDA_OK(cudaMalloc(&p, (size_t)nbytes));
+  CUDA_OK(cudaMemset(p, 0, (size_t)nbytes));
+  cudaIpcMemHandle_t h;
+  CUDA_OK(cudaIpcGetMemHandle(&h, p));
+  return py::make_tuple((int64_t) reinterpret_cast<uintptr_t>(p), py::bytes(reinterpret_cast<const char*>(&h), sizeof(h)));
+}
+int64_t ipc_open(const std::string& handle) {
+  TORCH_CHECK(handle.size() == sizeof(cudaIpcMemHandle_t), "bad IPC handle size");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle.data(), sizeof(h));
+  void* p = nullptr;
+  CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  return (int64_t) reinterpret_cast<uintptr_t>(p);
+}
+void enable_peer_access(int64_t peer) {
+  int can = 0, dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  CUDA_OK(cudaDeviceCanAccessPeer(&can, dev, (int)peer));
+  TORCH_CHECK(can, "device ", dev, " cannot access peer ", peer);
+  cudaError_t e = cudaDeviceEnablePeerAccess((int)peer, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return; }
+  CUDA_OK(e);
+}
+Tensor tensor_from_ptr(int64_t ptr, std::vector<int64_t> shape, const std::string& dtype, int64_t device) {
+  auto dt = dtype == "bfloat16" ? torch::kBFloat16 : dtype == "float32" ? torch::kFloat32 : dtype == "int32" ? torch::kInt32
+            : dtype == "int64" ? torch::kInt64 : torch::kUInt8;
+  return torch::from_blob(reinterpret_cast<void*>(ptr), shape, torch::dtype(dt).device(torch::kCUDA, (int)device));
+}
+void wait_flag(int64_t flag_ptr, int64_t expected, int64_t error_ptr) {
+  CUDA_OK(b200::wait_flag_launch(reinterpret_cast<const uint32_t*>(flag_ptr), (uint32_t)expected, reinterpret_cast<uint32_t*>(error_ptr), cur_stream()));
+}
+void set_flag(int64_t flag_ptr, int64_t value) { CUDA_OK(b200::set_flag_launch(reinterpret_cast<uint32_t*>(flag_ptr), (uint32_t)value, cur_stream())); }
+void copy_signal(const Tensor& src, int64_t dst_ptr, int64_t flag_ptr, int64_t value) {
+  TORCH_CHECK(src.is_cuda() && src.is_contiguous());
+  const c10::cuda::CUDAGuard guard(src.device());
+  CUDA_OK(b200::copy_signal_launch(src.data_ptr(), reinterpret_cast<void*>(dst_ptr), (size_t)src.numel() * src.element_size(),
+                                   reinterpret_cast<uint32_t*>(flag_ptr), (uint32_t)value, cur_stream()));
+}
+void advance_meta(Tensor positions, Tensor context_lens, Tensor slots, const Tensor& block_tables, int64_t page) {
+  TORCH_CHECK(positions.scalar_type() == torch::kInt32 && block_tables.scalar_type() == torch::kInt32 && block_tables.is_contiguous());
+  const c10::cuda::CUDAGuard guard(positions.device());
+  CUDA_OK(b200::advance_meta_launch(positions.data_ptr<int>(), context_lens.data_ptr<int>(), slots.data_ptr<int>(), block_tables.data_ptr<int>(),
+                                    (int)block_tables.size(1), (int)page, (int)positions.numel(), cur_stream()));
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "mlx_sharding_b200 sm_100a kernels";
+  m.def("linear", &linear, py::arg("x"), py::arg("w"), py::arg("w2") = py::none(), py::arg("residual") = py::none(),
+        py::arg("bias") = py::none(), py::arg("act") = 0, py::arg("softcap") = 0.0, py::arg("out_fp32") = false,
+        py::arg("out") = py::none(), py::arg("splits") = 0, py::arg("signal_flag_ptr") = 0, py::arg("signal_value") = 0);
+  m.def("grouped_linear", &grouped_linear, py::arg("x"), py::arg("w"), py::arg("w2") = py::none(), py::arg("expert_offsets"),
+        py::arg("max_rows"), py::arg("act") = 0, py::arg("out_fp32") = false);
+  m.def("rmsnorm", &rmsnorm, py::arg("x"), py::arg("w"), py::arg("eps"), py::arg("gemma") = false, py::arg("residual") = py::none());
+  m.def("rope_", &rope_);
+  m.def("embed", &embed, py::arg("ids"), py::arg("table"), py::arg("scales") = py::none(), py::arg("biases") = py::none(),
+        py::arg("bits") = 0, py::arg("group") = 64, py::arg("scale") = 1.0);
+  m.def("kv_write", &kv_write);
+  m.def("kv_write_mla", &kv_write_mla);
+  m.def("paged_attention", &paged_attention);
+  m.def("moe_route", &moe_route);
+  m.def("moe_permute", &moe_permute);
+  m.def("moe_combine", &moe_combine, py::arg("y_perm"), py::arg("pair_row"), py::arg("wts"), py::arg("residual") = py::none(),
+        py::arg("out") = py::none(), py::arg("top_k"), py::arg("signal_flag_ptr") = 0, py::arg("signal_value") = 0);
+  m.def("apply_penalties_", &apply_penalties_);
+  m.def("sample", &sample);
+  m.def("ipc_alloc", &ipc_alloc);
+  m.def("ipc_open", &ipc_open);
+  m.def("enable_peer_access", &enable_peer_access);
+  m.def("tensor_from_ptr", &tensor_from_ptr);
+  m.def("wait_flag", &wait_flag);
+  m.def("set_flag", &set_flag);
+  m.def("copy_signal", &copy_signal);
+  m.def("advance_meta", &advance_meta);
+  m.def("sm_arch", []() { return std::string("sm_100a"); });
+}

@@ -1,0 +1,102 @@
+// Device-side primitives of the fused P2P stage boundary (SURVEY §5.8 tier T0, call sites X1/X3):
+// flag wait (bounded spin, acquire.sys), flag set (release.sys), copy-with-signal for hand-offs that
+// cannot ride a GEMM epilogue, and the on-device step-metadata advance that lets a CUDA-graphed decode
+// step re-run without any host -> device traffic.  The reference's equivalent is a blocking gRPC unary
+// call per stage per token with host staging (shard/utils.py:71-90,162-164).
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+namespace {
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Spin until *flag >= expected (monotonic step counters).  Bounded: after ~timeout the kernel records an
+// error and returns instead of hanging the GPU (a dead peer must never wedge the box).
+__global__ void wait_flag_kernel(const uint32_t* flag, uint32_t expected, uint32_t* error_flag, unsigned long long timeout_ns) {
+  const unsigned long long t0 = globaltimer_ns();
+  while (true) {
+    const uint32_t v = ld_acquire_sys(flag);
+    if ((int32_t)(v - expected) >= 0) break;
+    if (globaltimer_ns() - t0 > timeout_ns) {
+      if (error_flag != nullptr) atomicExch(error_flag, 1u);
+      break;
+    }
+    __nanosleep(64);
+  }
+}
+
+__global__ void set_flag_kernel(uint32_t* flag, uint32_t value) {
+  __threadfence_system();
+  st_release_sys(flag, value);
+}
+
+// dst may be peer memory: stream src -> dst with 16 B stores, then publish the flag from the last CTA.
+__global__ void copy_signal_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t nvec, uint32_t* flag,
+                                   uint32_t value, unsigned int* done_counter) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(done_counter, 1u) + 1u;
+    if (done == gridDim.x) {
+      *done_counter = 0u;
+      __threadfence_system();
+      st_release_sys(flag, value);
+    }
+  }
+}
+
+// decode step k -> k+1 for every sequence of a micro-batch: position, context length, KV slot
+__global__ void advance_meta_kernel(int* positions, int* context_lens, int* slots, const int* block_tables, int max_blocks,
+                                    int page, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int p = positions[b] + 1;
+  positions[b] = p;
+  context_lens[b] = p + 1;
+  slots[b] = block_tables[(size_t)b * max_blocks + p / page] * page + p % page;
+}
+
+unsigned int* g_copy_counter = nullptr;
+
+}  // namespace
+
+cudaError_t wait_flag_launch(const uint32_t* flag, uint32_t expected, uint32_t* error_flag, cudaStream_t s) {
+  wait_flag_kernel<<<1, 1, 0, s>>>(flag, expected, error_flag, 20ull * 1000ull * 1000ull * 1000ull);
+  return cudaGetLastError();
+}
+
+cudaError_t set_flag_launch(uint32_t* flag, uint32_t value, cudaStream_t s) {
+  set_flag_kernel<<<1, 1, 0, s>>>(flag, value);
+  return cudaGetLastError();
+}
+
+cudaError_t copy_signal_launch(const void* src, void* dst, size_t bytes, uint32_t* flag, uint32_t value, cudaStream_t s) {
+  if (bytes % 16) return cudaErrorInvalidValue;
+  if (g_copy_counter == nullptr) {
+    cudaError_t e = cudaMalloc(&g_copy_counter, sizeof(unsigned int));
+    if (e != cudaSuccess) return e;
+    cudaMemset(g_copy_counter, 0, sizeof(unsigned int));
+  }
+  const size_t nvec = bytes / 16;
+  int grid = (int)((nvec + 255) / 256);
+  if (grid > 296) grid = 296;
+  if (grid < 1) grid = 1;
+  copy_signal_kernel<<<grid, 256, 0, s>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), nvec, flag, value, g_copy_counter);
+  return cudaGetLastError();
+}
+
+cudaError_t advance_meta_launch(int* positions, int* context_lens, int* slots, const int* block_tables, int max_blocks,
+                                int page, int B, cudaStream_t s) {
+  if (B == 0) return cudaSuccess;
+  advance_meta_kernel<<<(B + 127) / 128, 128, 0, s>>>(positions, context_lens, slots, block_tables, max_blocks, page, B);
+  return cudaGetLastError();
+}
+
+}  // namespace b200

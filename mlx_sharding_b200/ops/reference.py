@@ -20,6 +20,11 @@ from .weights import LinearWeight, RopeSpec
 
 NAME = "reference"
 
+# Oracle mode (default): every matmul accumulates and returns true fp32.  ``FAST_BASELINE = True`` turns
+# this module into the "straight PyTorch + cuBLAS" baseline: bf16 tensor-core GEMMs via F.linear with bf16
+# outputs, the way a plain PyTorch re-implementation of the reference pipeline would run on a B200.
+FAST_BASELINE = False
+
 
 # ------------------------------------------------------------------------------------------ K1
 def embed(ids: torch.Tensor, emb: LinearWeight, scale: float = 1.0,
@@ -62,8 +67,8 @@ def add_rmsnorm(x: torch.Tensor, residual: torch.Tensor, w: torch.Tensor, eps: f
 def linear(x: torch.Tensor, W: LinearWeight, residual: Optional[torch.Tensor] = None,
            out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """``y = x @ W^T (+ bias) (+ residual)``; fp32 accumulate, single rounding at the end."""
-    if x.is_cuda and not W.is_quantized and W.weight.dtype == x.dtype and x.dtype != torch.float32:
-        y = F.linear(x, W.weight).float()  # cuBLAS path (baseline role)
+    if FAST_BASELINE and x.is_cuda and x.dtype != torch.float32:
+        y = F.linear(x, W.dense_cached(x.dtype)).float()  # cuBLAS bf16 path (baseline role)
     else:
         y = x.float() @ W.dense(torch.float32).t()
     if W.bias is not None:
@@ -229,17 +234,18 @@ def apply_repetition_penalty_(logits: torch.Tensor, ctx_tokens: torch.Tensor, pe
 
 def apply_penalties_(logits: torch.Tensor, rep_ctx: torch.Tensor, penalty: torch.Tensor,
                      bias_idx: torch.Tensor, bias_val: torch.Tensor) -> torch.Tensor:
-    """Batched in-place logit_bias add then repetition penalty (reference utils.py:127-130,167-170).
-    ``rep_ctx int32 [B, C]`` / ``bias_idx int32 [B, Nb]`` are padded with ``-1``."""
+    """Batched in-place repetition penalty (reference utils.py:167-170) then logit_bias add
+    (utils.py:127-130, inside ``sample``).  ``rep_ctx int32 [B, C]`` / ``bias_idx int32 [B, Nb]`` are
+    padded with ``-1``."""
     B = logits.shape[0]
     for b in range(B):
+        c = rep_ctx[b]
+        c = c[c >= 0]
+        apply_repetition_penalty_(logits[b], c, float(penalty[b]))
         bi = bias_idx[b]
         m = bi >= 0
         if m.any():
             logits[b].index_add_(0, bi[m].long(), bias_val[b][m].to(logits.dtype))
-        c = rep_ctx[b]
-        c = c[c >= 0]
-        apply_repetition_penalty_(logits[b], c, float(penalty[b]))
     return logits
 
 

@@ -48,6 +48,16 @@ class LinearWeight:
             return quant.dequantize(self.wq, self.scales, self.biases, self.group_size, self.bits, dtype)
         return self.weight.to(dtype)
 
+    def dense_cached(self, dtype: torch.dtype) -> torch.Tensor:
+        """Dense weight in ``dtype``; quantised weights are expanded once and kept."""
+        if not self.is_quantized:
+            return self.weight if self.weight.dtype == dtype else self.weight.to(dtype)
+        c = getattr(self, "_dense_cache", None)
+        if c is None or c.dtype != dtype:
+            c = self.dense(dtype)
+            self._dense_cache = c
+        return c
+
     def to(self, device=None, dtype=None) -> "LinearWeight":
         def mv(t, cast):
             if t is None:

@@ -54,3 +54,21 @@ def run_sequence(stages, tokens, n_decode=0, page_size=16, chunk=None, greedy_de
         done += 1
         outs.append(logits[0].float().cpu())
     return outs
+
+# GPU-shaped tiny configs: head dims are multiples of 64, hidden/intermediate multiples of 128 (kernel tiles)
+GPU_LLAMA = dict(model_type="llama", vocab_size=512, hidden_size=256, intermediate_size=512,
+                 num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, rms_norm_eps=1e-5,
+                 rope_theta=10000.0, max_position_embeddings=4096, tie_word_embeddings=False)
+GPU_GEMMA2 = dict(model_type="gemma2", vocab_size=512, hidden_size=256, intermediate_size=512,
+                  num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=64,
+                  rms_norm_eps=1e-6, rope_theta=10000.0, query_pre_attn_scalar=64,
+                  attn_logit_softcapping=50.0, final_logit_softcapping=30.0, max_position_embeddings=4096)
+GPU_DSV2 = dict(model_type="deepseek_v2", vocab_size=512, hidden_size=256, intermediate_size=512,
+                moe_intermediate_size=128, num_hidden_layers=4, num_attention_heads=2, num_key_value_heads=2,
+                n_shared_experts=2, n_routed_experts=8, routed_scaling_factor=1.0, kv_lora_rank=64,
+                q_lora_rank=None, qk_rope_head_dim=64, v_head_dim=128, qk_nope_head_dim=128,
+                topk_method="greedy", n_group=1, topk_group=1, num_experts_per_tok=3, moe_layer_freq=1,
+                first_k_dense_replace=1, norm_topk_prob=False, rms_norm_eps=1e-6, rope_theta=10000.0,
+                max_position_embeddings=4096, tie_word_embeddings=False,
+                rope_scaling=dict(beta_fast=32, beta_slow=1, factor=40, mscale=0.707, mscale_all_dim=0.707,
+                                  original_max_position_embeddings=4096, type="yarn"))
