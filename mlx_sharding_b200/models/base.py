@@ -98,6 +98,9 @@ class StageModel:
         self.lm_head: Optional[LinearWeight] = None
         self.layer_weights: Dict[int, dict] = {}
         self.rope: Optional[RopeSpec] = None
+        # fused stage boundary (parallel/p2p_fused.py): when set to (out_rows_tensor, flag_ptr) the last
+        # kernel of the last local layer stores straight into that (peer-mapped) buffer and bumps the flag
+        self.boundary = None
 
     # reference-compatible surface ------------------------------------------------------------
     @property
@@ -197,6 +200,13 @@ class StageModel:
 
     def layer_forward(self, i: int, h: torch.Tensor, meta: BatchMeta, kpool, vpool) -> torch.Tensor:
         raise NotImplementedError
+
+    def _final_kwargs(self, i: int, T: int) -> dict:
+        """Extra kwargs for the last op of layer ``i``: the fused P2P store + signal on a stage boundary."""
+        if self.boundary is None or self.spec.is_last or i != self.spec.end_layer - 1:
+            return {}
+        out, flag_ptr = self.boundary
+        return dict(out=out[:T], signal=(flag_ptr, 0))
 
     def head(self, h: torch.Tensor, meta: BatchMeta, all_logits: bool = False) -> torch.Tensor:
         """Final norm + LM head -> fp32 logits for the last position of each sequence (the reference

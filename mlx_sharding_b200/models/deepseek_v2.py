@@ -114,8 +114,10 @@ class DeepseekV2Stage(StageModel):
                                    c.norm_topk_prob)
             if "s_gate" in w:
                 h = O.linear(O.gated_up(normed, w["s_gate"], w["s_up"], "silu"), w["s_down"], residual=h)
-            return O.moe_experts(normed, idx, wts, w["e_gate"], w["e_up"], w["e_down"], "silu", residual=h)
-        return O.linear(O.gated_up(normed, w["gate"], w["up"], "silu"), w["down"], residual=h)
+            return O.moe_experts(normed, idx, wts, w["e_gate"], w["e_up"], w["e_down"], "silu", residual=h,
+                                 **self._final_kwargs(i, T))
+        return O.linear(O.gated_up(normed, w["gate"], w["up"], "silu"), w["down"], residual=h,
+                        **self._final_kwargs(i, T))
 
 
 Model = DeepseekV2Stage

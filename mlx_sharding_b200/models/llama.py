@@ -61,7 +61,7 @@ class LlamaStage(StageModel):
         h = O.linear(attn, w["o"], residual=h)
         normed = O.rmsnorm(h, w["post_ln"], c.rms_norm_eps)
         act = O.gated_up(normed, w["gate"], w["up"], self.act)
-        return O.linear(act, w["down"], residual=h)
+        return O.linear(act, w["down"], residual=h, **self._final_kwargs(i, h.shape[0]))
 
 
 Model = LlamaStage

@@ -41,6 +41,10 @@ def load_extension(build_if_missing: bool = False):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     _C = mod
+    if torch.cuda.is_available():
+        # persistent scratch (split-K / attention-split workspace, tile tickets) must exist before any
+        # CUDA-graph capture
+        mod.init_scratch(torch.cuda.current_device(), 32 << 20)
     return _C
 
 

@@ -22,6 +22,14 @@ namespace {
     TORCH_CHECK(e__ == cudaSuccess, #expr, " failed: ", cudaGetErrorString(e__));                 \
   } while (0)
 
+// number of kernels launched by this module (bench.py reports it as gpu_launches)
+int64_t g_launches = 0;
+#define LAUNCH_OK(expr) \
+  do {                   \
+    CUDA_OK(expr);       \
+    ++g_launches;        \
+  } while (0)
+
 cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
 
 void check_bf16(const Tensor& t, const char* name) {
@@ -109,7 +117,7 @@ Tensor linear(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& w2,
     a.signal_value = (uint32_t)signal_value;
     a.done_counter = reinterpret_cast<unsigned int*>(ctr.data_ptr<int>()) + 65535;
   }
-  CUDA_OK(b200::gemm_launch(a, cur_stream()));
+  LAUNCH_OK(b200::gemm_launch(a, cur_stream()));
   return out;
 }
 
@@ -129,7 +137,7 @@ Tensor grouped_linear(const Tensor& x, const Tensor& w, const c10::optional<Tens
   a.m = (int)R; a.n = (int)N; a.k = (int)K; a.max_rows = (int)std::min<int64_t>(max_rows, R);
   a.num_experts = (int)E; a.expert_offsets = expert_offsets.data_ptr<int>();
   a.out = out.data_ptr(); a.ld_out = N; a.out_fp32 = out_fp32; a.act = (int)act; a.splits = 1;
-  CUDA_OK(b200::gemm_launch(a, cur_stream()));
+  LAUNCH_OK(b200::gemm_launch(a, cur_stream()));
   return out;
 }
 
@@ -140,7 +148,7 @@ Tensor rmsnorm(const Tensor& x, const Tensor& w, double eps, bool gemma, const c
   Tensor out = torch::empty({x.size(0), x.size(1)}, x.options());
   const void* res = nullptr; long long ldr = 0;
   if (residual.has_value()) { check_bf16(*residual, "residual"); check_rows(*residual, "residual"); res = residual->data_ptr(); ldr = residual->stride(0); }
-  CUDA_OK(b200::rmsnorm_launch(x.data_ptr(), x.stride(0), w.data_ptr(), res, ldr, out.data_ptr(), out.stride(0), (int)x.size(0),
+  LAUNCH_OK(b200::rmsnorm_launch(x.data_ptr(), x.stride(0), w.data_ptr(), res, ldr, out.data_ptr(), out.stride(0), (int)x.size(0),
                                (int)x.size(1), (float)eps, gemma, cur_stream()));
   return out;
 }
@@ -150,7 +158,7 @@ void rope_(Tensor x, const Tensor& positions, const Tensor& inv_freq, int64_t ro
   TORCH_CHECK(x.dim() == 3 && x.stride(2) == 1, "x must be [T, heads, D] with contiguous D");
   TORCH_CHECK(positions.scalar_type() == torch::kInt32 && inv_freq.scalar_type() == torch::kFloat32 && inv_freq.is_cuda());
   const c10::cuda::CUDAGuard guard(x.device());
-  CUDA_OK(b200::rope_launch(x.data_ptr(), x.stride(0), x.stride(1), (int)x.size(1), positions.data_ptr<int>(), inv_freq.data_ptr<float>(),
+  LAUNCH_OK(b200::rope_launch(x.data_ptr(), x.stride(0), x.stride(1), (int)x.size(1), positions.data_ptr<int>(), inv_freq.data_ptr<float>(),
                             (int)rot_off, (int)rot_dim, interleaved, (float)mscale, (int)x.size(0), cur_stream()));
 }
 
@@ -164,7 +172,7 @@ Tensor embed(const Tensor& ids, const Tensor& table, const c10::optional<Tensor>
   else { TORCH_CHECK(table.scalar_type() == torch::kInt32 && scales.has_value() && biases.has_value()); check_bf16(*scales, "scales"); check_bf16(*biases, "biases"); H = table.size(1) * (32 / bits); }
   TORCH_CHECK(table.is_contiguous());
   Tensor out = torch::empty({T, H}, torch::dtype(torch::kBFloat16).device(ids.device()));
-  CUDA_OK(b200::embed_launch(reinterpret_cast<const long long*>(ids.data_ptr<int64_t>()), table.data_ptr(),
+  LAUNCH_OK(b200::embed_launch(reinterpret_cast<const long long*>(ids.data_ptr<int64_t>()), table.data_ptr(),
                              scales.has_value() ? scales->data_ptr() : nullptr, biases.has_value() ? biases->data_ptr() : nullptr,
                              (int)bits, (int)group, out.data_ptr(), (int)H, (float)scale, (int)T, cur_stream()));
   return out;
@@ -175,7 +183,7 @@ void kv_write(const Tensor& k, const Tensor& v, Tensor kpool, Tensor vpool, cons
   TORCH_CHECK(k.dim() == 3 && v.dim() == 3 && k.stride(2) == 1 && v.stride(2) == 1 && kpool.is_contiguous() && vpool.is_contiguous());
   TORCH_CHECK(slots.scalar_type() == torch::kInt32);
   const c10::cuda::CUDAGuard guard(k.device());
-  CUDA_OK(b200::kv_write_launch(k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(), v.stride(0), v.stride(1), kpool.data_ptr(),
+  LAUNCH_OK(b200::kv_write_launch(k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(), v.stride(0), v.stride(1), kpool.data_ptr(),
                                 vpool.data_ptr(), slots.data_ptr<int>(), (int)k.size(1), (int)k.size(2), (int)v.size(2),
                                 (int)kpool.size(2), (int)k.size(0), cur_stream()));
 }
@@ -185,7 +193,7 @@ void kv_write_mla(const Tensor& kv, const Tensor& kpe, Tensor kpool, Tensor vpoo
   TORCH_CHECK(kv.dim() == 3 && kv.stride(2) == 1 && kv.stride(1) == kv.size(2) && kpe.dim() == 2 && kpe.stride(1) == 1);
   TORCH_CHECK(kpool.is_contiguous() && vpool.is_contiguous() && slots.scalar_type() == torch::kInt32);
   const c10::cuda::CUDAGuard guard(kv.device());
-  CUDA_OK(b200::kv_write_mla_launch(kv.data_ptr(), kv.stride(0), kpe.data_ptr(), kpe.stride(0), kpool.data_ptr(), vpool.data_ptr(),
+  LAUNCH_OK(b200::kv_write_mla_launch(kv.data_ptr(), kv.stride(0), kpe.data_ptr(), kpe.stride(0), kpool.data_ptr(), vpool.data_ptr(),
                                     slots.data_ptr<int>(), (int)kv.size(1), (int)nope, (int)kpe.size(1), (int)vd, (int)kpool.size(2),
                                     (int)kv.size(0), cur_stream()));
 }
@@ -221,7 +229,8 @@ Tensor paged_attention(const Tensor& q, const Tensor& kpool, const Tensor& vpool
     a.part_acc = ws.data_ptr<float>();
     a.part_ml = ws.data_ptr<float>() + n_acc;
   }
-  CUDA_OK(b200::paged_attention_launch(a, cur_stream()));
+  LAUNCH_OK(b200::paged_attention_launch(a, cur_stream()));
+  if (nsplit > 1) ++g_launches;  // + LSE combine kernel
   return out;
 }
 
@@ -234,7 +243,7 @@ std::vector<Tensor> moe_route(const Tensor& x, const Tensor& gate_w, int64_t top
   const int T = (int)x.size(0);
   Tensor idx = torch::empty({T, top_k}, torch::dtype(torch::kInt32).device(x.device()));
   Tensor w = torch::empty({T, top_k}, torch::dtype(torch::kFloat32).device(x.device()));
-  CUDA_OK(b200::moe_route_launch(x.data_ptr(), x.stride(0), gate_w.data_ptr(), T, (int)x.size(1), (int)gate_w.size(0), (int)top_k,
+  LAUNCH_OK(b200::moe_route_launch(x.data_ptr(), x.stride(0), gate_w.data_ptr(), T, (int)x.size(1), (int)gate_w.size(0), (int)top_k,
                                  (int)n_group, (int)topk_group, (float)scaling, norm_topk, idx.data_ptr<int>(), w.data_ptr<float>(),
                                  cur_stream()));
   return {idx, w};
@@ -248,8 +257,9 @@ std::vector<Tensor> moe_permute(const Tensor& idx, const Tensor& x, int64_t E) {
   auto io = torch::dtype(torch::kInt32).device(x.device());
   Tensor offs = torch::empty({E + 1}, io), pair_row = torch::empty({T * k}, io);
   Tensor xp = torch::empty({(int64_t)T * k, H}, x.options());
-  CUDA_OK(b200::moe_permute_launch(idx.data_ptr<int>(), T, k, (int)E, offs.data_ptr<int>(), pair_row.data_ptr<int>(), nullptr,
+  LAUNCH_OK(b200::moe_permute_launch(idx.data_ptr<int>(), T, k, (int)E, offs.data_ptr<int>(), pair_row.data_ptr<int>(), nullptr,
                                    x.data_ptr(), x.stride(0), xp.data_ptr(), H, cur_stream()));
+  ++g_launches;  // offsets + gather
   return {offs, pair_row, xp};
 }
 
@@ -265,7 +275,7 @@ Tensor moe_combine(const Tensor& y_perm, const Tensor& pair_row, const Tensor& w
   if (residual.has_value()) { check_bf16(*residual, "residual"); check_rows(*residual, "residual"); res = residual->data_ptr(); ldr = residual->stride(0); }
   unsigned int* done = nullptr;
   if (signal_flag_ptr != 0) done = reinterpret_cast<unsigned int*>(scratch().get_counters(y_perm.device()).data_ptr<int>()) + 65534;
-  CUDA_OK(b200::moe_combine_launch(y_perm.data_ptr(), pair_row.data_ptr<int>(), wts.data_ptr<float>(), res, ldr, out.data_ptr(),
+  LAUNCH_OK(b200::moe_combine_launch(y_perm.data_ptr(), pair_row.data_ptr<int>(), wts.data_ptr<float>(), res, ldr, out.data_ptr(),
                                    out.stride(0), T, (int)top_k, H, reinterpret_cast<uint32_t*>(signal_flag_ptr), (uint32_t)signal_value,
                                    done, cur_stream()));
   return out;
@@ -276,7 +286,7 @@ void apply_penalties_(Tensor logits, const Tensor& rep_ctx, const Tensor& penalt
   TORCH_CHECK(logits.is_cuda() && logits.scalar_type() == torch::kFloat32 && logits.is_contiguous());
   TORCH_CHECK(rep_ctx.scalar_type() == torch::kInt32 && bias_idx.scalar_type() == torch::kInt32 && rep_ctx.is_contiguous() && bias_idx.is_contiguous());
   const c10::cuda::CUDAGuard guard(logits.device());
-  CUDA_OK(b200::apply_penalties_launch(logits.data_ptr<float>(), (int)logits.size(0), (int)logits.size(1), rep_ctx.data_ptr<int>(),
+  LAUNCH_OK(b200::apply_penalties_launch(logits.data_ptr<float>(), (int)logits.size(0), (int)logits.size(1), rep_ctx.data_ptr<int>(),
                                        (int)rep_ctx.size(1), penalty.data_ptr<float>(), bias_idx.data_ptr<int>(), bias_val.data_ptr<float>(),
                                        (int)bias_idx.size(1), cur_stream()));
 }
@@ -290,7 +300,7 @@ std::vector<Tensor> sample(const Tensor& logits, const Tensor& temperature, cons
   Tensor lp = torch::empty({B}, torch::dtype(torch::kFloat32).device(dev));
   Tensor top_ids = torch::empty({B, top_k}, torch::dtype(torch::kInt64).device(dev));
   Tensor top_lp = torch::empty({B, top_k}, torch::dtype(torch::kFloat32).device(dev));
-  CUDA_OK(b200::sample_launch(logits.data_ptr<float>(), B, (int)logits.size(1), temperature.data_ptr<float>(), top_p.data_ptr<float>(),
+  LAUNCH_OK(b200::sample_launch(logits.data_ptr<float>(), B, (int)logits.size(1), temperature.data_ptr<float>(), top_p.data_ptr<float>(),
                               (unsigned long long)seed, (unsigned long long)step, reinterpret_cast<long long*>(tokens.data_ptr<int64_t>()),
                               lp.data_ptr<float>(), (int)top_k, reinterpret_cast<long long*>(top_ids.data_ptr<int64_t>()),
                               top_lp.data_ptr<float>(), cur_stream()));
@@ -329,19 +339,31 @@ Tensor tensor_from_ptr(int64_t ptr, std::vector<int64_t> shape, const std::strin
   return torch::from_blob(reinterpret_cast<void*>(ptr), shape, torch::dtype(dt).device(torch::kCUDA, (int)device));
 }
 void wait_flag(int64_t flag_ptr, int64_t expected, int64_t error_ptr) {
-  CUDA_OK(b200::wait_flag_launch(reinterpret_cast<const uint32_t*>(flag_ptr), (uint32_t)expected, reinterpret_cast<uint32_t*>(error_ptr), cur_stream()));
+  LAUNCH_OK(b200::wait_flag_launch(reinterpret_cast<const uint32_t*>(flag_ptr), (uint32_t)expected, reinterpret_cast<uint32_t*>(error_ptr), cur_stream()));
 }
-void set_flag(int64_t flag_ptr, int64_t value) { CUDA_OK(b200::set_flag_launch(reinterpret_cast<uint32_t*>(flag_ptr), (uint32_t)value, cur_stream())); }
+void wait_flag_counter(int64_t flag_ptr, int64_t counter_ptr, int64_t error_ptr) {
+  LAUNCH_OK(b200::wait_flag_counter_launch(reinterpret_cast<const uint32_t*>(flag_ptr), reinterpret_cast<uint32_t*>(counter_ptr),
+                                         reinterpret_cast<uint32_t*>(error_ptr), cur_stream()));
+}
+void set_flag(int64_t flag_ptr, int64_t value) { LAUNCH_OK(b200::set_flag_launch(reinterpret_cast<uint32_t*>(flag_ptr), (uint32_t)value, cur_stream())); }
 void copy_signal(const Tensor& src, int64_t dst_ptr, int64_t flag_ptr, int64_t value) {
   TORCH_CHECK(src.is_cuda() && src.is_contiguous());
   const c10::cuda::CUDAGuard guard(src.device());
-  CUDA_OK(b200::copy_signal_launch(src.data_ptr(), reinterpret_cast<void*>(dst_ptr), (size_t)src.numel() * src.element_size(),
-                                   reinterpret_cast<uint32_t*>(flag_ptr), (uint32_t)value, cur_stream()));
+  LAUNCH_OK(b200::copy_signal_launch(src.data_ptr(), reinterpret_cast<void*>(dst_ptr), (size_t)src.numel() * src.element_size(),
+                                   reinterpret_cast<uint32_t*>(flag_ptr), (uint32_t)value,
+                                   reinterpret_cast<unsigned int*>(scratch().get_counters(src.device()).data_ptr<int>()) + 65533,
+                                   cur_stream()));
+}
+// allocate the persistent scratch eagerly (must happen before any CUDA-graph capture)
+void init_scratch(int64_t device, int64_t ws_floats) {
+  const c10::cuda::CUDAGuard guard(torch::Device(torch::kCUDA, (int)device));
+  scratch().get_counters(torch::Device(torch::kCUDA, (int)device));
+  scratch().get_ws(ws_floats, torch::Device(torch::kCUDA, (int)device));
 }
 void advance_meta(Tensor positions, Tensor context_lens, Tensor slots, const Tensor& block_tables, int64_t page) {
   TORCH_CHECK(positions.scalar_type() == torch::kInt32 && block_tables.scalar_type() == torch::kInt32 && block_tables.is_contiguous());
   const c10::cuda::CUDAGuard guard(positions.device());
-  CUDA_OK(b200::advance_meta_launch(positions.data_ptr<int>(), context_lens.data_ptr<int>(), slots.data_ptr<int>(), block_tables.data_ptr<int>(),
+  LAUNCH_OK(b200::advance_meta_launch(positions.data_ptr<int>(), context_lens.data_ptr<int>(), slots.data_ptr<int>(), block_tables.data_ptr<int>(),
                                     (int)block_tables.size(1), (int)page, (int)positions.numel(), cur_stream()));
 }
 
@@ -372,8 +394,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("enable_peer_access", &enable_peer_access);
   m.def("tensor_from_ptr", &tensor_from_ptr);
   m.def("wait_flag", &wait_flag);
+  m.def("wait_flag_counter", &wait_flag_counter);
   m.def("set_flag", &set_flag);
   m.def("copy_signal", &copy_signal);
   m.def("advance_meta", &advance_meta);
+  m.def("init_scratch", &init_scratch);
+  m.def("launch_count", []() { return g_launches; });
   m.def("sm_arch", []() { return std::string("sm_100a"); });
 }

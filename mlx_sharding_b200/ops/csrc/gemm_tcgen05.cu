@@ -313,7 +313,9 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         if (done == p.signal_tiles) {
           *p.done_counter = 0u;
           __threadfence_system();
-          st_release_sys(p.signal_flag, p.signal_value);
+          // signal_value == 0: counting flag (graph-replay safe: +1 per completed hand-off)
+          if (p.signal_value == 0u) atomicAdd_system(p.signal_flag, 1u);
+          else st_release_sys(p.signal_flag, p.signal_value);
         }
       }
     }

@@ -59,8 +59,10 @@ cudaError_t sample_launch(const float* logits, int B, int V, const float* temper
 
 // ---- p2p.cu
 cudaError_t wait_flag_launch(const uint32_t* flag, uint32_t expected, uint32_t* error_flag, cudaStream_t s);
+cudaError_t wait_flag_counter_launch(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag, cudaStream_t s);
 cudaError_t set_flag_launch(uint32_t* flag, uint32_t value, cudaStream_t s);
-cudaError_t copy_signal_launch(const void* src, void* dst, size_t bytes, uint32_t* flag, uint32_t value, cudaStream_t s);
+cudaError_t copy_signal_launch(const void* src, void* dst, size_t bytes, uint32_t* flag, uint32_t value,
+                               unsigned int* done_counter, cudaStream_t s);
 cudaError_t advance_meta_launch(int* positions, int* context_lens, int* slots, const int* block_tables, int max_blocks,
                                 int page, int B, cudaStream_t s);
 

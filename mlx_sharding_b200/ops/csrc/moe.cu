@@ -240,7 +240,8 @@ __global__ void moe_combine_kernel(const float* __restrict__ y_perm, const int* 
       if (done == gridDim.x) {
         *done_counter = 0u;
         __threadfence_system();
-        st_release_sys(signal_flag, signal_value);
+        if (signal_value == 0u) atomicAdd_system(signal_flag, 1u);
+        else st_release_sys(signal_flag, signal_value);
       }
     }
   }

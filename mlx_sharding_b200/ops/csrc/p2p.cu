@@ -31,6 +31,23 @@ __global__ void wait_flag_kernel(const uint32_t* flag, uint32_t expected, uint32
   }
 }
 
+// Counting variant for CUDA-graph replay: the expected value is this consumer's own arrival count, kept in
+// device memory (`local_counter`), so the same captured node is correct on every replay.
+__global__ void wait_flag_counter_kernel(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag,
+                                         unsigned long long timeout_ns) {
+  const uint32_t expected = atomicAdd(local_counter, 1u) + 1u;
+  const unsigned long long t0 = globaltimer_ns();
+  while (true) {
+    const uint32_t v = ld_acquire_sys(flag);
+    if ((int32_t)(v - expected) >= 0) break;
+    if (globaltimer_ns() - t0 > timeout_ns) {
+      if (error_flag != nullptr) atomicExch(error_flag, 1u);
+      break;
+    }
+    __nanosleep(32);
+  }
+}
+
 __global__ void set_flag_kernel(uint32_t* flag, uint32_t value) {
   __threadfence_system();
   st_release_sys(flag, value);
@@ -47,7 +64,8 @@ __global__ void copy_signal_kernel(const uint4* __restrict__ src, uint4* __restr
     if (done == gridDim.x) {
       *done_counter = 0u;
       __threadfence_system();
-      st_release_sys(flag, value);
+      if (value == 0u) atomicAdd_system(flag, 1u);
+      else st_release_sys(flag, value);
     }
   }
 }
@@ -63,12 +81,15 @@ __global__ void advance_meta_kernel(int* positions, int* context_lens, int* slot
   slots[b] = block_tables[(size_t)b * max_blocks + p / page] * page + p % page;
 }
 
-unsigned int* g_copy_counter = nullptr;
-
 }  // namespace
 
 cudaError_t wait_flag_launch(const uint32_t* flag, uint32_t expected, uint32_t* error_flag, cudaStream_t s) {
   wait_flag_kernel<<<1, 1, 0, s>>>(flag, expected, error_flag, 20ull * 1000ull * 1000ull * 1000ull);
+  return cudaGetLastError();
+}
+
+cudaError_t wait_flag_counter_launch(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag, cudaStream_t s) {
+  wait_flag_counter_kernel<<<1, 1, 0, s>>>(flag, local_counter, error_flag, 20ull * 1000ull * 1000ull * 1000ull);
   return cudaGetLastError();
 }
 
@@ -77,18 +98,14 @@ cudaError_t set_flag_launch(uint32_t* flag, uint32_t value, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t copy_signal_launch(const void* src, void* dst, size_t bytes, uint32_t* flag, uint32_t value, cudaStream_t s) {
+cudaError_t copy_signal_launch(const void* src, void* dst, size_t bytes, uint32_t* flag, uint32_t value,
+                               unsigned int* done_counter, cudaStream_t s) {
   if (bytes % 16) return cudaErrorInvalidValue;
-  if (g_copy_counter == nullptr) {
-    cudaError_t e = cudaMalloc(&g_copy_counter, sizeof(unsigned int));
-    if (e != cudaSuccess) return e;
-    cudaMemset(g_copy_counter, 0, sizeof(unsigned int));
-  }
   const size_t nvec = bytes / 16;
   int grid = (int)((nvec + 255) / 256);
   if (grid > 296) grid = 296;
   if (grid < 1) grid = 1;
-  copy_signal_kernel<<<grid, 256, 0, s>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), nvec, flag, value, g_copy_counter);
+  copy_signal_kernel<<<grid, 256, 0, s>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), nvec, flag, value, done_counter);
   return cudaGetLastError();
 }
 

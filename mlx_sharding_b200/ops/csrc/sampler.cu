@@ -78,7 +78,7 @@ sample_kernel(const float* __restrict__ logits, int V, const float* __restrict__
   int token = am.i;
   if (temp > 0.f) {
     const float inv_t = 1.0f / temp;
-    float thresh = -INFINITY;  // keep logits >= thresh
+    float thresh = -INFINITY;  // keep logits > thresh
     if (tp > 0.f && tp < 1.f) {
       // Z at temperature
       float zs = 0.f;
@@ -98,13 +98,13 @@ sample_kernel(const float* __restrict__ logits, int V, const float* __restrict__
         ms = block_sum(ms, sm_f);
         if (ms > target) hi = mid; else lo = mid;
       }
-      thresh = hi;
+      thresh = lo;  // F(lo) <= target < F(hi): everything strictly above lo is in the nucleus
     }
     // Gumbel-max over the kept set: argmax (logit / T + g), g = -log(-log(u))
     ArgMax gm{-INFINITY, 0x7fffffff};
     for (int i = threadIdx.x; i < V; i += kSampThreads) {
       const float x = lg[i];
-      if (x >= thresh) {
+      if (x > thresh) {
         const float u = uniform01(seed, step, b, i);
         const float g = -__logf(-__logf(u));
         gm = better(gm, ArgMax{(x - am.v) * inv_t + g, i});

@@ -48,6 +48,28 @@ class StageExecutor:
                           None if so.top_logprobs is None else so.top_logprobs.tolist())
 
 
+def _pinned_to(t: torch.Tensor, device) -> torch.Tensor:
+    """Host tensor -> device through pinned memory (async copy on the current stream)."""
+    if torch.device(device).type != "cuda":
+        return t
+    return t.pin_memory().to(device, non_blocking=True)
+
+
+def stage_inputs(inp: StepInput, device):
+    """H2D transfer of one step's inputs (token ids + packed metadata); returns (tokens, meta, bytes)."""
+    m = inp.meta
+    if torch.device(device).type != "cuda":
+        return inp.tokens, m, 0
+    parts = [m.positions, m.slot_mapping, m.cu_seqlens, m.context_lens, m.last_idx, m.block_tables.reshape(-1)]
+    sizes = [p.numel() for p in parts]
+    flat = _pinned_to(torch.cat([p.to(torch.int32) for p in parts]), device)
+    v = list(torch.split(flat, sizes))
+    meta = BatchMeta(v[0], v[1], v[2], v[3], v[5].view(m.block_tables.shape), v[4], m.num_tokens, m.num_seqs,
+                     m.max_q_len, m.max_ctx_len, m.page_size)
+    toks = _pinned_to(inp.tokens, device)
+    return toks, meta, flat.numel() * 4 + toks.numel() * 8
+
+
 class LocalPipeline:
     """All stages in-process, executed back to back."""
 
@@ -55,17 +77,22 @@ class LocalPipeline:
         assert stages[0].model.spec.is_first and stages[-1].model.spec.is_last
         self.stages = stages
         self.num_stages = 1  # one executor thread: a single micro-batch group keeps it busy
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
 
     @classmethod
     def from_models(cls, models, num_pages: int, page_size: int = 64, seed: int = 0):
         return cls([StageExecutor(m, num_pages, page_size, seed) for m in models])
 
     def submit(self, inp: StepInput):
-        x = inp.tokens.to(self.stages[0].device)
-        for st in self.stages:
-            meta = inp.meta.to(st.device)
+        x, meta0, nbytes = stage_inputs(inp, self.stages[0].device)
+        self.h2d_bytes += nbytes
+        for i, st in enumerate(self.stages):
+            meta = meta0 if i == 0 or st.device == self.stages[0].device else inp.meta.to(st.device)
             x = st.forward(x.to(st.device), meta)
-        return self.stages[-1].sample(x, inp.params, inp.contexts)
+        out = self.stages[-1].sample(x, inp.params, inp.contexts)
+        self.d2h_bytes += len(out.tokens) * 12  # int64 token id + fp32 logprob per sequence
+        return out
 
     def wait(self, handle) -> StepOutput:
         return handle
@@ -92,11 +119,15 @@ class ChainPipeline:
         self.rank = transport.rank
         assert self.rank == 0 and stage.model.spec.is_first
         self._pending = deque()
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
 
     def submit(self, inp: StepInput):
         tp = self.tp
-        meta = inp.meta.to(self.stage.device)
-        x = self.stage.forward(inp.tokens.to(self.stage.device), meta)
+        toks, meta, nbytes = stage_inputs(inp, self.stage.device)
+        self.h2d_bytes += nbytes
+        x = self.stage.forward(toks, meta)
+        self.d2h_bytes += len(inp.seq_ids) * 12
         if self.num_stages == 1:
             return ("local", self.stage.sample(x, inp.params, inp.contexts))
         tp.send_ctrl(_ctrl_of(inp), 1)
