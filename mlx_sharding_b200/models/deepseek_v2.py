@@ -100,11 +100,9 @@ class DeepseekV2Stage(StageModel):
             q = O.linear(O.rmsnorm(qa[:, :ql], w["q_a_ln"], c.rms_norm_eps), w["q_b"])
             ckv, k_pe = qa[:, ql: ql + lr], qa[:, ql + lr:]
         q = q.view(T, nh, qd) if q.is_contiguous() else q.unflatten(1, (nh, qd))
-        k_pe = k_pe.unflatten(1, (1, rd))
-        O.rope_(q, meta.positions, self.rope, nope)
-        O.rope_(k_pe, meta.positions, self.rope, 0)
         kv = O.linear(O.rmsnorm(ckv, w["kv_a_ln"], c.rms_norm_eps), w["kv_b"]).view(T, nh, nope + vd)
-        O.kv_write_mla(kv, k_pe.squeeze(1), kpool, vpool, meta.slot_mapping, nope, vd)
+        # rope(q_pe), rope(k_pe) and the cache append K=[k_nope|k_pe], V: one fused launch
+        O.mla_rope_kv_write(q, k_pe, kv, kpool, vpool, meta, self.rope, nope, vd)
         attn = O.paged_attention(q, kpool, vpool, meta, c.attn_scale, 0.0)
         h = O.linear(attn.reshape(T, nh * vd), w["o"], residual=h)
         normed = O.rmsnorm(h, w["post_ln"], c.rms_norm_eps)

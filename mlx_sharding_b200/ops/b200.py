@@ -179,3 +179,10 @@ def sample(logits, temperature, top_p, generator: Optional[torch.Generator] = No
     if top_logprobs > 0:
         return toks, lp, ti, tl
     return toks, lp, None, None
+
+
+def mla_rope_kv_write(q, k_pe, kv, kpool, vpool, meta: BatchMeta, spec: RopeSpec, nope: int, vdim: int):
+    if not spec.interleaved:
+        raise NotImplementedError("fused MLA prologue expects interleaved (traditional) rope pairs")
+    C().mla_rope_kv_write(q, k_pe, kv, kpool, vpool, meta.slot_mapping, meta.positions, spec.inv_freq, float(spec.mscale),
+                          int(nope), int(vdim))

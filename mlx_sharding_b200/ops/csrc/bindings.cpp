@@ -198,6 +198,19 @@ void kv_write_mla(const Tensor& kv, const Tensor& kpe, Tensor kpool, Tensor vpoo
                                     (int)kv.size(0), cur_stream()));
 }
 
+void mla_rope_kv_write(Tensor q, const Tensor& kpe, const Tensor& kv, Tensor kpool, Tensor vpool, const Tensor& slots,
+                       const Tensor& positions, const Tensor& inv_freq, double mscale, int64_t nope, int64_t vd) {
+  check_bf16(q, "q"); check_bf16(kpe, "kpe"); check_bf16(kv, "kv");
+  TORCH_CHECK(q.dim() == 3 && q.stride(2) == 1 && kpe.dim() == 2 && kpe.stride(1) == 1);
+  TORCH_CHECK(kv.dim() == 3 && kv.stride(2) == 1 && kv.stride(1) == kv.size(2) && kpool.is_contiguous() && vpool.is_contiguous());
+  TORCH_CHECK(slots.scalar_type() == torch::kInt32 && positions.scalar_type() == torch::kInt32 && inv_freq.scalar_type() == torch::kFloat32);
+  const c10::cuda::CUDAGuard guard(q.device());
+  LAUNCH_OK(b200::mla_rope_kv_launch(q.data_ptr(), q.stride(0), q.stride(1), kpe.data_ptr(), kpe.stride(0), kv.data_ptr(), kv.stride(0),
+                                     kpool.data_ptr(), vpool.data_ptr(), slots.data_ptr<int>(), positions.data_ptr<int>(),
+                                     inv_freq.data_ptr<float>(), (float)mscale, (int)q.size(1), (int)nope, (int)kpe.size(1), (int)vd,
+                                     (int)kpool.size(2), (int)q.size(0), cur_stream()));
+}
+
 // ---- attention --------------------------------------------------------------------------------------------------
 Tensor paged_attention(const Tensor& q, const Tensor& kpool, const Tensor& vpool, const Tensor& block_tables, const Tensor& positions,
                        const Tensor& token_seq, double scale, double softcap, int64_t max_ctx) {
@@ -367,6 +380,56 @@ void advance_meta(Tensor positions, Tensor context_lens, Tensor slots, const Ten
                                     (int)block_tables.size(1), (int)page, (int)positions.numel(), cur_stream()));
 }
 
+// ---- expert parallel --------------------------------------------------------------------------------------------
+std::vector<unsigned long long> to_u64(const std::vector<int64_t>& v) {
+  std::vector<unsigned long long> o(v.size());
+  for (size_t i = 0; i < v.size(); ++i) o[i] = (unsigned long long)v[i];
+  return o;
+}
+void ep_dispatch(const Tensor& x, const Tensor& idx, int64_t experts_per_rank, int64_t my_rank, int64_t cap,
+                 std::vector<int64_t> recv_x, std::vector<int64_t> recv_meta, std::vector<int64_t> recv_count,
+                 std::vector<int64_t> recv_flag, Tensor send_counts, Tensor done_counter) {
+  check_bf16(x, "x"); check_rows(x, "x");
+  TORCH_CHECK(idx.scalar_type() == torch::kInt32 && idx.is_contiguous() && idx.dim() == 2);
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int world = (int)recv_x.size();
+  auto a = to_u64(recv_x), b = to_u64(recv_meta), c = to_u64(recv_count), d = to_u64(recv_flag);
+  LAUNCH_OK(b200::ep_dispatch_launch(x.data_ptr(), x.stride(0), idx.data_ptr<int>(), (int)idx.numel(), (int)idx.size(1), (int)x.size(1),
+                                     (int)experts_per_rank, world, (int)my_rank, (int)cap, a.data(), b.data(), c.data(), d.data(),
+                                     send_counts.data_ptr<int>(), reinterpret_cast<unsigned int*>(done_counter.data_ptr<int>()),
+                                     cur_stream()));
+}
+std::vector<Tensor> ep_regroup(int64_t flag_ptr, int64_t counter_ptr, int64_t error_ptr, int64_t recv_count_ptr, int64_t recv_meta_ptr,
+                               int64_t recv_x_ptr, int64_t world, int64_t cap, int64_t E_local, int64_t H, int64_t device) {
+  auto dev = torch::Device(torch::kCUDA, (int)device);
+  const c10::cuda::CUDAGuard guard(dev);
+  auto io = torch::dtype(torch::kInt32).device(dev);
+  const int64_t R = world * cap;
+  Tensor offs = torch::empty({E_local + 1}, io), row_perm = torch::empty({R}, io), total = torch::empty({1}, io);
+  Tensor perm_src = torch::empty({R, 2}, io);
+  Tensor x_perm = torch::empty({R, H}, torch::dtype(torch::kBFloat16).device(dev));
+  LAUNCH_OK(b200::ep_regroup_launch(reinterpret_cast<const uint32_t*>(flag_ptr), reinterpret_cast<uint32_t*>(counter_ptr),
+                                    reinterpret_cast<uint32_t*>(error_ptr), reinterpret_cast<const int*>(recv_count_ptr),
+                                    reinterpret_cast<const void*>(recv_meta_ptr), reinterpret_cast<const void*>(recv_x_ptr), (int)world,
+                                    (int)cap, (int)E_local, (int)H, offs.data_ptr<int>(), row_perm.data_ptr<int>(), total.data_ptr<int>(),
+                                    x_perm.data_ptr(), perm_src.data_ptr(), cur_stream()));
+  ++g_launches;
+  return {offs, total, x_perm, perm_src};
+}
+void ep_return(const Tensor& y_perm, const Tensor& perm_src, const Tensor& total_rows, std::vector<int64_t> ret_y,
+               std::vector<int64_t> ret_flag, Tensor done_counter) {
+  TORCH_CHECK(y_perm.scalar_type() == torch::kFloat32 && y_perm.is_contiguous());
+  const c10::cuda::CUDAGuard guard(y_perm.device());
+  auto a = to_u64(ret_y), b = to_u64(ret_flag);
+  LAUNCH_OK(b200::ep_return_launch(y_perm.data_ptr<float>(), perm_src.data_ptr(), total_rows.data_ptr<int>(), (int)y_perm.size(0),
+                                   (int)y_perm.size(1), (int)ret_y.size(), a.data(), b.data(),
+                                   reinterpret_cast<unsigned int*>(done_counter.data_ptr<int>()), cur_stream()));
+}
+void ep_wait_all(int64_t flag_ptr, int64_t counter_ptr, int64_t world, int64_t error_ptr) {
+  LAUNCH_OK(b200::ep_wait_all_launch(reinterpret_cast<const uint32_t*>(flag_ptr), reinterpret_cast<uint32_t*>(counter_ptr), (int)world,
+                                     reinterpret_cast<uint32_t*>(error_ptr), cur_stream()));
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -382,6 +445,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("bits") = 0, py::arg("group") = 64, py::arg("scale") = 1.0);
   m.def("kv_write", &kv_write);
   m.def("kv_write_mla", &kv_write_mla);
+  m.def("mla_rope_kv_write", &mla_rope_kv_write);
   m.def("paged_attention", &paged_attention);
   m.def("moe_route", &moe_route);
   m.def("moe_permute", &moe_permute);
@@ -398,6 +462,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("set_flag", &set_flag);
   m.def("copy_signal", &copy_signal);
   m.def("advance_meta", &advance_meta);
+  m.def("ep_dispatch", &ep_dispatch);
+  m.def("ep_regroup", &ep_regroup);
+  m.def("ep_return", &ep_return);
+  m.def("ep_wait_all", &ep_wait_all);
   m.def("init_scratch", &init_scratch);
   m.def("launch_count", []() { return g_launches; });
   m.def("sm_arch", []() { return std::string("sm_100a"); });

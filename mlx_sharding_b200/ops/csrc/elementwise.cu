@@ -273,4 +273,66 @@ cudaError_t kv_write_mla_launch(const void* kv, long long kv_ld_t, const void* k
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ fused MLA prologue
+// DeepSeek-V2 attention prologue in ONE launch (replaces rope(q) + rope(k_pe) + kv_write_mla):
+//   * rotates the rope slice of every q head in place (interleaved pairs, YaRN inv_freq, mscale),
+//   * assembles K = [k_nope | rope(k_pe)] and V straight into the paged cache.
+// One thread per 32-bit word (= one interleaved pair) of the rope parts, one per 16 B vector of the copies.
+__global__ void mla_rope_kv_kernel(__nv_bfloat16* __restrict__ q, long long q_ld_t, long long q_ld_h,
+                                   const __nv_bfloat16* __restrict__ kpe, long long pe_ld_t,
+                                   const __nv_bfloat16* __restrict__ kv, long long kv_ld_t,
+                                   __nv_bfloat16* __restrict__ kpool, __nv_bfloat16* __restrict__ vpool,
+                                   const int* __restrict__ slots, const int* __restrict__ positions,
+                                   const float* __restrict__ inv_freq, float mscale, int heads, int nope, int rd, int vd,
+                                   int page, int T) {
+  const int half = rd / 2, vn = nope / 8, vv = vd / 8;
+  const int per = half + vn + half + vv;  // work items per (token, head)
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)T * heads * per) return;
+  const int c = idx % per;
+  const int h = (idx / per) % heads;
+  const int t = idx / ((long long)per * heads);
+  const int dk = nope + rd;
+  const int slot = slots[t];
+  const size_t pg = slot / page, off = slot % page;
+  __nv_bfloat16* krow = kpool + ((pg * heads + h) * page + off) * dk;
+  const __nv_bfloat16* src = kv + (size_t)t * kv_ld_t + (size_t)h * (nope + vd);
+  if (c < half) {  // q rope pair
+    float sn, cs;
+    sincosf((float)positions[t] * inv_freq[c], &sn, &cs);
+    uint32_t* w = reinterpret_cast<uint32_t*>(q + (size_t)t * q_ld_t + (size_t)h * q_ld_h + nope) + c;
+    const uint32_t u = *w;
+    const float a = bf16_lo(u) * mscale, b = bf16_hi(u) * mscale;
+    *w = pack_bf16(a * cs - b * sn, a * sn + b * cs);
+  } else if (c < half + vn) {  // k_nope copy
+    const int v = c - half;
+    reinterpret_cast<uint4*>(krow)[v] = reinterpret_cast<const uint4*>(src)[v];
+  } else if (c < half + vn + half) {  // k_pe rope pair -> cache (shared by all heads, rotated per head write)
+    const int i = c - half - vn;
+    float sn, cs;
+    sincosf((float)positions[t] * inv_freq[i], &sn, &cs);
+    const uint32_t u = reinterpret_cast<const uint32_t*>(kpe + (size_t)t * pe_ld_t)[i];
+    const float a = bf16_lo(u) * mscale, b = bf16_hi(u) * mscale;
+    reinterpret_cast<uint32_t*>(krow + nope)[i] = pack_bf16(a * cs - b * sn, a * sn + b * cs);
+  } else {  // v copy
+    const int v = c - half - vn - half;
+    __nv_bfloat16* vrow = vpool + ((pg * heads + h) * page + off) * vd;
+    reinterpret_cast<uint4*>(vrow)[v] = reinterpret_cast<const uint4*>(src + nope)[v];
+  }
+}
+
+cudaError_t mla_rope_kv_launch(void* q, long long q_ld_t, long long q_ld_h, const void* kpe, long long pe_ld_t, const void* kv,
+                               long long kv_ld_t, void* kpool, void* vpool, const int* slots, const int* positions,
+                               const float* inv_freq, float mscale, int heads, int nope, int rd, int vd, int page, int T,
+                               cudaStream_t s) {
+  if (T == 0) return cudaSuccess;
+  if ((nope % 8) || (rd % 8) || (vd % 8) || (kv_ld_t % 8) || (pe_ld_t % 2) || (q_ld_t % 2) || (q_ld_h % 2)) return cudaErrorInvalidValue;
+  const long long n = (long long)T * heads * (rd + nope / 8 + vd / 8);
+  mla_rope_kv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+      static_cast<__nv_bfloat16*>(q), q_ld_t, q_ld_h, static_cast<const __nv_bfloat16*>(kpe), pe_ld_t,
+      static_cast<const __nv_bfloat16*>(kv), kv_ld_t, static_cast<__nv_bfloat16*>(kpool), static_cast<__nv_bfloat16*>(vpool),
+      slots, positions, inv_freq, mscale, heads, nope, rd, vd, page, T);
+  return cudaGetLastError();
+}
+
 }  // namespace b200

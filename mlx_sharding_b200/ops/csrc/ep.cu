@@ -1,0 +1,240 @@
+// Expert-parallel MoE all-to-all over NVSwitch peer memory (SURVEY §2.4 "EP", §2.6 K11-EP, BASELINE config 5).
+//
+// The reference keeps all 64 routed experts of a layer on one stage (`mx.gather_qmm`); there is no
+// collective anywhere in it.  Here the experts of every MoE layer can be sharded across the ranks of one
+// NVSwitch domain and the token exchange is done by our own kernels — no NCCL call, no host hop:
+//
+//   dispatch  : every (token, k) pair whose expert lives on rank r is written *directly* into r's receive
+//               region for this source (peer-mapped memory, 16 B stores), together with a (local expert,
+//               source pair) record; the last CTA publishes the per-destination row counts and bumps each
+//               destination's flag (release.sys).
+//   regroup   : the destination buckets what it received by local expert (offsets + gather) so the swap-AB
+//               grouped tcgen05 GEMMs run on contiguous rows.
+//   return    : each expert-output row is pushed straight back into the source rank's return buffer at the
+//               pair's original index; the last CTA bumps the sources' flags.  The source then finishes with
+//               the ordinary weighted combine (+ residual) over its own pairs.
+//
+// Counting flags + device-resident arrival counters make every step CUDA-graph replay safe.  Buffer reuse
+// is race-free by construction: a source only dispatches layer l+1 after it has combined layer l, which
+// requires every destination to have regrouped (consumed) layer l.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int kMaxWorld = 16;
+
+struct PeerTable {
+  unsigned long long p[kMaxWorld];
+};
+
+// ---------------------------------------------------------------------------------------------- dispatch
+// one warp per (token, k) pair
+__global__ void ep_dispatch_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const int* __restrict__ idx, int npairs,
+                                   int top_k, int H, int experts_per_rank, int world, int my_rank, int cap,
+                                   PeerTable recv_x,      // per dst: base of [world][cap][H] bf16 (its receive regions)
+                                   PeerTable recv_meta,   // per dst: base of [world][cap] int2
+                                   PeerTable recv_count,  // per dst: base of [world] int
+                                   PeerTable recv_flag,   // per dst: uint32 flag (counting)
+                                   int* __restrict__ send_counts, unsigned int* __restrict__ done_counter) {
+  const int warps_per_cta = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = H / 8;
+  for (int p = blockIdx.x * warps_per_cta + warp; p < npairs; p += gridDim.x * warps_per_cta) {
+    const int e = idx[p];
+    const int dst = e / experts_per_rank;
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(&send_counts[dst], 1);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot < cap) {
+      const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)(p / top_k) * ld_x);
+      uint4* drow = reinterpret_cast<uint4*>(recv_x.p[dst]) + ((size_t)my_rank * cap + slot) * nvec;
+      for (int v = lane; v < nvec; v += 32) drow[v] = src[v];
+      if (lane == 0) {
+        int2* m = reinterpret_cast<int2*>(recv_meta.p[dst]) + (size_t)my_rank * cap + slot;
+        *m = make_int2(e - dst * experts_per_rank, p);
+      }
+    }
+  }
+  // publish: last CTA writes the row counts into every destination and raises its flag
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) + 1u == gridDim.x);
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    for (int r = threadIdx.x; r < world; r += blockDim.x) {
+      int c = __ldcg(&send_counts[r]);
+      if (c > cap) c = cap;
+      reinterpret_cast<int*>(recv_count.p[r])[my_rank] = c;
+      send_counts[r] = 0;
+      __threadfence_system();
+      atomicAdd_system(reinterpret_cast<unsigned int*>(recv_flag.p[r]), 1u);
+    }
+    if (threadIdx.x == 0) *done_counter = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- regroup
+// single CTA: wait for all sources, bucket received rows by local expert
+__global__ void __launch_bounds__(1024)
+ep_regroup_offsets_kernel(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag, unsigned long long timeout_ns,
+                          const int* __restrict__ recv_count, const int2* __restrict__ recv_meta, int world, int cap,
+                          int E_local, int* __restrict__ expert_offsets, int* __restrict__ row_perm /*[world*cap]*/,
+                          int* __restrict__ total_rows) {
+  __shared__ int cnt[256], cur[256];
+  __shared__ int counts[kMaxWorld];
+  if (threadIdx.x == 0) {
+    // every source bumps the flag once per step: wait until `world` more arrivals than we have consumed
+    const uint32_t expected = atomicAdd(local_counter, (uint32_t)world) + (uint32_t)world;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    while (true) {
+      const uint32_t v = ld_acquire_sys(flag);
+      if ((int32_t)(v - expected) >= 0) break;
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) { if (error_flag) atomicExch(error_flag, 1u); break; }
+      __nanosleep(32);
+    }
+    __threadfence_system();
+  }
+  for (int e = threadIdx.x; e < E_local; e += blockDim.x) cnt[e] = 0;
+  __syncthreads();
+  if (threadIdx.x < world) counts[threadIdx.x] = __ldcv(&recv_count[threadIdx.x]);
+  __syncthreads();
+  for (int s = 0; s < world; ++s)
+    for (int j = threadIdx.x; j < counts[s]; j += blockDim.x) atomicAdd(&cnt[__ldcv(&recv_meta[(size_t)s * cap + j].x)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int e = 0; e < E_local; ++e) { cur[e] = acc; expert_offsets[e] = acc; acc += cnt[e]; }
+    expert_offsets[E_local] = acc;
+    *total_rows = acc;
+  }
+  __syncthreads();
+  for (int s = 0; s < world; ++s)
+    for (int j = threadIdx.x; j < counts[s]; j += blockDim.x)
+      row_perm[(size_t)s * cap + j] = atomicAdd(&cur[__ldcv(&recv_meta[(size_t)s * cap + j].x)], 1);
+}
+
+// gather received rows into expert-contiguous order; remember where each permuted row came from
+__global__ void ep_regroup_gather_kernel(const __nv_bfloat16* __restrict__ recv_x, const int2* __restrict__ recv_meta,
+                                         const int* __restrict__ recv_count, const int* __restrict__ row_perm, int world, int cap,
+                                         int H, __nv_bfloat16* __restrict__ x_perm, int2* __restrict__ perm_src /*(src rank, src pair)*/) {
+  const int nvec = H / 8;
+  const int s = blockIdx.y;
+  const int n = recv_count[s];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)n * nvec; i += (long long)gridDim.x * blockDim.x) {
+    const int j = i / nvec, v = i % nvec;
+    const int row = row_perm[(size_t)s * cap + j];
+    reinterpret_cast<uint4*>(x_perm + (size_t)row * H)[v] =
+        __ldcv(reinterpret_cast<const uint4*>(recv_x + ((size_t)s * cap + j) * H) + v);
+    if (v == 0) perm_src[row] = make_int2(s, recv_meta[(size_t)s * cap + j].y);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- return
+// one warp per permuted row: push the fp32 expert output back to its source rank
+__global__ void ep_return_kernel(const float* __restrict__ y_perm, const int2* __restrict__ perm_src, const int* __restrict__ total_rows,
+                                 int H, int world, PeerTable ret_y /*per src: [pairs][H] fp32*/, PeerTable ret_flag,
+                                 unsigned int* __restrict__ done_counter) {
+  const int warps_per_cta = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = *total_rows;
+  const int nvec = H / 4;
+  for (int r = blockIdx.x * warps_per_cta + warp; r < n; r += gridDim.x * warps_per_cta) {
+    const int2 sp = perm_src[r];
+    const float4* src = reinterpret_cast<const float4*>(y_perm + (size_t)r * H);
+    float4* dst = reinterpret_cast<float4*>(ret_y.p[sp.x]) + (size_t)sp.y * nvec;
+    for (int v = lane; v < nvec; v += 32) dst[v] = src[v];
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) + 1u == gridDim.x);
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    for (int r = threadIdx.x; r < world; r += blockDim.x) atomicAdd_system(reinterpret_cast<unsigned int*>(ret_flag.p[r]), 1u);
+    if (threadIdx.x == 0) *done_counter = 0u;
+  }
+}
+
+// source side: wait until every rank has returned its share
+__global__ void ep_wait_all_kernel(const uint32_t* flag, uint32_t* local_counter, int world, uint32_t* error_flag,
+                                   unsigned long long timeout_ns) {
+  const uint32_t expected = atomicAdd(local_counter, (uint32_t)world) + (uint32_t)world;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  while (true) {
+    const uint32_t v = ld_acquire_sys(flag);
+    if ((int32_t)(v - expected) >= 0) break;
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    if (t1 - t0 > timeout_ns) { if (error_flag) atomicExch(error_flag, 1u); break; }
+    __nanosleep(32);
+  }
+  __threadfence_system();
+}
+
+constexpr unsigned long long kTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+PeerTable make_table(const unsigned long long* v, int world) {
+  PeerTable t;
+  for (int i = 0; i < kMaxWorld; ++i) t.p[i] = i < world ? v[i] : 0ull;
+  return t;
+}
+
+}  // namespace
+
+cudaError_t ep_dispatch_launch(const void* x, long long ld_x, const int* idx, int npairs, int top_k, int H, int experts_per_rank,
+                               int world, int my_rank, int cap, const unsigned long long* recv_x, const unsigned long long* recv_meta,
+                               const unsigned long long* recv_count, const unsigned long long* recv_flag, int* send_counts,
+                               unsigned int* done_counter, cudaStream_t s) {
+  if (world > kMaxWorld || (H % 8)) return cudaErrorInvalidValue;
+  int grid = (npairs + 7) / 8;
+  if (grid < 1) grid = 1;
+  if (grid > 592) grid = 592;
+  ep_dispatch_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ld_x, idx, npairs, top_k, H, experts_per_rank, world,
+                                          my_rank, cap, make_table(recv_x, world), make_table(recv_meta, world),
+                                          make_table(recv_count, world), make_table(recv_flag, world), send_counts, done_counter);
+  return cudaGetLastError();
+}
+
+cudaError_t ep_regroup_launch(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag, const int* recv_count,
+                              const void* recv_meta, const void* recv_x, int world, int cap, int E_local, int H, int* expert_offsets,
+                              int* row_perm, int* total_rows, void* x_perm, void* perm_src, cudaStream_t s) {
+  if (E_local > 256 || world > kMaxWorld) return cudaErrorInvalidValue;
+  ep_regroup_offsets_kernel<<<1, 1024, 0, s>>>(flag, local_counter, error_flag, kTimeoutNs, recv_count,
+                                               static_cast<const int2*>(recv_meta), world, cap, E_local, expert_offsets, row_perm,
+                                               total_rows);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  dim3 grid(64, world);
+  ep_regroup_gather_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(recv_x), static_cast<const int2*>(recv_meta), recv_count,
+                                                row_perm, world, cap, H, static_cast<__nv_bfloat16*>(x_perm), static_cast<int2*>(perm_src));
+  return cudaGetLastError();
+}
+
+cudaError_t ep_return_launch(const float* y_perm, const void* perm_src, const int* total_rows, int max_rows, int H, int world,
+                             const unsigned long long* ret_y, const unsigned long long* ret_flag, unsigned int* done_counter,
+                             cudaStream_t s) {
+  if (H % 4) return cudaErrorInvalidValue;
+  int grid = (max_rows + 7) / 8;
+  if (grid < 1) grid = 1;
+  if (grid > 592) grid = 592;
+  ep_return_kernel<<<grid, 256, 0, s>>>(y_perm, static_cast<const int2*>(perm_src), total_rows, H, world, make_table(ret_y, world),
+                                        make_table(ret_flag, world), done_counter);
+  return cudaGetLastError();
+}
+
+cudaError_t ep_wait_all_launch(const uint32_t* flag, uint32_t* local_counter, int world, uint32_t* error_flag, cudaStream_t s) {
+  ep_wait_all_kernel<<<1, 1, 0, s>>>(flag, local_counter, world, error_flag, kTimeoutNs);
+  return cudaGetLastError();
+}
+
+}  // namespace b200

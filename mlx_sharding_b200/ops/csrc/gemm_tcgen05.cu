@@ -22,6 +22,10 @@
 //    NVLink); when `signal_flag` is set the last CTA of the grid publishes it with st.release.sys
 //    after a system-scope fence — GEMM + P2P hand-off in one kernel, no NCCL call, no host hop.
 #include "gemm_tcgen05.h"
+
+#include <mutex>
+#include <unordered_map>
+
 #include "ptx.cuh"
 
 namespace b200 {
@@ -233,12 +237,26 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         if (p.splits > 1) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) { g[j] = 0.f; u[j] = 0.f; }
-          for (int s = 0; s < p.splits; ++s) {
-            const float* w = ws0 + static_cast<size_t>(s) * (BN * (DUAL ? 2 : 1) * kTileM);
+          // deterministic split order, but 2 splits x 16 columns of independent L2 loads are in flight
+          // per thread before they are consumed (the reduction is latency-, not bandwidth-bound)
+          for (int s = 0; s < p.splits; s += 2) {
+            const float* w0 = ws0 + static_cast<size_t>(s) * (BN * (DUAL ? 2 : 1) * kTileM);
+            const bool two = (s + 1) < p.splits;
+            const float* w1 = two ? w0 + (BN * (DUAL ? 2 : 1) * kTileM) : w0;
+            float a0[16], a1[16], b0[16], b1[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              g[j] += __ldcg(&w[(c + j) * kTileM + f_local]);
-              if (DUAL) u[j] += __ldcg(&w[(BN + c + j) * kTileM + f_local]);
+              a0[j] = __ldcg(&w0[(c + j) * kTileM + f_local]);
+              a1[j] = two ? __ldcg(&w1[(c + j) * kTileM + f_local]) : 0.f;
+              if (DUAL) {
+                b0[j] = __ldcg(&w0[(BN + c + j) * kTileM + f_local]);
+                b1[j] = two ? __ldcg(&w1[(BN + c + j) * kTileM + f_local]) : 0.f;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              g[j] = (g[j] + a0[j]) + a1[j];
+              if (DUAL) u[j] = (u[j] + b0[j]) + b1[j];
             }
           }
         } else {
@@ -348,8 +366,38 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Descriptor cache: encoding a tensor map costs a few microseconds of host time; weights (and the static
+// activation buffers of graph-captured steps) are encoded once.
+struct TmapKey {
+  const void* ptr; uint64_t rows, cols, ld; uint32_t box;
+  bool operator==(const TmapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box == o.box; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    h ^= std::hash<uint64_t>()(k.rows * 1000003ull + k.cols) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    h ^= std::hash<uint64_t>()(k.ld * 31ull + k.box) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+std::mutex g_tmap_mutex;
+
+bool encode_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
 // bf16 row-major [rows, cols] (row stride ld elements) -> tiles of box_rows x 64 with 128B swizzle
 bool make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  const TmapKey key{ptr, rows, cols, ld, box_rows};
+  std::lock_guard<std::mutex> lock(g_tmap_mutex);
+  auto it = g_tmap_cache.find(key);
+  if (it != g_tmap_cache.end()) { *m = it->second; return true; }
+  if (!encode_tmap(m, ptr, rows, cols, ld, box_rows)) return false;
+  if (g_tmap_cache.size() > 16384) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *m);
+  return true;
+}
+
+bool encode_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return false;
   cuuint64_t dims[2] = {cols, rows};

@@ -19,6 +19,10 @@ cudaError_t kv_write_launch(const void* k, long long k_ld_t, long long k_ld_h, c
 cudaError_t kv_write_mla_launch(const void* kv, long long kv_ld_t, const void* kpe, long long pe_ld_t, void* kpool,
                                 void* vpool, const int* slots, int heads, int nope, int rd, int vd, int page, int T,
                                 cudaStream_t s);
+cudaError_t mla_rope_kv_launch(void* q, long long q_ld_t, long long q_ld_h, const void* kpe, long long pe_ld_t, const void* kv,
+                               long long kv_ld_t, void* kpool, void* vpool, const int* slots, const int* positions,
+                               const float* inv_freq, float mscale, int heads, int nope, int rd, int vd, int page, int T,
+                               cudaStream_t s);
 
 // ---- attention.cu
 struct PagedAttnArgs {
@@ -65,5 +69,18 @@ cudaError_t copy_signal_launch(const void* src, void* dst, size_t bytes, uint32_
                                unsigned int* done_counter, cudaStream_t s);
 cudaError_t advance_meta_launch(int* positions, int* context_lens, int* slots, const int* block_tables, int max_blocks,
                                 int page, int B, cudaStream_t s);
+
+// ---- ep.cu (expert-parallel all-to-all over peer memory)
+cudaError_t ep_dispatch_launch(const void* x, long long ld_x, const int* idx, int npairs, int top_k, int H, int experts_per_rank,
+                               int world, int my_rank, int cap, const unsigned long long* recv_x, const unsigned long long* recv_meta,
+                               const unsigned long long* recv_count, const unsigned long long* recv_flag, int* send_counts,
+                               unsigned int* done_counter, cudaStream_t s);
+cudaError_t ep_regroup_launch(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag, const int* recv_count,
+                              const void* recv_meta, const void* recv_x, int world, int cap, int E_local, int H, int* expert_offsets,
+                              int* row_perm, int* total_rows, void* x_perm, void* perm_src, cudaStream_t s);
+cudaError_t ep_return_launch(const float* y_perm, const void* perm_src, const int* total_rows, int max_rows, int H, int world,
+                             const unsigned long long* ret_y, const unsigned long long* ret_flag, unsigned int* done_counter,
+                             cudaStream_t s);
+cudaError_t ep_wait_all_launch(const uint32_t* flag, uint32_t* local_counter, int world, uint32_t* error_flag, cudaStream_t s);
 
 }  // namespace b200

@@ -9,7 +9,6 @@ namespace b200 {
 
 namespace {
 
-constexpr int kRouteToks = 8;       // tokens per CTA (share every router-weight read)
 constexpr int kRouteThreads = 256;  // 8 warps
 constexpr int kMaxEPerLane = 8;     // E <= 256
 
@@ -33,6 +32,9 @@ __device__ __forceinline__ void warp_argmax(float& v, int& i) {
   }
 }
 
+// TOKS tokens per CTA share every router-weight read: 8 for prefill-sized batches, 1 for decode batches
+// (more CTAs; the 256 KB router matrix is L2 resident).
+template <int kRouteToks>
 __global__ void __launch_bounds__(kRouteThreads)
 moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv_bfloat16* __restrict__ gw, int T, int H,
                  int E, int top_k, int n_group, int topk_group, float scaling, int norm_topk, int* __restrict__ idx,
@@ -79,7 +81,7 @@ moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv
   // ---- one warp per token: softmax, (group mask), top-k
   const int tk = warp;
   const int t = t0 + tk;
-  if (t >= T) return;
+  if (tk >= kRouteToks || t >= T) return;
   float sc[kMaxEPerLane], sel[kMaxEPerLane];
   float mx = -INFINITY;
 #pragma unroll
@@ -171,20 +173,10 @@ moe_offsets_kernel(const int* __restrict__ idx, int npairs, int E, int* __restri
     expert_offsets[E] = acc;
   }
   __syncthreads();
-  // deterministic placement: pairs of one expert keep their (token, k) order.  One warp per expert scans
-  // the pair list with ballots — npairs is small in decode and this stays off the critical path in prefill.
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int e = warp; e < E; e += nwarps) {
-    if (cnt[e] == 0) continue;
-    int base = cur[e];
-    for (int p0 = 0; p0 < npairs; p0 += 32) {
-      const int p = p0 + lane;
-      const bool mine = (p < npairs) && (idx[p] == e);
-      const unsigned bal = __ballot_sync(0xffffffffu, mine);
-      if (mine) pair_row[p] = base + __popc(bal & ((1u << lane) - 1u));
-      base += __popc(bal);
-    }
-  }
+  // Row placement inside an expert's segment is claimed with shared-memory atomics.  The order is arbitrary
+  // but results do not depend on it: every permuted row is an independent GEMM column and the combine
+  // gathers by (token, k) -> row, so outputs stay bit-identical run to run.
+  for (int p = threadIdx.x; p < npairs; p += blockDim.x) pair_row[p] = atomicAdd(&cur[idx[p]], 1);
 }
 
 __global__ void moe_gather_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const int* __restrict__ pair_row,
@@ -253,16 +245,25 @@ cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, 
                              int topk_group, float scaling, bool norm_topk, int* idx, float* wts, cudaStream_t s) {
   if (T == 0) return cudaSuccess;
   if (E > 32 * kMaxEPerLane || top_k > 32 || (H % 8) || n_group > 32 || (n_group > 1 && E % n_group)) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)kRouteToks * H * 2 + (size_t)kRouteToks * E * 4;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(moe_route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
+  auto xx = static_cast<const __nv_bfloat16*>(x);
+  auto gw = static_cast<const __nv_bfloat16*>(gate_w);
+  if (T <= 1024) {
+    const size_t smem = (size_t)H * 2 + (size_t)E * 4;
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;
+    moe_route_kernel<1><<<T, kRouteThreads, smem, s>>>(xx, ld_x, gw, T, H, E, top_k, n_group, topk_group, scaling,
+                                                       norm_topk ? 1 : 0, idx, wts);
+  } else {
+    constexpr int TOKS = 8;
+    const size_t smem = (size_t)TOKS * H * 2 + (size_t)TOKS * E * 4;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(moe_route_kernel<TOKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured = smem;
+    }
+    moe_route_kernel<TOKS><<<(T + TOKS - 1) / TOKS, kRouteThreads, smem, s>>>(xx, ld_x, gw, T, H, E, top_k, n_group, topk_group,
+                                                                           scaling, norm_topk ? 1 : 0, idx, wts);
   }
-  moe_route_kernel<<<(T + kRouteToks - 1) / kRouteToks, kRouteThreads, smem, s>>>(
-      static_cast<const __nv_bfloat16*>(x), ld_x, static_cast<const __nv_bfloat16*>(gate_w), T, H, E, top_k, n_group,
-      topk_group, scaling, norm_topk ? 1 : 0, idx, wts);
   return cudaGetLastError();
 }
 

@@ -282,3 +282,13 @@ def sample(logits: torch.Tensor, temperature: torch.Tensor, top_p: torch.Tensor,
         tk = torch.topk(logprobs, top_logprobs, dim=-1)
         return tokens, tok_lp, tk.indices, tk.values
     return tokens, tok_lp, None, None
+
+
+def mla_rope_kv_write(q: torch.Tensor, k_pe: torch.Tensor, kv: torch.Tensor, kpool: torch.Tensor, vpool: torch.Tensor,
+                      meta: BatchMeta, spec: RopeSpec, nope: int, vdim: int):
+    """DeepSeek-V2 attention prologue: rope the ``*_pe`` slices (q in place) and append
+    ``K = [k_nope | rope(k_pe)]``, ``V`` to the paged cache (one fused kernel on the b200 backend)."""
+    rope_(q, meta.positions, spec, nope)
+    kp = k_pe.clone().unsqueeze(1)
+    rope_(kp, meta.positions, spec, 0)
+    kv_write_mla(kv, kp.squeeze(1), kpool, vpool, meta.slot_mapping, nope, vdim)

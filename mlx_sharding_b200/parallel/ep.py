@@ -1,0 +1,119 @@
+"""Expert parallelism for DeepSeek MoE blocks with a fused all-to-all over NVSwitch peer memory
+(BASELINE config 5; SURVEY §2.4 "EP", K11-EP).
+
+The reference executes all routed experts of a layer on the stage that owns the layer (``mx.gather_qmm``).
+``ExpertParallelMoE`` shards the ``E`` routed experts of a layer across the ``world`` ranks of one NVSwitch
+domain: rank ``r`` keeps experts ``[r*E/world, (r+1)*E/world)`` (1/world of the MoE weights — the dominant
+HBM stream of a decode step) and every rank routes *its own* tokens.  Token exchange is done by the kernels
+in ``ops/csrc/ep.cu`` — dispatch rows are written straight into the owner's receive region, expert outputs
+are pushed straight back into the source's return buffer, flags use release/acquire at system scope; there
+is no NCCL call and no host involvement on the path.
+
+``forward(x, idx, w, residual)`` == ``ops.moe_experts`` on the un-sharded weights (verified in
+``tests/test_multigpu.py``).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from ..ops.weights import LinearWeight
+
+
+class EPBuffers:
+    """IPC-mapped receive / return buffers of one rank (shared by all MoE layers of that rank)."""
+
+    def __init__(self, hidden: int, max_tokens: int, top_k: int, group=None):
+        from ..ops import b200
+
+        self.C = b200.load_extension()
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.dev = torch.cuda.current_device()
+        self.H, self.top_k = hidden, top_k
+        self.cap = max_tokens * top_k                      # rows one source can send to one destination
+        W, cap, H = self.world, self.cap, hidden
+        self.off_recv_x = 0
+        self.off_recv_meta = self.off_recv_x + W * cap * H * 2
+        self.off_recv_count = self.off_recv_meta + W * cap * 8
+        self.off_ret_y = (self.off_recv_count + W * 4 + 255) // 256 * 256
+        self.off_flags = self.off_ret_y + cap * H * 4
+        total = self.off_flags + 256
+        self.base, handle = self.C.ipc_alloc(total)
+        handles: List = [None] * W
+        dist.all_gather_object(handles, (handle, self.dev), group=group)
+        self.peer = []
+        for r, (h, pdev) in enumerate(handles):
+            if r == self.rank:
+                self.peer.append(self.base)
+            else:
+                if pdev != self.dev:
+                    self.C.enable_peer_access(pdev)
+                self.peer.append(self.C.ipc_open(h))
+        # tables of peer addresses
+        self.t_recv_x = [p + self.off_recv_x for p in self.peer]
+        self.t_recv_meta = [p + self.off_recv_meta for p in self.peer]
+        self.t_recv_count = [p + self.off_recv_count for p in self.peer]
+        self.t_recv_flag = [p + self.off_flags for p in self.peer]
+        self.t_ret_y = [p + self.off_ret_y for p in self.peer]
+        self.t_ret_flag = [p + self.off_flags + 128 for p in self.peer]
+        # device-resident local state: [send_counts(world) | done counters(2) | arrival counters(2) | error]
+        self.state = torch.zeros(W + 8, dtype=torch.int32, device="cuda")
+        self.ret_y = self.C.tensor_from_ptr(self.base + self.off_ret_y, [cap, H], "float32", self.dev)
+        dist.barrier(group=group)
+
+    def error(self) -> bool:
+        return bool(self.state[-1].item())
+
+
+class ExpertParallelMoE:
+    """One MoE layer's routed experts, sharded over the ranks of ``bufs``."""
+
+    def __init__(self, bufs: EPBuffers, Wg: LinearWeight, Wu: LinearWeight, Wd: LinearWeight, num_experts: int,
+                 act: str = "silu", weights_are_local: bool = False):
+        from ..ops import b200
+
+        self.b = bufs
+        self.ops = b200
+        self.E = num_experts
+        assert num_experts % bufs.world == 0
+        self.E_local = num_experts // bufs.world
+        lo, hi = bufs.rank * self.E_local, (bufs.rank + 1) * self.E_local
+        pick = (lambda W: b200._dense(W)) if weights_are_local else (lambda W: b200._dense(W)[lo:hi].contiguous())
+        self.wg, self.wu, self.wd = pick(Wg), pick(Wu), pick(Wd)
+        self.act = b200.ACT_IDS[act]
+
+    def forward(self, x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        b, C = self.b, self.b.C
+        T, k = idx.shape
+        assert T * k <= b.cap, "token batch exceeds the EP buffer capacity"
+        W = b.world
+        st = b.state
+        # 1) dispatch my pairs to the owners of their experts (remote stores + count/flag publication)
+        C.ep_dispatch(x, idx, self.E_local, b.rank, b.cap, b.t_recv_x, b.t_recv_meta, b.t_recv_count, b.t_recv_flag,
+                      st[:W], st[W:W + 1])
+        # 2) wait for every source, bucket what I received by local expert
+        offs, total, x_perm, perm_src = C.ep_regroup(b.base + b.off_flags, st[W + 2:W + 3].data_ptr(), st[-1:].data_ptr(),
+                                                     b.base + b.off_recv_count, b.base + b.off_recv_meta,
+                                                     b.base + b.off_recv_x, W, b.cap, self.E_local, b.H, b.dev)
+        # 3) my experts: grouped swap-AB tcgen05 GEMMs on the received rows
+        max_rows = min(W * T, x_perm.shape[0])  # upper bound of rows one expert can receive (every rank sends <= T)
+        h = C.grouped_linear(x_perm, self.wg, self.wu, offs, max_rows, self.act, False)
+        y = C.grouped_linear(h, self.wd, None, offs, max_rows, 0, True)
+        # 4) push every output row back to the rank / pair it came from
+        C.ep_return(y, perm_src, total, b.t_ret_y, b.t_ret_flag, st[W + 1:W + 2])
+        # 5) wait for all my pairs to come home, weighted combine (+ residual)
+        C.ep_wait_all(b.base + b.off_flags + 128, st[W + 3:W + 4].data_ptr(), W, st[-1:].data_ptr())
+        pair_row = self._identity(T * k, x.device)
+        return C.moe_combine(b.ret_y, pair_row, w, residual, out, int(k), 0, 0)
+
+    _ident = {}
+
+    @classmethod
+    def _identity(cls, n, device):
+        key = (n, str(device))
+        if key not in cls._ident:
+            cls._ident[key] = torch.arange(n, dtype=torch.int32, device=device)
+        return cls._ident[key]

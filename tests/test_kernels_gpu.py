@@ -215,3 +215,22 @@ def test_apply_penalties(B):
     B.apply_penalties_(a, ctx, pen, bidx, bval)
     R.apply_penalties_(b, ctx, pen, bidx, bval)
     close(a, b, 1e-6, 1e-6)
+
+
+def test_mla_rope_kv_write_fused(B):
+    """Fused DeepSeek prologue (rope q_pe in place + assemble K=[k_nope|rope(k_pe)], V into the cache)."""
+    T, nh, nope, rd, vd, page = 37, 16, 128, 64, 128, 16
+    meta, kpool, vpool = _paged_setup([5, 32], [3, 100], nh, nope + rd, vd, page)
+    assert meta.num_tokens == T
+    inv = (1.0 / (10000.0 ** (torch.arange(0, rd, 2, dtype=torch.float32) / rd))).to(DEV)
+    spec = RopeSpec(inv, rd, True, mscale=1.1)
+    big = rnd(T, nh * (nope + rd) + 512 + rd)          # strided q / k_pe slices of one projection output
+    q = big[:, : nh * (nope + rd)].unflatten(1, (nh, nope + rd))
+    kpe = big[:, nh * (nope + rd) + 512:]
+    kv = rnd(T, nh, nope + vd, seed=3)
+    q2, kp2, vp2 = q.clone(), kpool.clone(), vpool.clone()
+    B.mla_rope_kv_write(q, kpe, kv, kpool, vpool, meta, spec, nope, vd)
+    R.mla_rope_kv_write(q2, kpe.clone(), kv, kp2, vp2, meta, spec, nope, vd)
+    close(q, q2, 2e-2, 1e-2)
+    close(kpool, kp2, 2e-2, 1e-2)
+    assert torch.equal(vpool, vp2)
