@@ -72,6 +72,27 @@ def _dense(W: LinearWeight) -> torch.Tensor:
     return _bf16(W.weight)
 
 
+def _qpack(W: LinearWeight):
+    """(packed int32 codes [rows, words], scales_t, biases_t [K/g, rows]) for the in-kernel dequant GEMM, or None
+    when the layout is not supported by the kernel (then the weight is expanded to bf16 once)."""
+    if not W.is_quantized:
+        return None
+    qt = getattr(W, "_qt", None)
+    if qt is None:
+        K = W.in_features
+        if not C().gemm_q_supported(W.bits, W.group_size, K) or W.scales.dtype != torch.bfloat16:
+            W._qt = False
+            return None
+        rows = W.wq.numel() // W.wq.shape[-1]
+        ng = K // W.group_size
+        wq = W.wq.reshape(rows, W.wq.shape[-1]).contiguous()
+        st = W.scales.reshape(rows, ng).t().contiguous()
+        bt = W.biases.reshape(rows, ng).t().contiguous()
+        qt = (wq, st, bt)
+        W._qt = qt
+    return qt or None
+
+
 # ------------------------------------------------------------------------------------------------ ops
 def embed(ids: torch.Tensor, emb: LinearWeight, scale: float = 1.0, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
     ids = ids.to(torch.int64).contiguous()
@@ -94,12 +115,20 @@ def linear(x: torch.Tensor, W: LinearWeight, residual: Optional[torch.Tensor] = 
            signal: Optional[Tuple[int, int]] = None, softcap: float = 0.0) -> torch.Tensor:
     fp32 = out_dtype == torch.float32
     flag, val = signal if signal is not None else (0, 0)
+    q = _qpack(W)
+    if q is not None:
+        return C().linear_q(x, q[0], q[1], q[2], None, None, None, W.bits, W.group_size, W.out_features, residual, W.bias, 0,
+                            float(softcap), fp32, out, 0, int(flag), int(val))
     return C().linear(x, _dense(W), None, residual, W.bias, 0, float(softcap), fp32, out, 0, int(flag), int(val))
 
 
 def gated_up(x: torch.Tensor, Wg: LinearWeight, Wu: LinearWeight, act: str = "silu") -> torch.Tensor:
     if Wg.bias is not None or Wu.bias is not None:
         raise NotImplementedError("gated MLP with bias")
+    qg, qu = _qpack(Wg), _qpack(Wu)
+    if qg is not None and qu is not None:
+        return C().linear_q(x, qg[0], qg[1], qg[2], qu[0], qu[1], qu[2], Wg.bits, Wg.group_size, Wg.out_features, None, None,
+                            ACT_IDS[act], 0.0, False, None, 0, 0, 0)
     return C().linear(x, _dense(Wg), _dense(Wu), None, None, ACT_IDS[act], 0.0, False, None, 0, 0, 0)
 
 
@@ -129,6 +158,11 @@ def _token_seq(meta: BatchMeta) -> torch.Tensor:
 
 
 def paged_attention(q, kpool, vpool, meta: BatchMeta, scale: float, softcap: float = 0.0):
+    c = C()
+    if meta.max_q_len > 1 and not softcap and c.flash_prefill_supported(kpool.shape[3], vpool.shape[3]):
+        # prefill chunk / mixed batch: tensor-core causal flash attention over the paged cache
+        return c.flash_prefill(q, kpool, vpool, meta.block_tables, meta.cu_seqlens, meta.context_lens, float(scale),
+                               int(meta.num_tokens))
     return C().paged_attention(q, kpool, vpool, meta.block_tables, meta.positions, _token_seq(meta), float(scale),
                                float(softcap or 0.0), int(meta.max_ctx_len))
 
@@ -148,11 +182,20 @@ def moe_experts(x, idx, w, Wg: LinearWeight, Wu: LinearWeight, Wd: LinearWeight,
     weighted combine (+ residual [+ P2P store & flag])."""
     c = C()
     T, k = idx.shape
-    wg, wu, wd = _dense(Wg), _dense(Wu), _dense(Wd)
-    E = wg.shape[0]
-    offs, pair_row, xp = c.moe_permute(idx, x, E)
-    h = c.grouped_linear(xp, wg, wu, offs, T, ACT_IDS[act], False)
-    y = c.grouped_linear(h, wd, None, offs, T, 0, True)
+    qg, qu, qd = _qpack(Wg), _qpack(Wu), _qpack(Wd)
+    if qg is not None and qu is not None and qd is not None:
+        E = Wg.wq.shape[0]
+        offs, pair_row, xp = c.moe_permute(idx, x, E)
+        h = c.grouped_linear_q(xp, qg[0], qg[1], qg[2], qu[0], qu[1], qu[2], Wg.bits, Wg.group_size, E, Wg.out_features,
+                               offs, T, ACT_IDS[act], False)
+        y = c.grouped_linear_q(h, qd[0], qd[1], qd[2], None, None, None, Wd.bits, Wd.group_size, E, Wd.out_features, offs, T,
+                               0, True)
+    else:
+        wg, wu, wd = _dense(Wg), _dense(Wu), _dense(Wd)
+        E = wg.shape[0]
+        offs, pair_row, xp = c.moe_permute(idx, x, E)
+        h = c.grouped_linear(xp, wg, wu, offs, T, ACT_IDS[act], False)
+        y = c.grouped_linear(h, wd, None, offs, T, 0, True)
     if extra is not None:
         residual = extra if residual is None else residual + extra
     flag, val = signal if signal is not None else (0, 0)

@@ -141,6 +141,83 @@ Tensor grouped_linear(const Tensor& x, const Tensor& w, const c10::optional<Tens
   return out;
 }
 
+// ---- quantised GEMM (in-kernel MLX affine dequant) ---------------------------------------------------------------
+struct QW { const Tensor& wq; const Tensor& st; const Tensor& bt; };
+void check_q(const Tensor& wq, const Tensor& st, const Tensor& bt, int64_t rows, int64_t K, int64_t bits, int64_t group) {
+  TORCH_CHECK(wq.is_cuda() && wq.scalar_type() == torch::kInt32 && wq.is_contiguous(), "packed weight must be contiguous int32");
+  TORCH_CHECK(wq.numel() == rows * K * bits / 32, "packed weight size mismatch");
+  check_bf16(st, "scales_t"); check_bf16(bt, "biases_t");
+  TORCH_CHECK(st.is_contiguous() && bt.is_contiguous() && st.numel() == rows * (K / group) && bt.numel() == st.numel(), "scales_t/biases_t must be [K/g, rows]");
+}
+Tensor linear_q(const Tensor& x, const Tensor& wq, const Tensor& scales_t, const Tensor& biases_t, const c10::optional<Tensor>& wq2,
+                const c10::optional<Tensor>& scales2_t, const c10::optional<Tensor>& biases2_t, int64_t bits, int64_t group, int64_t N,
+                const c10::optional<Tensor>& residual, const c10::optional<Tensor>& bias, int64_t act, double softcap, bool out_fp32,
+                const c10::optional<Tensor>& out_, int64_t splits, int64_t signal_flag_ptr, int64_t signal_value) {
+  check_bf16(x, "x"); check_rows(x, "x");
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int64_t T = x.size(0), K = x.size(1);
+  check_q(wq, scales_t, biases_t, N, K, bits, group);
+  Tensor out = out_.has_value() ? *out_ : torch::empty({T, N}, x.options().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16));
+  TORCH_CHECK(out.dim() == 2 && out.stride(1) == 1 && out.size(0) >= T && out.size(1) == N, "bad out tensor");
+  if (T == 0) return out;
+  b200::GemmArgs a;
+  a.x = x.data_ptr(); a.x_rows = T; a.ld_x = x.stride(0);
+  a.w = wq.data_ptr(); a.q_scales_t = scales_t.data_ptr(); a.q_biases_t = biases_t.data_ptr();
+  a.q_bits = (int)bits; a.q_group = (int)group;
+  if (wq2.has_value()) {
+    check_q(*wq2, *scales2_t, *biases2_t, N, K, bits, group);
+    a.w2 = wq2->data_ptr(); a.q_scales2_t = scales2_t->data_ptr(); a.q_biases2_t = biases2_t->data_ptr();
+  }
+  a.m = (int)T; a.n = (int)N; a.k = (int)K; a.max_rows = (int)T;
+  a.out = out.data_ptr(); a.ld_out = out.stride(0); a.out_fp32 = out.scalar_type() == torch::kFloat32;
+  if (residual.has_value()) { check_bf16(*residual, "residual"); check_rows(*residual, "residual"); a.residual = residual->data_ptr(); a.ld_res = residual->stride(0); }
+  if (bias.has_value()) { check_bf16(*bias, "bias"); a.bias = bias->data_ptr(); }
+  a.act = (int)act; a.softcap = (float)softcap;
+  int sp = splits > 0 ? (int)splits : auto_splits((int)T, (int)N, (int)K, false);
+  a.splits = sp;
+  auto& sc = scratch();
+  Tensor ctr = sc.get_counters(x.device());
+  if (sp > 1) {
+    const int bn = b200::gemm_pick_bn((int)T);
+    Tensor ws = sc.get_ws((int64_t)b200::gemm_workspace_floats(a, bn, sp), x.device());
+    a.workspace = ws.data_ptr<float>();
+    a.tile_counters = reinterpret_cast<unsigned int*>(ctr.data_ptr<int>());
+  }
+  if (signal_flag_ptr != 0) {
+    a.signal_flag = reinterpret_cast<uint32_t*>(signal_flag_ptr);
+    a.signal_value = (uint32_t)signal_value;
+    a.done_counter = reinterpret_cast<unsigned int*>(ctr.data_ptr<int>()) + 65535;
+  }
+  LAUNCH_OK(b200::gemm_q_launch(a, cur_stream()));
+  return out;
+}
+
+Tensor grouped_linear_q(const Tensor& x, const Tensor& wq, const Tensor& scales_t, const Tensor& biases_t, const c10::optional<Tensor>& wq2,
+                        const c10::optional<Tensor>& scales2_t, const c10::optional<Tensor>& biases2_t, int64_t bits, int64_t group,
+                        int64_t E, int64_t N, const Tensor& expert_offsets, int64_t max_rows, int64_t act, bool out_fp32) {
+  check_bf16(x, "x"); check_rows(x, "x");
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int64_t R = x.size(0), K = x.size(1);
+  check_q(wq, scales_t, biases_t, E * N, K, bits, group);
+  TORCH_CHECK(expert_offsets.numel() == E + 1 && expert_offsets.scalar_type() == torch::kInt32);
+  Tensor out = torch::empty({R, N}, x.options().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16));
+  if (R == 0) return out;
+  b200::GemmArgs a;
+  a.x = x.data_ptr(); a.x_rows = R; a.ld_x = x.stride(0);
+  a.w = wq.data_ptr(); a.q_scales_t = scales_t.data_ptr(); a.q_biases_t = biases_t.data_ptr();
+  a.q_bits = (int)bits; a.q_group = (int)group;
+  if (wq2.has_value()) {
+    check_q(*wq2, *scales2_t, *biases2_t, E * N, K, bits, group);
+    a.w2 = wq2->data_ptr(); a.q_scales2_t = scales2_t->data_ptr(); a.q_biases2_t = biases2_t->data_ptr();
+  }
+  a.m = (int)R; a.n = (int)N; a.k = (int)K; a.max_rows = (int)std::min<int64_t>(max_rows, R);
+  a.num_experts = (int)E; a.expert_offsets = expert_offsets.data_ptr<int>();
+  a.out = out.data_ptr(); a.ld_out = N; a.out_fp32 = out_fp32; a.act = (int)act; a.splits = 1;
+  LAUNCH_OK(b200::gemm_q_launch(a, cur_stream()));
+  return out;
+}
+bool gemm_q_supported(int64_t bits, int64_t group, int64_t k) { return b200::gemm_q_supported((int)bits, (int)group, (int)k); }
+
 // ---- elementwise ------------------------------------------------------------------------------------------------
 Tensor rmsnorm(const Tensor& x, const Tensor& w, double eps, bool gemma, const c10::optional<Tensor>& residual) {
   check_bf16(x, "x"); check_bf16(w, "w"); check_rows(x, "x");
@@ -246,6 +323,29 @@ Tensor paged_attention(const Tensor& q, const Tensor& kpool, const Tensor& vpool
   if (nsplit > 1) ++g_launches;  // + LSE combine kernel
   return out;
 }
+
+Tensor flash_prefill(const Tensor& q, const Tensor& kpool, const Tensor& vpool, const Tensor& block_tables, const Tensor& cu_seqlens,
+                     const Tensor& context_lens, double scale, int64_t num_tokens) {
+  check_bf16(q, "q"); check_bf16(kpool, "kpool"); check_bf16(vpool, "vpool");
+  TORCH_CHECK(q.dim() == 3 && q.stride(2) == 1 && kpool.is_contiguous() && vpool.is_contiguous());
+  TORCH_CHECK(block_tables.scalar_type() == torch::kInt32 && block_tables.is_contiguous() && cu_seqlens.scalar_type() == torch::kInt32 &&
+              context_lens.scalar_type() == torch::kInt32);
+  const c10::cuda::CUDAGuard guard(q.device());
+  const int T = (int)q.size(0), Hq = (int)q.size(1), dv = (int)vpool.size(3);
+  Tensor out = torch::empty({T, Hq, dv}, q.options());
+  if (T == 0) return out;
+  b200::FlashPrefillArgs a;
+  a.q = q.data_ptr(); a.q_ld_t = q.stride(0); a.q_ld_h = q.stride(1);
+  a.kpool = kpool.data_ptr(); a.vpool = vpool.data_ptr();
+  a.block_tables = block_tables.data_ptr<int>(); a.max_blocks = (int)block_tables.size(1);
+  a.cu_seqlens = cu_seqlens.data_ptr<int>(); a.context_lens = context_lens.data_ptr<int>();
+  a.num_seqs = (int)context_lens.numel(); a.max_tiles = (int)((num_tokens + 63) / 64 + a.num_seqs);
+  a.q_heads = Hq; a.kv_heads = (int)kpool.size(1); a.dk_ = (int)kpool.size(3); a.dv_ = dv; a.page = (int)kpool.size(2);
+  a.scale = (float)scale; a.out = out.data_ptr(); a.o_ld_t = (long long)Hq * dv;
+  LAUNCH_OK(b200::flash_prefill_launch(a, cur_stream()));
+  return out;
+}
+bool flash_prefill_supported(int64_t dk, int64_t dv) { return b200::flash_prefill_supported((int)dk, (int)dv); }
 
 // ---- MoE --------------------------------------------------------------------------------------------------------
 std::vector<Tensor> moe_route(const Tensor& x, const Tensor& gate_w, int64_t top_k, int64_t n_group, int64_t topk_group, double scaling,
@@ -439,6 +539,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("out") = py::none(), py::arg("splits") = 0, py::arg("signal_flag_ptr") = 0, py::arg("signal_value") = 0);
   m.def("grouped_linear", &grouped_linear, py::arg("x"), py::arg("w"), py::arg("w2") = py::none(), py::arg("expert_offsets"),
         py::arg("max_rows"), py::arg("act") = 0, py::arg("out_fp32") = false);
+  m.def("linear_q", &linear_q);
+  m.def("grouped_linear_q", &grouped_linear_q);
+  m.def("gemm_q_supported", &gemm_q_supported);
   m.def("rmsnorm", &rmsnorm, py::arg("x"), py::arg("w"), py::arg("eps"), py::arg("gemma") = false, py::arg("residual") = py::none());
   m.def("rope_", &rope_);
   m.def("embed", &embed, py::arg("ids"), py::arg("table"), py::arg("scales") = py::none(), py::arg("biases") = py::none(),
@@ -447,6 +550,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("kv_write_mla", &kv_write_mla);
   m.def("mla_rope_kv_write", &mla_rope_kv_write);
   m.def("paged_attention", &paged_attention);
+  m.def("flash_prefill", &flash_prefill);
+  m.def("flash_prefill_supported", &flash_prefill_supported);
   m.def("moe_route", &moe_route);
   m.def("moe_permute", &moe_permute);
   m.def("moe_combine", &moe_combine, py::arg("y_perm"), py::arg("pair_row"), py::arg("wts"), py::arg("residual") = py::none(),

@@ -39,6 +39,19 @@ struct PagedAttnArgs {
 };
 cudaError_t paged_attention_launch(const PagedAttnArgs& a, cudaStream_t s);
 
+// ---- attention_prefill.cu (tensor-core causal flash attention for prefill chunks)
+struct FlashPrefillArgs {
+  const void* q; long long q_ld_t, q_ld_h;
+  const void* kpool; const void* vpool;
+  const int* block_tables; int max_blocks;
+  const int* cu_seqlens; const int* context_lens;
+  int num_seqs, max_tiles, q_heads, kv_heads, dk_, dv_, page;
+  float scale;
+  void* out; long long o_ld_t;
+};
+bool flash_prefill_supported(int dk, int dv);
+cudaError_t flash_prefill_launch(const FlashPrefillArgs& a, cudaStream_t s);
+
 // ---- moe.cu
 // router: fp32 softmax(x W^T) -> top-k (optionally group limited) -> weights * scaling (or normalised)
 cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, int T, int H, int E, int top_k,

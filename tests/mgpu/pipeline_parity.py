@@ -55,6 +55,8 @@ def run(cfgd, transport, steps=6, B=16, S=24, PS=16):
     history = [[firsts[g].clone()] for g in range(G)]
     for _ in range(steps):
         loop.step_all()
+        if loop.transport != "fused":
+            continue  # NCCL sends rendezvous with the *next* step's receives: no host sync in between
         torch.cuda.synchronize()
         dist.barrier()
         # after a full step every group's freshly sampled tokens are on stage 0 (token inbox / tokens buffer)

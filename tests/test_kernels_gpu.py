@@ -234,3 +234,53 @@ def test_mla_rope_kv_write_fused(B):
     close(q, q2, 2e-2, 1e-2)
     close(kpool, kp2, 2e-2, 1e-2)
     assert torch.equal(vpool, vp2)
+
+
+@pytest.mark.parametrize("Hq,Hk,dk,dv", [(16, 16, 192, 128), (32, 8, 128, 128), (4, 2, 64, 64)])
+def test_flash_prefill_chunks(B, Hq, Hk, dk, dv):
+    """Tensor-core prefill kernel: long prompts, chunk continuation at a context offset, ragged tails."""
+    q_lens, ctx0 = [300, 64, 1, 129, 17], [0, 500, 77, 64, 1000]
+    meta, kpool, vpool = _paged_setup(q_lens, ctx0, Hk, dk, dv, page=64 if dk == 192 else 16, seed=3)
+    T = meta.num_tokens
+    q = rnd(T, Hq, dk, seed=9)
+    scale = dk ** -0.5
+    got = B.paged_attention(q, kpool, vpool, meta, scale, 0.0)
+    ref = R.paged_attention(q, kpool, vpool, meta, scale, 0.0)
+    close(got, ref, 2e-2, 2e-2)
+    # strided q (slice of a fused projection output)
+    big = rnd(T, Hq * dk + 64, seed=10)
+    qs = big[:, : Hq * dk].unflatten(1, (Hq, dk))
+    close(B.paged_attention(qs, kpool, vpool, meta, scale, 0.0), R.paged_attention(qs.contiguous(), kpool, vpool, meta, scale, 0.0),
+          2e-2, 2e-2)
+
+
+def _qweight(*shape, bits=4, group=64, seed=0):
+    w = rnd(*shape, scale=0.05, seed=seed).float()
+    wq, s, b = quant.quantize(w, group, bits, out_dtype=torch.bfloat16)
+    return LinearWeight(wq=wq, scales=s, biases=b, group_size=group, bits=bits)
+
+
+@pytest.mark.parametrize("bits,group", [(4, 64), (8, 64), (4, 128)])
+@pytest.mark.parametrize("T", [1, 64, 300])
+def test_quantized_linear_in_kernel_dequant(B, bits, group, T):
+    """int4/int8 MLX-affine weights dequantised inside the tcgen05 GEMM == dequantise-then-matmul oracle."""
+    K, N = 2048, 1408
+    x = rnd(T, K)
+    W = _qweight(N, K, bits=bits, group=group, seed=1)
+    assert B._qpack(W) is not None
+    close(B.linear(x, W), R.linear(x, W), 3e-2, 2e-2)
+    res = rnd(T, N)
+    close(B.linear(x, W, residual=res, out_dtype=torch.float32), R.linear(x, W, residual=res, out_dtype=torch.float32), 2e-2, 5e-3)
+    Wu = _qweight(N, K, bits=bits, group=group, seed=2)
+    close(B.gated_up(x, W, Wu, "silu"), R.gated_up(x, W, Wu, "silu"), 3e-2, 2e-2)
+
+
+def test_quantized_moe_experts(B):
+    H, I, E, k, T = 2048, 1408, 64, 6, 70
+    x = rnd(T, H)
+    Wg, Wu, Wd = _qweight(E, I, H, seed=1), _qweight(E, I, H, seed=2), _qweight(E, H, I, seed=3)
+    idx, w = R.moe_route(x, rnd(E, H, scale=0.05, seed=12), k)
+    res = rnd(T, H)
+    got = B.moe_experts(x, idx, w, Wg, Wu, Wd, "silu", residual=res)
+    ref = R.moe_experts(x, idx, w, Wg, Wu, Wd, "silu", residual=res)
+    close(got, ref, 5e-2, 2e-2)
