@@ -43,6 +43,8 @@ def parse_args(argv=None):
     p.add_argument("--transport", type=str, default="auto", choices=["auto", "fused", "nccl"])
     p.add_argument("--layers", type=int, default=None, help="debug only: truncate the model (result is marked invalid)")
     p.add_argument("--groups", type=int, default=0, help="micro-batch groups in flight (default: one per stage)")
+    p.add_argument("--quant", type=int, default=0, choices=[0, 4, 8],
+                   help="MLX affine quantised weights (group 64), dequantised inside the GEMM kernels (BASELINE config 2)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-graphs", action="store_true")
     p.add_argument("--page-size", type=int, default=64)
@@ -131,7 +133,9 @@ def main(argv=None):
     cfg = ModelConfig.from_dict(cfgd)
     spec = balanced_split(cfg, world)[rank]
     t0 = time.time()
-    model = random_model(cfgd, spec.start_layer, spec.end_layer, dtype=torch.bfloat16, device=dev, backend=backend, seed=1)
+    qcfg = dict(group_size=64, bits=args.quant) if args.quant else None
+    model = random_model(cfgd, spec.start_layer, spec.end_layer, dtype=torch.bfloat16, device=dev, backend=backend, seed=1,
+                         quantization=qcfg)
     torch.cuda.synchronize()
     log = lambda *a: print(f"[rank {rank}]", *a, file=sys.stderr, flush=True)
     log(f"layers [{spec.start_layer},{spec.end_layer}) weights {model.weight_bytes() / 1e9:.2f} GB built in {time.time() - t0:.1f}s")
@@ -248,6 +252,7 @@ def main(argv=None):
                        "global_batch": G * B, "seq_len": S, "parallelism": f"pp{world}",
                        "micro_batches_in_flight": G, "tokens_per_step": G * B, "transport": loop.transport,
                        "cuda_graphs": loop.use_graphs, "kv_page_size": PS,
+                       "weights": f"mlx-affine-int{args.quant}-g64 (in-kernel dequant)" if args.quant else "bf16",
                        "l2": "weights streamed per step (31 GB/stage-set) far exceed the 126 MB L2; no explicit flush",
                        "layers": [spec.start_layer, spec.end_layer] if world == 1 else "cost-balanced"},
             "ttft_p50_ms": round(ttft_p50 * 1e3, 2),
