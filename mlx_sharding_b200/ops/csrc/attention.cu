@@ -13,6 +13,7 @@
 // xor-shuffle tree, and each lane keeps the slice of the output accumulator matching its V pairs.
 // Bandwidth-bound by design: every K/V byte is read once per (token, kv head).
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -31,6 +32,7 @@ paged_attn_kernel(const __nv_bfloat16* __restrict__ q, long long q_ld_t, long lo
                   const int* __restrict__ token_seq, int kv_heads, int page, float scale, float softcap,
                   int nsplit, __nv_bfloat16* __restrict__ out, long long o_ld_t, float* __restrict__ part_acc,
                   float* __restrict__ part_ml) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   constexpr int PK = DK / 64;  // bf16x2 pairs per lane for K
   constexpr int PV = DV / 64;  // pairs per lane for V
   static_assert(DK % 64 == 0 && DV % 64 == 0, "head dims must be multiples of 64");
@@ -149,6 +151,7 @@ paged_attn_kernel(const __nv_bfloat16* __restrict__ q, long long q_ld_t, long lo
 template <int DV>
 __global__ void attn_combine_kernel(const float* __restrict__ part_acc, const float* __restrict__ part_ml, int nsplit,
                                     __nv_bfloat16* __restrict__ out, long long o_ld_t, int Hq) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const int t = blockIdx.x, hq = blockIdx.y;
   const size_t base = ((size_t)t * Hq + hq) * nsplit;
   float mm = -INFINITY;
@@ -168,7 +171,7 @@ __global__ void attn_combine_kernel(const float* __restrict__ part_acc, const fl
 template <int DK, int DV, int G>
 cudaError_t launch_attn(const PagedAttnArgs& a, cudaStream_t s) {
   dim3 grid(a.T, a.kv_heads, a.nsplit);
-  paged_attn_kernel<DK, DV, G><<<grid, kAttnThreads, 0, s>>>(
+  (void)launch_pdl(paged_attn_kernel<DK, DV, G>, dim3(grid), dim3(kAttnThreads), 0, s, 
       static_cast<const __nv_bfloat16*>(a.q), a.q_ld_t, a.q_ld_h, static_cast<const __nv_bfloat16*>(a.kpool),
       static_cast<const __nv_bfloat16*>(a.vpool), a.block_tables, a.max_blocks, a.positions, a.token_seq, a.kv_heads,
       a.page, a.scale, a.softcap, a.nsplit, static_cast<__nv_bfloat16*>(a.out), a.o_ld_t, a.part_acc, a.part_ml);
@@ -176,7 +179,7 @@ cudaError_t launch_attn(const PagedAttnArgs& a, cudaStream_t s) {
   if (e != cudaSuccess) return e;
   if (a.nsplit > 1) {
     dim3 g2(a.T, a.kv_heads * G);
-    attn_combine_kernel<DV><<<g2, 64, 0, s>>>(a.part_acc, a.part_ml, a.nsplit, static_cast<__nv_bfloat16*>(a.out), a.o_ld_t,
+    (void)launch_pdl(attn_combine_kernel<DV>, dim3(g2), dim3(64), 0, s, a.part_acc, a.part_ml, a.nsplit, static_cast<__nv_bfloat16*>(a.out), a.o_ld_t,
                                               a.kv_heads * G);
     e = cudaGetLastError();
   }

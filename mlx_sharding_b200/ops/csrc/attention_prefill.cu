@@ -12,6 +12,7 @@
 // registers with exp2.  NOTE: this is the legacy (HMMA) tensor path — the tcgen05/TMEM version of this
 // kernel is the planned replacement; the GEMMs that dominate prefill FLOPs already run on tcgen05.
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -46,6 +47,7 @@ flash_prefill_kernel(const __nv_bfloat16* __restrict__ q, long long q_ld_t, long
                      const int* __restrict__ block_tables, int max_blocks, const int* __restrict__ cu_seqlens,
                      const int* __restrict__ context_lens, int num_seqs, int q_heads, int kv_heads, int page, float scale_log2,
                      __nv_bfloat16* __restrict__ out, long long o_ld_t) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   constexpr int KS = DK + 8, VS = DV + 8;  // padded row strides (elements): (stride/2) % 32 == 4 -> conflict free
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_raw);      // [2][kBN][KS]
@@ -203,7 +205,7 @@ cudaError_t launch_prefill(const FlashPrefillArgs& a, cudaStream_t s) {
     configured = true;
   }
   dim3 grid(a.max_tiles, a.q_heads);
-  kern<<<grid, kThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(a.q), a.q_ld_t, a.q_ld_h,
+  (void)launch_pdl(kern, dim3(grid), dim3(kThreads), smem, s, static_cast<const __nv_bfloat16*>(a.q), a.q_ld_t, a.q_ld_h,
                                     static_cast<const __nv_bfloat16*>(a.kpool), static_cast<const __nv_bfloat16*>(a.vpool),
                                     a.block_tables, a.max_blocks, a.cu_seqlens, a.context_lens, a.num_seqs, a.q_heads, a.kv_heads,
                                     a.page, a.scale * 1.4426950408889634f, static_cast<__nv_bfloat16*>(a.out), a.o_ld_t);

@@ -5,6 +5,7 @@
 // KVCache.update_and_fetch via mlx_lm blocks); these are from-scratch sm_100a kernels: 128-bit
 // vectorised accesses, one warp-shuffle reduction tree, no shared-memory round trips beyond one exchange.
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(kNormThreads)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv_bfloat16* __restrict__ w,
                const __nv_bfloat16* __restrict__ residual, long long ld_res, __nv_bfloat16* __restrict__ out,
                long long ld_out, int H, float eps, int gemma) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const int row = blockIdx.x;
   const int nvec = H / 8;
   const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * ld_x);
@@ -93,7 +95,7 @@ cudaError_t rmsnorm_launch(const void* x, long long ld_x, const void* w, const v
                            void* out, long long ld_out, int rows, int H, float eps, bool gemma, cudaStream_t s) {
   if (H % 8 != 0 || H > kNormThreads * 8 * kNormMaxV || (ld_x % 8) || (ld_out % 8)) return cudaErrorInvalidValue;
   if (rows == 0) return cudaSuccess;
-  rmsnorm_kernel<<<rows, kNormThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ld_x,
+  (void)launch_pdl(rmsnorm_kernel, dim3(rows), dim3(kNormThreads), 0, s, static_cast<const __nv_bfloat16*>(x), ld_x,
                                                  static_cast<const __nv_bfloat16*>(w),
                                                  static_cast<const __nv_bfloat16*>(residual), ld_res,
                                                  static_cast<__nv_bfloat16*>(out), ld_out, H, eps, gemma ? 1 : 0);
@@ -106,6 +108,7 @@ cudaError_t rmsnorm_launch(const void* x, long long ld_x, const void* w, const v
 __global__ void rope_kernel(__nv_bfloat16* __restrict__ x, long long ld_t, long long ld_h, int heads,
                             const int* __restrict__ positions, const float* __restrict__ inv_freq, int rot_off,
                             int rot_dim, int interleaved, float mscale, int T) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const int half = rot_dim / 2;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long total = (long long)T * heads * half;
@@ -127,7 +130,7 @@ cudaError_t rope_launch(void* x, long long ld_t, long long ld_h, int heads, cons
                         int rot_off, int rot_dim, bool interleaved, float mscale, int T, cudaStream_t s) {
   const long long total = (long long)T * heads * (rot_dim / 2);
   if (total == 0) return cudaSuccess;
-  rope_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(static_cast<__nv_bfloat16*>(x), ld_t, ld_h, heads, positions,
+  (void)launch_pdl(rope_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, static_cast<__nv_bfloat16*>(x), ld_t, ld_h, heads, positions,
                                                               inv_freq, rot_off, rot_dim, interleaved ? 1 : 0, mscale, T);
   return cudaGetLastError();
 }
@@ -137,6 +140,7 @@ cudaError_t rope_launch(void* x, long long ld_t, long long ld_h, int heads, cons
 // w = scales * q + biases, group size g, codes packed LSB-first in uint32 words (MLX affine layout).
 __global__ void embed_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
                              __nv_bfloat16* __restrict__ out, int H, float scale, int T) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const int nvec = H / 8;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= (long long)T * nvec) return;
@@ -157,6 +161,7 @@ template <int BITS>
 __global__ void embed_quant_kernel(const long long* __restrict__ ids, const uint32_t* __restrict__ wq,
                                    const __nv_bfloat16* __restrict__ scales, const __nv_bfloat16* __restrict__ biases,
                                    __nv_bfloat16* __restrict__ out, int H, int group, float scale, int T) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   constexpr int PER = 32 / BITS;  // codes per word
   const int words = H / PER;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -185,7 +190,7 @@ cudaError_t embed_launch(const long long* ids, const void* table, const void* sc
   if (bits == 0) {
     if (H % 8) return cudaErrorInvalidValue;
     const long long n = (long long)T * (H / 8);
-    embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ids, static_cast<const __nv_bfloat16*>(table),
+    (void)launch_pdl(embed_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, ids, static_cast<const __nv_bfloat16*>(table),
                                                               static_cast<__nv_bfloat16*>(out), H, scale, T);
   } else {
     const int per = 32 / bits;
@@ -195,9 +200,9 @@ cudaError_t embed_launch(const long long* ids, const void* table, const void* sc
     auto wq = static_cast<const uint32_t*>(table);
     auto o = static_cast<__nv_bfloat16*>(out);
     const unsigned grid = (unsigned)((n + 255) / 256);
-    if (bits == 4) embed_quant_kernel<4><<<grid, 256, 0, s>>>(ids, wq, sc, bi, o, H, group, scale, T);
-    else if (bits == 8) embed_quant_kernel<8><<<grid, 256, 0, s>>>(ids, wq, sc, bi, o, H, group, scale, T);
-    else if (bits == 2) embed_quant_kernel<2><<<grid, 256, 0, s>>>(ids, wq, sc, bi, o, H, group, scale, T);
+    if (bits == 4) (void)launch_pdl(embed_quant_kernel<4>, dim3(grid), dim3(256), 0, s, ids, wq, sc, bi, o, H, group, scale, T);
+    else if (bits == 8) (void)launch_pdl(embed_quant_kernel<8>, dim3(grid), dim3(256), 0, s, ids, wq, sc, bi, o, H, group, scale, T);
+    else if (bits == 2) (void)launch_pdl(embed_quant_kernel<2>, dim3(grid), dim3(256), 0, s, ids, wq, sc, bi, o, H, group, scale, T);
     else return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -209,6 +214,7 @@ __global__ void kv_write_kernel(const __nv_bfloat16* __restrict__ k, long long k
                                 const __nv_bfloat16* __restrict__ v, long long v_ld_t, long long v_ld_h,
                                 __nv_bfloat16* __restrict__ kpool, __nv_bfloat16* __restrict__ vpool,
                                 const int* __restrict__ slots, int heads, int dk, int dv, int page, int T) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const int vk = dk / 8, vv = dv / 8, per = vk + vv;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= (long long)T * heads * per) return;
@@ -232,7 +238,7 @@ cudaError_t kv_write_launch(const void* k, long long k_ld_t, long long k_ld_h, c
   if (T == 0) return cudaSuccess;
   if ((dk % 8) || (dv % 8) || (k_ld_t % 8) || (k_ld_h % 8) || (v_ld_t % 8) || (v_ld_h % 8)) return cudaErrorInvalidValue;
   const long long n = (long long)T * heads * (dk / 8 + dv / 8);
-  kv_write_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+  (void)launch_pdl(kv_write_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, 
       static_cast<const __nv_bfloat16*>(k), k_ld_t, k_ld_h, static_cast<const __nv_bfloat16*>(v), v_ld_t, v_ld_h,
       static_cast<__nv_bfloat16*>(kpool), static_cast<__nv_bfloat16*>(vpool), slots, heads, dk, dv, page, T);
   return cudaGetLastError();
@@ -244,6 +250,7 @@ __global__ void kv_write_mla_kernel(const __nv_bfloat16* __restrict__ kv, long l
                                     const __nv_bfloat16* __restrict__ kpe, long long pe_ld_t,
                                     __nv_bfloat16* __restrict__ kpool, __nv_bfloat16* __restrict__ vpool,
                                     const int* __restrict__ slots, int heads, int nope, int rd, int vd, int page, int T) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const int vn = nope / 8, vr = rd / 8, vvv = vd / 8, per = vn + vr + vvv;
   const int dk = nope + rd;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -267,7 +274,7 @@ cudaError_t kv_write_mla_launch(const void* kv, long long kv_ld_t, const void* k
   if (T == 0) return cudaSuccess;
   if ((nope % 8) || (rd % 8) || (vd % 8) || (kv_ld_t % 8) || (pe_ld_t % 8)) return cudaErrorInvalidValue;
   const long long n = (long long)T * heads * ((nope + rd + vd) / 8);
-  kv_write_mla_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+  (void)launch_pdl(kv_write_mla_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, 
       static_cast<const __nv_bfloat16*>(kv), kv_ld_t, static_cast<const __nv_bfloat16*>(kpe), pe_ld_t,
       static_cast<__nv_bfloat16*>(kpool), static_cast<__nv_bfloat16*>(vpool), slots, heads, nope, rd, vd, page, T);
   return cudaGetLastError();
@@ -285,6 +292,7 @@ __global__ void mla_rope_kv_kernel(__nv_bfloat16* __restrict__ q, long long q_ld
                                    const int* __restrict__ slots, const int* __restrict__ positions,
                                    const float* __restrict__ inv_freq, float mscale, int heads, int nope, int rd, int vd,
                                    int page, int T) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const int half = rd / 2, vn = nope / 8, vv = vd / 8;
   const int per = half + vn + half + vv;  // work items per (token, head)
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -328,7 +336,7 @@ cudaError_t mla_rope_kv_launch(void* q, long long q_ld_t, long long q_ld_h, cons
   if (T == 0) return cudaSuccess;
   if ((nope % 8) || (rd % 8) || (vd % 8) || (kv_ld_t % 8) || (pe_ld_t % 2) || (q_ld_t % 2) || (q_ld_h % 2)) return cudaErrorInvalidValue;
   const long long n = (long long)T * heads * (rd + nope / 8 + vd / 8);
-  mla_rope_kv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+  (void)launch_pdl(mla_rope_kv_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, 
       static_cast<__nv_bfloat16*>(q), q_ld_t, q_ld_h, static_cast<const __nv_bfloat16*>(kpe), pe_ld_t,
       static_cast<const __nv_bfloat16*>(kv), kv_ld_t, static_cast<__nv_bfloat16*>(kpool), static_cast<__nv_bfloat16*>(vpool),
       slots, positions, inv_freq, mscale, heads, nope, rd, vd, page, T);

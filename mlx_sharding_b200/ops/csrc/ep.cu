@@ -18,6 +18,7 @@
 // is race-free by construction: a source only dispatches layer l+1 after it has combined layer l, which
 // requires every destination to have regrouped (consumed) layer l.
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -39,6 +40,7 @@ __global__ void ep_dispatch_kernel(const __nv_bfloat16* __restrict__ x, long lon
                                    PeerTable recv_count,  // per dst: base of [world] int
                                    PeerTable recv_flag,   // per dst: uint32 flag (counting)
                                    int* __restrict__ send_counts, unsigned int* __restrict__ done_counter) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const int warps_per_cta = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = H / 8;
@@ -85,6 +87,7 @@ ep_regroup_offsets_kernel(const uint32_t* flag, uint32_t* local_counter, uint32_
                           const int* __restrict__ recv_count, const int2* __restrict__ recv_meta, int world, int cap,
                           int E_local, int* __restrict__ expert_offsets, int* __restrict__ row_perm /*[world*cap]*/,
                           int* __restrict__ total_rows) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   __shared__ int cnt[256], cur[256];
   __shared__ int counts[kMaxWorld];
   if (threadIdx.x == 0) {
@@ -125,6 +128,7 @@ ep_regroup_offsets_kernel(const uint32_t* flag, uint32_t* local_counter, uint32_
 __global__ void ep_regroup_gather_kernel(const __nv_bfloat16* __restrict__ recv_x, const int2* __restrict__ recv_meta,
                                          const int* __restrict__ recv_count, const int* __restrict__ row_perm, int world, int cap,
                                          int H, __nv_bfloat16* __restrict__ x_perm, int2* __restrict__ perm_src /*(src rank, src pair)*/) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const int nvec = H / 8;
   const int s = blockIdx.y;
   const int n = recv_count[s];
@@ -142,6 +146,7 @@ __global__ void ep_regroup_gather_kernel(const __nv_bfloat16* __restrict__ recv_
 __global__ void ep_return_kernel(const float* __restrict__ y_perm, const int2* __restrict__ perm_src, const int* __restrict__ total_rows,
                                  int H, int world, PeerTable ret_y /*per src: [pairs][H] fp32*/, PeerTable ret_flag,
                                  unsigned int* __restrict__ done_counter) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const int warps_per_cta = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = *total_rows;
@@ -167,6 +172,7 @@ __global__ void ep_return_kernel(const float* __restrict__ y_perm, const int2* _
 // source side: wait until every rank has returned its share
 __global__ void ep_wait_all_kernel(const uint32_t* flag, uint32_t* local_counter, int world, uint32_t* error_flag,
                                    unsigned long long timeout_ns) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const uint32_t expected = atomicAdd(local_counter, (uint32_t)world) + (uint32_t)world;
   unsigned long long t0;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
@@ -199,7 +205,7 @@ cudaError_t ep_dispatch_launch(const void* x, long long ld_x, const int* idx, in
   int grid = (npairs + 7) / 8;
   if (grid < 1) grid = 1;
   if (grid > 592) grid = 592;
-  ep_dispatch_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ld_x, idx, npairs, top_k, H, experts_per_rank, world,
+  (void)launch_pdl(ep_dispatch_kernel, dim3(grid), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(x), ld_x, idx, npairs, top_k, H, experts_per_rank, world,
                                           my_rank, cap, make_table(recv_x, world), make_table(recv_meta, world),
                                           make_table(recv_count, world), make_table(recv_flag, world), send_counts, done_counter);
   return cudaGetLastError();
@@ -209,13 +215,13 @@ cudaError_t ep_regroup_launch(const uint32_t* flag, uint32_t* local_counter, uin
                               const void* recv_meta, const void* recv_x, int world, int cap, int E_local, int H, int* expert_offsets,
                               int* row_perm, int* total_rows, void* x_perm, void* perm_src, cudaStream_t s) {
   if (E_local > 256 || world > kMaxWorld) return cudaErrorInvalidValue;
-  ep_regroup_offsets_kernel<<<1, 1024, 0, s>>>(flag, local_counter, error_flag, kTimeoutNs, recv_count,
+  (void)launch_pdl(ep_regroup_offsets_kernel, dim3(1), dim3(1024), 0, s, flag, local_counter, error_flag, kTimeoutNs, recv_count,
                                                static_cast<const int2*>(recv_meta), world, cap, E_local, expert_offsets, row_perm,
                                                total_rows);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   dim3 grid(64, world);
-  ep_regroup_gather_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(recv_x), static_cast<const int2*>(recv_meta), recv_count,
+  (void)launch_pdl(ep_regroup_gather_kernel, dim3(grid), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(recv_x), static_cast<const int2*>(recv_meta), recv_count,
                                                 row_perm, world, cap, H, static_cast<__nv_bfloat16*>(x_perm), static_cast<int2*>(perm_src));
   return cudaGetLastError();
 }
@@ -227,13 +233,13 @@ cudaError_t ep_return_launch(const float* y_perm, const void* perm_src, const in
   int grid = (max_rows + 7) / 8;
   if (grid < 1) grid = 1;
   if (grid > 592) grid = 592;
-  ep_return_kernel<<<grid, 256, 0, s>>>(y_perm, static_cast<const int2*>(perm_src), total_rows, H, world, make_table(ret_y, world),
+  (void)launch_pdl(ep_return_kernel, dim3(grid), dim3(256), 0, s, y_perm, static_cast<const int2*>(perm_src), total_rows, H, world, make_table(ret_y, world),
                                         make_table(ret_flag, world), done_counter);
   return cudaGetLastError();
 }
 
 cudaError_t ep_wait_all_launch(const uint32_t* flag, uint32_t* local_counter, int world, uint32_t* error_flag, cudaStream_t s) {
-  ep_wait_all_kernel<<<1, 1, 0, s>>>(flag, local_counter, world, error_flag, kTimeoutNs);
+  (void)launch_pdl(ep_wait_all_kernel, dim3(1), dim3(1), 0, s, flag, local_counter, world, error_flag, kTimeoutNs);
   return cudaGetLastError();
 }
 

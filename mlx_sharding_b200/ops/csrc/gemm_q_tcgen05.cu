@@ -5,7 +5,7 @@
 // Data path per 64-wide k-block (== one or half a quantisation group):
 //   TMA:      packed codes [128 rows x 32|64 B]  + scales[128] + biases[128] (pre-transposed [K/g, rows] at load)
 //             + the bf16 token tile (128B swizzle)                                    -> full barrier
-//   4 dequant warps (one row per thread): unpack LSB-first nibbles/bytes, w = s*q + b in fp32, round to bf16,
+//   8 dequant warps (two threads per weight row): unpack LSB-first nibbles/bytes, w = s*q + b in fp32, round to bf16,
 //             store into the 128B-swizzled UMMA "A" tile, fence.proxy.async           -> dequant barrier
 //   1 thread: tcgen05.mma (fp32 accumulators in TMEM) ... tcgen05.commit              -> empty barrier
 // so HBM only ever sees 4.5 (or 8.5) bits per weight; everything downstream (TMEM epilogue, DUAL gate/up,
@@ -14,6 +14,7 @@
 #include <unordered_map>
 
 #include "gemm_common.cuh"
+#include "launch.h"
 
 namespace b200 {
 
@@ -21,7 +22,7 @@ using namespace gemm;
 
 namespace {
 
-constexpr int kQThreads = 320;  // + warps 6..9: dequant producers
+constexpr int kQThreads = 448;  // + warps 6..13: dequant producers (two threads per weight row)
 
 __host__ __device__ constexpr int q_stage_bytes(int BN, bool dual, int bits) {
   const int d = dual ? 2 : 1;
@@ -35,38 +36,57 @@ __host__ __device__ constexpr int q_num_stages(int BN, bool dual, int bits, int 
   return s;
 }
 
+// One thread dequantises half a row of the k-block: 32 weights = 4 chunks of 8 (chunks 4*half .. 4*half+3).
+//
+// int4 fast path (2.5 ALU ops / weight instead of ~5.5): nibbles i and i+4 of a word are isolated together with
+// (w >> 4i) & 0x000F000F, OR-ed with 0x4300'4300 they are the bf16 pair (128 + q_i, 128 + q_{i+4}) exactly; one HSUB2
+// removes the 128 and one HFMA2.BF16 produces bf16(s*q + b) with a *single* rounding; two PRMTs per word pair put
+// the results back in K order.  int8 keeps the fp32 magic-number path (8-bit codes do not fit the bf16 mantissa).
 template <int BITS>
-__device__ __forceinline__ void dequant_row(const uint8_t* packed_row, float s, float b, uint8_t* a_tile, int r) {
-  constexpr int WORDS = kBlockK * BITS / 32;  // 8 (int4) or 16 (int8) words per row per k-block
-  uint32_t w[WORDS];
-#pragma unroll
-  for (int i = 0; i < WORDS / 4; ++i) {
-    const uint4 v = reinterpret_cast<const uint4*>(packed_row)[i];
-    w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-  }
+__device__ __forceinline__ void dequant_half_row(const uint8_t* packed_row, float s, float b, uint8_t* a_tile, int r, int half) {
   uint8_t* row = a_tile + r * 128;
+  if (BITS == 4) {
+    const uint4 v = reinterpret_cast<const uint4*>(packed_row)[half];  // 4 words = 32 codes
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const __nv_bfloat162 s2 = __float2bfloat162_rn(s), b2 = __float2bfloat162_rn(b);
+    const uint32_t magic = 0x43004300u;
+    const __nv_bfloat162 c128 = *reinterpret_cast<const __nv_bfloat162*>(&magic);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {  // eight 16-byte chunks (8 bf16 each) per 128-byte row
-    float f[8];
-    if (BITS == 4) {
-      const uint32_t x = w[c];
+    for (int c = 0; c < 4; ++c) {
+      uint32_t x[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float q = __uint_as_float(((x >> (4 * i)) & 0xFu) | 0x4B000000u) - 8388608.0f;
-        f[i] = fmaf(s, q, b);
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t m = ((w[c] >> (4 * i)) & 0x000F000Fu) | magic;  // (128 + q_i, 128 + q_{i+4})
+        __nv_bfloat162 q = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&m), c128);
+        q = __hfma2(s2, q, b2);
+        x[i] = *reinterpret_cast<uint32_t*>(&q);
       }
-    } else {
+      uint4 o;
+      o.x = __byte_perm(x[0], x[1], 0x5410);  // (v0, v1)
+      o.y = __byte_perm(x[2], x[3], 0x5410);  // (v2, v3)
+      o.z = __byte_perm(x[0], x[1], 0x7632);  // (v4, v5)
+      o.w = __byte_perm(x[2], x[3], 0x7632);  // (v6, v7)
+      const int chunk = 4 * half + c;
+      // 128B swizzle (Swizzle<3,4,3>): 16-byte chunk index XOR (row mod 8)
+      *reinterpret_cast<uint4*>(row + ((chunk ^ (r & 7)) << 4)) = o;
+    }
+  } else {
+    const uint4 v0 = reinterpret_cast<const uint4*>(packed_row)[2 * half], v1 = reinterpret_cast<const uint4*>(packed_row)[2 * half + 1];
+    const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};  // 8 words = 32 codes
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float f[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint32_t x = w[2 * c + (i >> 2)];
         const float q = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7440u | (i & 3))) - 8388608.0f;
         f[i] = fmaf(s, q, b);
       }
+      uint4 o;
+      o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+      const int chunk = 4 * half + c;
+      *reinterpret_cast<uint4*>(row + ((chunk ^ (r & 7)) << 4)) = o;
     }
-    uint4 o;
-    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-    // 128B swizzle (Swizzle<3,4,3>): 16-byte chunk index XOR (row mod 8)
-    *reinterpret_cast<uint4*>(row + ((c ^ (r & 7)) << 4)) = o;
   }
 }
 
@@ -101,6 +121,10 @@ gemm_swapab_q_kernel(const __grid_constant__ CUtensorMap tmap_wq, const __grid_c
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // PDL: grouped launches read expert_offsets (written by the permutation kernel) right away, so they wait first;
+  // plain launches overlap their whole prologue (barrier init, TMEM allocation) with the predecessor's tail.
+  const bool pdl_early = p.expert_offsets != nullptr;
+  if (pdl_early) pdl_wait();
   const int n0 = blockIdx.x * kTileM;
   const int expert = blockIdx.y;
   const int split = blockIdx.z % p.splits;
@@ -131,7 +155,7 @@ gemm_swapab_q_kernel(const __grid_constant__ CUtensorMap tmap_wq, const __grid_c
     tma_prefetch_desc(&tmap_x);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&deq_bar[s], 4);
+      mbar_init(&deq_bar[s], 8);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
@@ -142,6 +166,8 @@ gemm_swapab_q_kernel(const __grid_constant__ CUtensorMap tmap_wq, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  if (!pdl_early) pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ============================================================== TMA producer
@@ -197,7 +223,8 @@ gemm_swapab_q_kernel(const __grid_constant__ CUtensorMap tmap_wq, const __grid_c
                                  num_kb);
   } else {
     // ============================================================== dequant producers: one weight row per thread
-    const int r = threadIdx.x - 192;  // 0..127
+    const int r = (threadIdx.x - 192) & 127;   // weight row of the tile
+    const int half = (threadIdx.x - 192) >> 7;  // which 32-weight half of the 64-wide k-block
     for (int i = 0; i < num_kb; ++i) {
       const int s = i % STAGES;
       const uint32_t ph = (i / STAGES) & 1;
@@ -207,7 +234,7 @@ gemm_swapab_q_kernel(const __grid_constant__ CUtensorMap tmap_wq, const __grid_c
       for (int d = 0; d < D; ++d) {
         const __nv_bfloat16* sb = reinterpret_cast<const __nv_bfloat16*>(st + OFF_SCALE + d * 512);
         const float sc = __bfloat162float(sb[r]), bi = __bfloat162float(sb[128 + r]);
-        dequant_row<BITS>(st + OFF_PACKED + d * PACKED_BYTES + r * (kBlockK * BITS / 8), sc, bi, st + d * kATileBytes, r);
+        dequant_half_row<BITS>(st + OFF_PACKED + d * PACKED_BYTES + r * (kBlockK * BITS / 8), sc, bi, st + d * kATileBytes, r, half);
       }
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
@@ -292,7 +319,7 @@ cudaError_t q_launch_one(const QMaps& t, const GemmParams& p, int group_kblocks,
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<grid, kQThreads, smem, stream>>>(t.wq, t.wq2, t.s, t.b, t.s2, t.b2, t.x, p, group_kblocks);
+  (void)launch_pdl(kern, dim3(grid), dim3(kQThreads), smem, stream, t.wq, t.wq2, t.s, t.b, t.s2, t.b2, t.x, p, group_kblocks);
   return cudaGetLastError();
 }
 
@@ -352,6 +379,7 @@ cudaError_t gemm_q_launch(const GemmArgs& a, cudaStream_t stream) {
 
   GemmParams p;
   p.m = a.m; p.n = a.n; p.k = a.k; p.splits = splits;
+  p.cluster_splitk = 0;
   p.expert_offsets = a.expert_offsets;
   p.out = a.out; p.ld_out = a.ld_out;
   p.residual = static_cast<const __nv_bfloat16*>(a.residual); p.ld_res = a.ld_res;

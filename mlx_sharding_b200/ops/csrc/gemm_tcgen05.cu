@@ -26,7 +26,8 @@
 #include <mutex>
 #include <unordered_map>
 
-#include "gemm_common.cuh"
+#include "gemm_cluster.cuh"
+#include "launch.h"
 
 namespace b200 {
 
@@ -54,6 +55,10 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   const int lane = threadIdx.x & 31;
 
   // ---------------------------------------------------------------- tile coordinates
+  // PDL: grouped launches read expert_offsets (written by the permutation kernel) right away, so they wait first;
+  // plain launches overlap their whole prologue (barrier init, TMEM allocation) with the predecessor's tail.
+  const bool pdl_early = p.expert_offsets != nullptr;
+  if (pdl_early) pdl_wait();
   const int n0 = blockIdx.x * kTileM;
   const int expert = blockIdx.y;
   const int split = blockIdx.z % p.splits;
@@ -94,6 +99,8 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  if (!pdl_early) pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ============================================================== TMA producer
@@ -140,8 +147,20 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     }
   } else {
     // ============================================================== epilogue warps (128 threads)
-    gemm::run_epilogue<BN, DUAL, OutT>(p, smem, tmem_base, tmem_full_bar, flag_smem, warp, lane, 64, n0, mt, split, row_base,
-                                       rows_valid, num_kb);
+    if (p.cluster_splitk)
+      gemm::cluster_epilogue_store_partial<BN, DUAL>(smem, tmem_base, tmem_full_bar, warp, lane, num_kb);
+    else
+      gemm::run_epilogue<BN, DUAL, OutT>(p, smem, tmem_base, tmem_full_bar, flag_smem, warp, lane, 64, n0, mt, split, row_base,
+                                         rows_valid, num_kb);
+  }
+  if (p.cluster_splitk) {
+    // split-K through DSMEM: the `splits` CTAs of this output tile are one cluster (gemm_cluster.cuh)
+    __syncwarp();
+    gemm::cluster_sync_all();
+    if (warp >= 2) gemm::cluster_epilogue_reduce_store<BN, DUAL, OutT>(p, smem, 64, n0, row_base, rows_valid);
+    __syncwarp();
+    gemm::cluster_sync_all();
+    gemm::cluster_signal(p, 64);
   }
 
   __syncthreads();
@@ -227,7 +246,7 @@ cudaError_t launch_one(const GemmArgs& a, const CUtensorMap& tw, const CUtensorM
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<grid, kNumThreads, smem, stream>>>(tw, tw2, tx, p);
+  (void)launch_pdl_cluster(kern, dim3(grid), dim3(kNumThreads), smem, stream, p.cluster_splitk ? (unsigned)p.splits : 1u, tw, tw2, tx, p);
   return cudaGetLastError();
 }
 
@@ -270,7 +289,7 @@ cudaError_t gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   if (splits > kb_total) splits = kb_total;
   if (grouped && (a.n % kTileM) != 0) return cudaErrorInvalidValue;
   if ((a.k % 8) != 0 || (a.n % 8) != 0) return cudaErrorInvalidValue;
-  if (splits > 1 && (a.workspace == nullptr || a.tile_counters == nullptr)) return cudaErrorInvalidValue;
+  if (splits > 1 && !a.cluster_splitk && (a.workspace == nullptr || a.tile_counters == nullptr)) return cudaErrorInvalidValue;
   if (dual && a.out_fp32) return cudaErrorInvalidValue;
 
   CUtensorMap tw, tw2, tx;
@@ -285,6 +304,8 @@ cudaError_t gemm_launch(const GemmArgs& a, cudaStream_t stream) {
 
   GemmParams p;
   p.m = a.m; p.n = a.n; p.k = a.k; p.splits = splits;
+  // DSMEM (cluster) split-K when the fp32 partial tile fits the idle stage ring and the cluster is portable
+  p.cluster_splitk = (a.cluster_splitk && splits > 1 && splits <= 8 && bn * (dual ? 2 : 1) <= 128) ? 1 : 0;
   p.expert_offsets = a.expert_offsets;
   p.out = a.out; p.ld_out = a.ld_out;
   p.residual = static_cast<const __nv_bfloat16*>(a.residual); p.ld_res = a.ld_res;

@@ -26,6 +26,7 @@ struct GemmParams {
   uint32_t signal_value;
   unsigned int* done_counter;
   unsigned int signal_tiles;
+  int cluster_splitk;  // 1: the `splits` CTAs of a tile form a cluster and reduce through DSMEM
 };
 
 // Host-side launch description.  Y[rows, n] = X[rows, k] * W[n, k]^T, bf16 in, fp32 accumulate.
@@ -58,6 +59,7 @@ struct GemmArgs {
   unsigned int signal_tiles = 0;          // 0 = all tiles of the grid
   // MLX affine-quantised weights (gemm_q_launch): w / w2 point at the packed uint32 codes [rows, k*bits/32];
   // scales / biases are pre-transposed to [k/group, rows] bf16 at load time (TMA-friendly)
+  bool cluster_splitk = true;             // prefer the DSMEM reduction when it applies (decode shapes)
   int q_bits = 0, q_group = 64;
   const void* q_scales_t = nullptr; const void* q_biases_t = nullptr;
   const void* q_scales2_t = nullptr; const void* q_biases2_t = nullptr;

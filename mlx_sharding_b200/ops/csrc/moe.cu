@@ -3,6 +3,7 @@
 // — on the last layer of a stage — with the P2P hand-off flag.  The reference gets this from
 // mlx_lm's MoEGate + SwitchGLU (`mx.gather_qmm`, `(y * scores[..., None]).sum(-2)`); nothing is ported.
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(kRouteThreads)
 moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv_bfloat16* __restrict__ gw, int T, int H,
                  int E, int top_k, int n_group, int topk_group, float scaling, int norm_topk, int* __restrict__ idx,
                  float* __restrict__ wts) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   extern __shared__ __align__(16) uint8_t smem[];
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem);                 // [kRouteToks][H]
   float* logits = reinterpret_cast<float*>(smem + (size_t)kRouteToks * H * 2);  // [kRouteToks][E]
@@ -162,6 +164,7 @@ moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv
 __global__ void __launch_bounds__(1024)
 moe_offsets_kernel(const int* __restrict__ idx, int npairs, int E, int* __restrict__ expert_offsets,
                    int* __restrict__ pair_row) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   __shared__ int cnt[256], cur[256];
   for (int e = threadIdx.x; e < E; e += blockDim.x) cnt[e] = 0;
   __syncthreads();
@@ -181,6 +184,7 @@ moe_offsets_kernel(const int* __restrict__ idx, int npairs, int E, int* __restri
 
 __global__ void moe_gather_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const int* __restrict__ pair_row,
                                   __nv_bfloat16* __restrict__ x_perm, int H, int top_k, long long total) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const int nvec = H / 8;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -196,6 +200,7 @@ __global__ void moe_combine_kernel(const float* __restrict__ y_perm, const int* 
                                    const float* __restrict__ wts, const __nv_bfloat16* __restrict__ residual,
                                    long long ld_res, __nv_bfloat16* __restrict__ out, long long ld_out, int T, int top_k,
                                    int H, uint32_t* signal_flag, uint32_t signal_value, unsigned int* done_counter) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const int nvec = H / 8;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < (long long)T * nvec) {
@@ -250,7 +255,7 @@ cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, 
   if (T <= 1024) {
     const size_t smem = (size_t)H * 2 + (size_t)E * 4;
     if (smem > 48 * 1024) return cudaErrorInvalidValue;
-    moe_route_kernel<1><<<T, kRouteThreads, smem, s>>>(xx, ld_x, gw, T, H, E, top_k, n_group, topk_group, scaling,
+    (void)launch_pdl(moe_route_kernel<1>, dim3(T), dim3(kRouteThreads), smem, s, xx, ld_x, gw, T, H, E, top_k, n_group, topk_group, scaling,
                                                        norm_topk ? 1 : 0, idx, wts);
   } else {
     constexpr int TOKS = 8;
@@ -261,7 +266,7 @@ cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, 
       if (e != cudaSuccess) return e;
       configured = smem;
     }
-    moe_route_kernel<TOKS><<<(T + TOKS - 1) / TOKS, kRouteThreads, smem, s>>>(xx, ld_x, gw, T, H, E, top_k, n_group, topk_group,
+    (void)launch_pdl(moe_route_kernel<TOKS>, dim3((T + TOKS - 1) / TOKS), dim3(kRouteThreads), smem, s, xx, ld_x, gw, T, H, E, top_k, n_group, topk_group,
                                                                            scaling, norm_topk ? 1 : 0, idx, wts);
   }
   return cudaGetLastError();
@@ -272,11 +277,11 @@ cudaError_t moe_permute_launch(const int* idx, int T, int top_k, int E, int* exp
   (void)counters;
   if (T == 0) return cudaSuccess;
   if (E > 256 || (H % 8)) return cudaErrorInvalidValue;
-  moe_offsets_kernel<<<1, 1024, 0, s>>>(idx, T * top_k, E, expert_offsets, pair_row);
+  (void)launch_pdl(moe_offsets_kernel, dim3(1), dim3(1024), 0, s, idx, T * top_k, E, expert_offsets, pair_row);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const long long total = (long long)T * top_k * (H / 8);
-  moe_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ld_x, pair_row,
+  (void)launch_pdl(moe_gather_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(x), ld_x, pair_row,
                                                                     static_cast<__nv_bfloat16*>(x_perm), H, top_k, total);
   return cudaGetLastError();
 }
@@ -287,7 +292,7 @@ cudaError_t moe_combine_launch(const void* y_perm, const int* pair_row, const fl
   if (T == 0) return cudaSuccess;
   if (H % 8) return cudaErrorInvalidValue;
   const long long total = (long long)T * (H / 8);
-  moe_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+  (void)launch_pdl(moe_combine_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, 
       static_cast<const float*>(y_perm), pair_row, wts, static_cast<const __nv_bfloat16*>(residual), ld_res,
       static_cast<__nv_bfloat16*>(out), ld_out, T, top_k, H, signal_flag, signal_value, done_counter);
   return cudaGetLastError();

@@ -4,6 +4,7 @@
 // step re-run without any host -> device traffic.  The reference's equivalent is a blocking gRPC unary
 // call per stage per token with host staging (shard/utils.py:71-90,162-164).
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -19,6 +20,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // Spin until *flag >= expected (monotonic step counters).  Bounded: after ~timeout the kernel records an
 // error and returns instead of hanging the GPU (a dead peer must never wedge the box).
 __global__ void wait_flag_kernel(const uint32_t* flag, uint32_t expected, uint32_t* error_flag, unsigned long long timeout_ns) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const unsigned long long t0 = globaltimer_ns();
   while (true) {
     const uint32_t v = ld_acquire_sys(flag);
@@ -35,6 +37,7 @@ __global__ void wait_flag_kernel(const uint32_t* flag, uint32_t expected, uint32
 // device memory (`local_counter`), so the same captured node is correct on every replay.
 __global__ void wait_flag_counter_kernel(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag,
                                          unsigned long long timeout_ns) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const uint32_t expected = atomicAdd(local_counter, 1u) + 1u;
   const unsigned long long t0 = globaltimer_ns();
   while (true) {
@@ -49,6 +52,7 @@ __global__ void wait_flag_counter_kernel(const uint32_t* flag, uint32_t* local_c
 }
 
 __global__ void set_flag_kernel(uint32_t* flag, uint32_t value) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   __threadfence_system();
   st_release_sys(flag, value);
 }
@@ -56,6 +60,7 @@ __global__ void set_flag_kernel(uint32_t* flag, uint32_t value) {
 // dst may be peer memory: stream src -> dst with 16 B stores, then publish the flag from the last CTA.
 __global__ void copy_signal_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t nvec, uint32_t* flag,
                                    uint32_t value, unsigned int* done_counter) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
   __threadfence_system();
   __syncthreads();
@@ -73,6 +78,7 @@ __global__ void copy_signal_kernel(const uint4* __restrict__ src, uint4* __restr
 // decode step k -> k+1 for every sequence of a micro-batch: position, context length, KV slot
 __global__ void advance_meta_kernel(int* positions, int* context_lens, int* slots, const int* block_tables, int max_blocks,
                                     int page, int B) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int p = positions[b] + 1;
@@ -84,17 +90,17 @@ __global__ void advance_meta_kernel(int* positions, int* context_lens, int* slot
 }  // namespace
 
 cudaError_t wait_flag_launch(const uint32_t* flag, uint32_t expected, uint32_t* error_flag, cudaStream_t s) {
-  wait_flag_kernel<<<1, 1, 0, s>>>(flag, expected, error_flag, 20ull * 1000ull * 1000ull * 1000ull);
+  (void)launch_pdl(wait_flag_kernel, dim3(1), dim3(1), 0, s, flag, expected, error_flag, 20ull * 1000ull * 1000ull * 1000ull);
   return cudaGetLastError();
 }
 
 cudaError_t wait_flag_counter_launch(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag, cudaStream_t s) {
-  wait_flag_counter_kernel<<<1, 1, 0, s>>>(flag, local_counter, error_flag, 20ull * 1000ull * 1000ull * 1000ull);
+  (void)launch_pdl(wait_flag_counter_kernel, dim3(1), dim3(1), 0, s, flag, local_counter, error_flag, 20ull * 1000ull * 1000ull * 1000ull);
   return cudaGetLastError();
 }
 
 cudaError_t set_flag_launch(uint32_t* flag, uint32_t value, cudaStream_t s) {
-  set_flag_kernel<<<1, 1, 0, s>>>(flag, value);
+  (void)launch_pdl(set_flag_kernel, dim3(1), dim3(1), 0, s, flag, value);
   return cudaGetLastError();
 }
 
@@ -105,14 +111,14 @@ cudaError_t copy_signal_launch(const void* src, void* dst, size_t bytes, uint32_
   int grid = (int)((nvec + 255) / 256);
   if (grid > 296) grid = 296;
   if (grid < 1) grid = 1;
-  copy_signal_kernel<<<grid, 256, 0, s>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), nvec, flag, value, done_counter);
+  (void)launch_pdl(copy_signal_kernel, dim3(grid), dim3(256), 0, s, static_cast<const uint4*>(src), static_cast<uint4*>(dst), nvec, flag, value, done_counter);
   return cudaGetLastError();
 }
 
 cudaError_t advance_meta_launch(int* positions, int* context_lens, int* slots, const int* block_tables, int max_blocks,
                                 int page, int B, cudaStream_t s) {
   if (B == 0) return cudaSuccess;
-  advance_meta_kernel<<<(B + 127) / 128, 128, 0, s>>>(positions, context_lens, slots, block_tables, max_blocks, page, B);
+  (void)launch_pdl(advance_meta_kernel, dim3((B + 127) / 128), dim3(128), 0, s, positions, context_lens, slots, block_tables, max_blocks, page, B);
   return cudaGetLastError();
 }
 

@@ -140,6 +140,12 @@ B200_DEVICE void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Programmatic dependent launch (see launch.h): wait for the predecessor grid's memory, then let the successor's
+// blocks be scheduled while this grid is still running.
+B200_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+B200_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+B200_DEVICE void pdl_sync() { pdl_wait(); pdl_launch_dependents(); }
+
 B200_DEVICE float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 B200_DEVICE float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 B200_DEVICE uint32_t pack_bf16(float a, float b) {

@@ -6,6 +6,7 @@
 // bisection on the logit threshold, and sampling inside it uses the Gumbel-max trick with a
 // counter-based RNG (stateless: seed, step, row, token id).
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(kSampThreads)
 sample_kernel(const float* __restrict__ logits, int V, const float* __restrict__ temperature, const float* __restrict__ top_p,
               unsigned long long seed, unsigned long long step, long long* __restrict__ tokens, float* __restrict__ logprobs,
               int top_k, long long* __restrict__ top_ids, float* __restrict__ top_lp) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   __shared__ ArgMax sm_a[kSampThreads / 32];
   __shared__ float sm_f[kSampThreads / 32];
   const int b = blockIdx.x;
@@ -138,6 +140,7 @@ sample_kernel(const float* __restrict__ logits, int V, const float* __restrict__
 __global__ void apply_penalties_kernel(float* __restrict__ logits, int V, const int* __restrict__ rep_ctx, int C,
                                        const float* __restrict__ penalty, const int* __restrict__ bias_idx,
                                        const float* __restrict__ bias_val, int NB) {
+  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const int b = blockIdx.x;
   float* lg = logits + (size_t)b * V;
   const float pen = penalty[b];
@@ -164,7 +167,7 @@ __global__ void apply_penalties_kernel(float* __restrict__ logits, int V, const 
 cudaError_t apply_penalties_launch(float* logits, int B, int V, const int* rep_ctx, int C, const float* penalty,
                                    const int* bias_idx, const float* bias_val, int NB, cudaStream_t s) {
   if (B == 0) return cudaSuccess;
-  apply_penalties_kernel<<<B, 128, 0, s>>>(logits, V, rep_ctx, C, penalty, bias_idx, bias_val, NB);
+  (void)launch_pdl(apply_penalties_kernel, dim3(B), dim3(128), 0, s, logits, V, rep_ctx, C, penalty, bias_idx, bias_val, NB);
   return cudaGetLastError();
 }
 
@@ -173,7 +176,7 @@ cudaError_t sample_launch(const float* logits, int B, int V, const float* temper
                           long long* top_ids, float* top_lp, cudaStream_t s) {
   if (B == 0) return cudaSuccess;
   if (top_k > 32) return cudaErrorInvalidValue;
-  sample_kernel<<<B, kSampThreads, 0, s>>>(logits, V, temperature, top_p, seed, step, tokens, logprobs, top_k, top_ids, top_lp);
+  (void)launch_pdl(sample_kernel, dim3(B), dim3(kSampThreads), 0, s, logits, V, temperature, top_p, seed, step, tokens, logprobs, top_k, top_ids, top_lp);
   return cudaGetLastError();
 }
 
