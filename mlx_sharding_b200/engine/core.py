@@ -251,7 +251,9 @@ class LLMEngine:
                 mask.append(True)
             is_prefill = False
         bts = [self.table.pages[r.id] for r in seqs]
-        meta = BatchMeta.build(q_lens, ctx0, bts, self.page_size)
+        # block-table width rounded up to a multiple of 8 so captured decode graphs (graph_decode.py) are reused
+        width = (max(len(p) for p in bts) + 7) // 8 * 8
+        meta = BatchMeta.build(q_lens, ctx0, bts, self.page_size, pad_blocks_to=width)
         ctxs = [(r.prompt + r.output)[-max(1, r.params.repetition_context_size):]
                 if r.params.repetition_penalty not in (0, 1.0) else [] for r in seqs]
         return StepInput(g, [r.id for r in seqs], torch.tensor(toks, dtype=torch.int64), meta,

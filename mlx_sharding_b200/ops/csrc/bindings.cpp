@@ -78,7 +78,7 @@ int auto_splits(int rows, int n, int k, bool grouped) {
   const int kb = (k + 63) / 64;
   int s = 1;
   // fill ~one wave of SMs while keeping >= 4 k-blocks per split
-  while (tiles * (s * 2) <= sm_count() && kb / (s * 2) >= 4) s *= 2;
+  while (tiles * (s * 2) <= sm_count() && kb / (s * 2) >= 8 && s < 4) s *= 2;  // measured: profiles/splitk_sweep.md
   return s;
 }
 

@@ -79,12 +79,30 @@ class LocalPipeline:
         self.num_stages = 1  # one executor thread: a single micro-batch group keeps it busy
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        from .graph_decode import DecodeGraphCache
+
+        self.gcache = DecodeGraphCache(stages[0]) if len(stages) == 1 else None
 
     @classmethod
     def from_models(cls, models, num_pages: int, page_size: int = 64, seed: int = 0):
         return cls([StageExecutor(m, num_pages, page_size, seed) for m in models])
 
+    def _submit_graph(self, inp: StepInput) -> StepOutput:
+        """Steady-state decode: one pinned H2D copy of (metadata, token ids), one graph replay, one D2H."""
+        m = inp.meta
+        e = self.gcache.entry(m.num_seqs, m.block_tables.shape[1], m.max_ctx_len)
+        packed = m.pack().pin_memory()
+        toks_h = inp.tokens.pin_memory()
+        e.flat.copy_(packed, non_blocking=True)
+        e.x.copy_(toks_h, non_blocking=True)
+        toks, lp = self.gcache.run(e)
+        self.h2d_bytes += packed.numel() * 4 + toks_h.numel() * 8
+        self.d2h_bytes += m.num_seqs * 12
+        return StepOutput(toks.tolist(), lp.tolist())
+
     def submit(self, inp: StepInput):
+        if self.gcache is not None and self.gcache.eligible(inp.meta, inp.params):
+            return self._submit_graph(inp)
         x, meta0, nbytes = stage_inputs(inp, self.stages[0].device)
         self.h2d_bytes += nbytes
         for i, st in enumerate(self.stages):
@@ -121,12 +139,24 @@ class ChainPipeline:
         self._pending = deque()
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        from .graph_decode import DecodeGraphCache
+
+        self.gcache = DecodeGraphCache(stage)
 
     def submit(self, inp: StepInput):
         tp = self.tp
-        toks, meta, nbytes = stage_inputs(inp, self.stage.device)
+        if self.num_stages > 1 and self.gcache.eligible(inp.meta, None):
+            m = inp.meta
+            e = self.gcache.entry(m.num_seqs, m.block_tables.shape[1], m.max_ctx_len)
+            packed, toks_h = m.pack().pin_memory(), inp.tokens.pin_memory()
+            e.flat.copy_(packed, non_blocking=True)
+            e.x.copy_(toks_h, non_blocking=True)
+            x = self.gcache.run(e)
+            nbytes = packed.numel() * 4 + toks_h.numel() * 8
+        else:
+            toks, meta, nbytes = stage_inputs(inp, self.stage.device)
+            x = self.stage.forward(toks, meta)
         self.h2d_bytes += nbytes
-        x = self.stage.forward(toks, meta)
         self.d2h_bytes += len(inp.seq_ids) * 12
         if self.num_stages == 1:
             return ("local", self.stage.sample(x, inp.params, inp.contexts))
@@ -162,6 +192,9 @@ def worker_loop(stage: StageExecutor, transport):
     rank, world = tp.rank, tp.world_size
     last = rank == world - 1
     H = stage.model.cfg.hidden_size
+    from .graph_decode import DecodeGraphCache
+
+    gcache = DecodeGraphCache(stage)
     while True:
         ctrl = tp.recv_ctrl(rank - 1)
         if ctrl["kind"] == "shutdown":
@@ -178,9 +211,23 @@ def worker_loop(stage: StageExecutor, transport):
                 tp.send_ctrl(ctrl, rank + 1)
             continue
         meta = BatchMeta.unpack(ctrl["meta"])
-        x = tp.recv_tensor((meta.num_tokens, H), stage.model.dtype, rank - 1, slot=ctrl["group"])
+        graphed = gcache.eligible(meta, ctrl["params"])
+        if graphed:
+            e = gcache.entry(meta.num_seqs, meta.block_tables.shape[1], meta.max_ctx_len)
+            x = tp.recv_tensor((meta.num_tokens, H), stage.model.dtype, rank - 1, slot=ctrl["group"], out=e.x)
+        else:
+            x = tp.recv_tensor((meta.num_tokens, H), stage.model.dtype, rank - 1, slot=ctrl["group"])
         try:
-            out = stage.forward(x, meta.to(stage.device))
+            if graphed:
+                e.flat.copy_(ctrl["meta"].pin_memory(), non_blocking=True)
+                out = gcache.run(e)
+                if last:
+                    toks, lp = out
+                    res = StepOutput(toks.tolist(), lp.tolist())
+                    tp.send_ctrl(dict(tokens=res.tokens, logprobs=res.logprobs, top_ids=None, top_logprobs=None), 0)
+                    continue
+            else:
+                out = stage.forward(x, meta.to(stage.device))
             if last:
                 res = stage.sample(out, ctrl["params"], ctrl["contexts"])
                 tp.send_ctrl(dict(tokens=res.tokens, logprobs=res.logprobs, top_ids=res.top_ids,

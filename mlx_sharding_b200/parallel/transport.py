@@ -104,7 +104,10 @@ class TorchDistTransport(ChainTransport):
             dist.send(t, dst, group=self.data_group)  # NCCL: stream-ordered, does not block the host
         self.bytes_sent += t.numel() * t.element_size()
 
-    def recv_tensor(self, shape, dtype, src: int, slot: int = 0) -> torch.Tensor:
+    def recv_tensor(self, shape, dtype, src: int, slot: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if out is not None and self.data_backend != "gloo":
+            dist.recv(out, src, group=self.data_group)  # straight into a static (graph-captured) buffer
+            return out
         if self.data_backend == "gloo":
             wire = torch.int16 if dtype == torch.bfloat16 else dtype
             buf = torch.empty(shape, dtype=wire)

@@ -134,7 +134,8 @@ class ModelProvider:
         page_size = getattr(a, "page_size", 64)
         num_pages = getattr(a, "kv_pages", None)
         if num_pages is None:
-            num_pages = self._default_pages(model, page_size)
+            # every stage of a chain must use the same pool geometry (block ids are global): fixed default there
+            num_pages = 2048 if int(os.environ.get("WORLD_SIZE", "1")) > 1 else self._default_pages(model, page_size)
         stage = StageExecutor(model, num_pages, page_size)
         world = int(os.environ.get("WORLD_SIZE", "1"))
         if world > 1:
@@ -538,10 +539,25 @@ def main(argv=None):
     stubs = []
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
+        # native chain (torchrun): rank 0 serves HTTP + the first stage, every other rank is a stage worker.
+        # Layer ranges default to an even split when neither --start-layer/--end-layer nor the config give them.
         from ..parallel.transport import init_distributed
 
-        init_distributed(device=args.device)
-    needs_remote = args.end_layer is not None
+        rank, _ = init_distributed(device=args.device)
+        if args.start_layer is None and args.end_layer is None and args.model is not None:
+            from ..config import ModelConfig, ShardSpec
+            from ..utils.checkpoint import get_model_path
+
+            cfg = ModelConfig.from_path(get_model_path(args.model))
+            if cfg.start_layer is None:
+                spec = ShardSpec.even_split(cfg.num_hidden_layers, world)[rank]
+                args.start_layer, args.end_layer = spec.start_layer, spec.end_layer
+        if rank != 0:
+            from .shard_server import serve_chain
+
+            return serve_chain(args.model, args.start_layer, args.end_layer, args.device, None,
+                               args.kv_pages or 2048, args.page_size)
+    needs_remote = args.end_layer is not None and world == 1
     if args.model is not None and not needs_remote:
         try:
             from ..config import ModelConfig

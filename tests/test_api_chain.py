@@ -1,0 +1,81 @@
+"""BASELINE config 4 shape on CPU: the OpenAI server on top of a multi-process chain pipeline (torchrun, gloo):
+rank 0 = HTTP + first stage, ranks 1.. = stage workers; `/v1/chat/completions` answers == single-process answers."""
+import http.client
+import json
+import os
+import signal
+import socket
+import subprocess
+import sys
+import time
+
+import pytest
+import torch
+
+from helpers import TINY_LLAMA
+from mlx_sharding_b200.utils.checkpoint import write_synthetic_checkpoint
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _post(port, body):
+    c = http.client.HTTPConnection("127.0.0.1", port, timeout=120)
+    c.request("POST", "/v1/chat/completions", json.dumps(body), {"Content-Type": "application/json"})
+    r = c.getresponse()
+    data = r.read()
+    c.close()
+    return r.status, json.loads(data)
+
+
+def _wait_http(port, proc, timeout=150):
+    t0 = time.time()
+    while time.time() - t0 < timeout:
+        if proc.poll() is not None:
+            raise RuntimeError("server exited early")
+        try:
+            c = http.client.HTTPConnection("127.0.0.1", port, timeout=2)
+            c.request("GET", "/health")
+            if c.getresponse().status == 200:
+                return
+        except OSError:
+            time.sleep(0.5)
+    raise TimeoutError("server did not come up")
+
+
+@pytest.mark.timeout(400)
+def test_chat_completions_over_4_stage_chain(tmp_path):
+    ckpt = write_synthetic_checkpoint(str(tmp_path / "tiny"), TINY_LLAMA, dtype=torch.float32)
+    env = dict(os.environ, PYTHONPATH=REPO, OMP_NUM_THREADS="1")
+    body = {"messages": [{"role": "user", "content": "hello pipeline"}], "max_tokens": 8, "temperature": 0}
+    answers = []
+    for nproc in (1, 4):
+        http_port, master_port = _free_port(), _free_port()
+        if nproc == 1:
+            cmd = [sys.executable, "-m", "shard.openai_api"]
+        else:
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr",
+                   "127.0.0.1", "--master-port", str(master_port), "-m", "shard.openai_api"]
+        cmd += ["--model", ckpt, "--port", str(http_port), "--device", "cpu", "--kv-pages", "64", "--page-size", "16"]
+        proc = subprocess.Popen(cmd, cwd=str(tmp_path), env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                                start_new_session=True)
+        try:
+            _wait_http(http_port, proc)
+            status, j = _post(http_port, body)
+            assert status == 200 and j["object"] == "chat.completions"
+            # a second, concurrent-capable request keeps working (sequence slots are recycled)
+            status2, j2 = _post(http_port, body)
+            assert j2["choices"][0]["logprobs"]["tokens"] == j["choices"][0]["logprobs"]["tokens"]
+            answers.append(j["choices"][0]["logprobs"]["tokens"])
+        finally:
+            os.killpg(proc.pid, signal.SIGTERM)  # exact process group we started
+            try:
+                proc.wait(timeout=20)
+            except subprocess.TimeoutExpired:
+                os.killpg(proc.pid, signal.SIGKILL)
+    assert answers[0] == answers[1] and len(answers[0]) == 8

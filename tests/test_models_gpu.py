@@ -69,3 +69,25 @@ def test_engine_on_gpu_batched():
         assert sum(int(x != y) for x, y in zip(solo, r.output)) <= 1, (solo, r.output)
     hot = eng.generate([1, 2, 3], SamplingParams(temperature=1.0, top_p=0.9), max_tokens=8)
     assert len(hot) == 8
+
+
+def test_engine_graph_decode_matches_eager():
+    """Steady-state decode steps run as captured CUDA graphs (parallel/graph_decode.py) — same tokens as eager."""
+    from mlx_sharding_b200.engine.core import LLMEngine
+    from mlx_sharding_b200.engine.sampler import SamplingParams
+    from mlx_sharding_b200.parallel.pipeline import LocalPipeline
+
+    fast, _ = _pair(GPU_DSV2)
+    prompts = [[5, 6, 7, 8, 9, 10, 11], [100, 50], list(range(20, 60)), [42] * 9]
+    outs = []
+    for use_graphs in (True, False):
+        pipe = LocalPipeline.from_models(fast, num_pages=64, page_size=16)
+        if not use_graphs:
+            pipe.gcache.enabled = False
+        eng = LLMEngine(pipe, num_pages=64, page_size=16)
+        reqs = [eng.submit(p, SamplingParams(), max_tokens=12) for p in prompts]
+        eng.drain()
+        outs.append([r.output for r in reqs])
+        if use_graphs:
+            assert pipe.gcache.captures >= 1 and pipe.gcache.replays >= 5
+    assert outs[0] == outs[1]
