@@ -27,6 +27,7 @@
 #include <unordered_map>
 
 #include "gemm_cluster.cuh"
+#include "gemm_tmap.h"
 #include "launch.h"
 
 namespace b200 {
@@ -265,6 +266,10 @@ cudaError_t dispatch_bn(int bn, const GemmArgs& a, const CUtensorMap& tw, const 
 
 }  // namespace
 
+bool gemm_make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  return make_tmap(m, ptr, rows, cols, ld, box_rows);
+}
+
 int gemm_pick_bn(int max_rows) {
   if (max_rows <= 16) return 16;
   if (max_rows <= 32) return 32;
@@ -287,6 +292,7 @@ cudaError_t gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   int splits = a.splits > 0 ? a.splits : 1;
   const int kb_total = (a.k + kBlockK - 1) / kBlockK;
   if (splits > kb_total) splits = kb_total;
+  if (splits == 1 && a.persistent) return gemm_persistent_launch(a, stream);  // no split-K: persistent tile loop
   if (grouped && (a.n % kTileM) != 0) return cudaErrorInvalidValue;
   if ((a.k % 8) != 0 || (a.n % 8) != 0) return cudaErrorInvalidValue;
   if (splits > 1 && !a.cluster_splitk && (a.workspace == nullptr || a.tile_counters == nullptr)) return cudaErrorInvalidValue;

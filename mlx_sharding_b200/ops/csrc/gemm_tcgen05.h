@@ -59,6 +59,7 @@ struct GemmArgs {
   unsigned int signal_tiles = 0;          // 0 = all tiles of the grid
   // MLX affine-quantised weights (gemm_q_launch): w / w2 point at the packed uint32 codes [rows, k*bits/32];
   // scales / biases are pre-transposed to [k/group, rows] bf16 at load time (TMA-friendly)
+  bool persistent = true;                 // splits == 1: persistent kernel (gemm_persistent.cu)
   bool cluster_splitk = true;             // prefer the DSMEM reduction when it applies (decode shapes)
   int q_bits = 0, q_group = 64;
   const void* q_scales_t = nullptr; const void* q_biases_t = nullptr;
@@ -68,6 +69,7 @@ struct GemmArgs {
 int gemm_pick_bn(int max_rows);
 size_t gemm_workspace_floats(const GemmArgs& a, int bn, int splits);
 cudaError_t gemm_launch(const GemmArgs& a, cudaStream_t stream);
+cudaError_t gemm_persistent_launch(const GemmArgs& a, cudaStream_t stream);
 bool gemm_q_supported(int bits, int group, int k);
 cudaError_t gemm_q_launch(const GemmArgs& a, cudaStream_t stream);
 

@@ -1,0 +1,9 @@
+// Cached TMA descriptor factory shared by the GEMM kernels (defined in gemm_tcgen05.cu).
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace b200 {
+// bf16 row-major [rows, cols] (row stride ld elements) -> tiles of box_rows x 64 elements, 128B swizzle
+bool gemm_make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+}  // namespace b200

@@ -35,10 +35,18 @@ class StageExecutor:
         self.device = model.device
         self.kv = PagedKVCache.for_model(model, num_pages, page_size)
         self.sampler = Sampler(model.ops, self.device, seed) if model.spec.is_last else None
+        import os
+
+        from ..utils.tracing import StageTimer
+
+        self.timer = StageTimer(enabled=os.environ.get("MLXB200_STAGE_TIMING", "0") == "1")
 
     @torch.inference_mode()
     def forward(self, x: torch.Tensor, meta: BatchMeta, all_logits: bool = False) -> torch.Tensor:
-        return self.model.forward(x, meta, self.kv, all_logits)
+        from ..utils.tracing import nvtx_range
+
+        with self.timer.measure(), nvtx_range(f"stage[{self.model.spec.start_layer},{self.model.spec.end_layer}) T={meta.num_tokens}"):
+            return self.model.forward(x, meta, self.kv, all_logits)
 
     @torch.inference_mode()
     def sample(self, logits: torch.Tensor, inp_params, contexts) -> StepOutput:
