@@ -13,7 +13,7 @@
 #include <mutex>
 #include <unordered_map>
 
-#include "gemm_common.cuh"
+#include "gemm_q_common.cuh"
 #include "launch.h"
 
 namespace b200 {
@@ -34,60 +34,6 @@ __host__ __device__ constexpr int q_num_stages(int BN, bool dual, int bits, int 
   s = s > 8 ? 8 : s;
   while (s * q_stage_bytes(BN, dual, bits) < BN * kTileM * out_bytes) ++s;
   return s;
-}
-
-// One thread dequantises half a row of the k-block: 32 weights = 4 chunks of 8 (chunks 4*half .. 4*half+3).
-//
-// int4 fast path (2.5 ALU ops / weight instead of ~5.5): nibbles i and i+4 of a word are isolated together with
-// (w >> 4i) & 0x000F000F, OR-ed with 0x4300'4300 they are the bf16 pair (128 + q_i, 128 + q_{i+4}) exactly; one HSUB2
-// removes the 128 and one HFMA2.BF16 produces bf16(s*q + b) with a *single* rounding; two PRMTs per word pair put
-// the results back in K order.  int8 keeps the fp32 magic-number path (8-bit codes do not fit the bf16 mantissa).
-template <int BITS>
-__device__ __forceinline__ void dequant_half_row(const uint8_t* packed_row, float s, float b, uint8_t* a_tile, int r, int half) {
-  uint8_t* row = a_tile + r * 128;
-  if (BITS == 4) {
-    const uint4 v = reinterpret_cast<const uint4*>(packed_row)[half];  // 4 words = 32 codes
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    const __nv_bfloat162 s2 = __float2bfloat162_rn(s), b2 = __float2bfloat162_rn(b);
-    const uint32_t magic = 0x43004300u;
-    const __nv_bfloat162 c128 = *reinterpret_cast<const __nv_bfloat162*>(&magic);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint32_t x[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t m = ((w[c] >> (4 * i)) & 0x000F000Fu) | magic;  // (128 + q_i, 128 + q_{i+4})
-        __nv_bfloat162 q = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&m), c128);
-        q = __hfma2(s2, q, b2);
-        x[i] = *reinterpret_cast<uint32_t*>(&q);
-      }
-      uint4 o;
-      o.x = __byte_perm(x[0], x[1], 0x5410);  // (v0, v1)
-      o.y = __byte_perm(x[2], x[3], 0x5410);  // (v2, v3)
-      o.z = __byte_perm(x[0], x[1], 0x7632);  // (v4, v5)
-      o.w = __byte_perm(x[2], x[3], 0x7632);  // (v6, v7)
-      const int chunk = 4 * half + c;
-      // 128B swizzle (Swizzle<3,4,3>): 16-byte chunk index XOR (row mod 8)
-      *reinterpret_cast<uint4*>(row + ((chunk ^ (r & 7)) << 4)) = o;
-    }
-  } else {
-    const uint4 v0 = reinterpret_cast<const uint4*>(packed_row)[2 * half], v1 = reinterpret_cast<const uint4*>(packed_row)[2 * half + 1];
-    const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};  // 8 words = 32 codes
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float f[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t x = w[2 * c + (i >> 2)];
-        const float q = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7440u | (i & 3))) - 8388608.0f;
-        f[i] = fmaf(s, q, b);
-      }
-      uint4 o;
-      o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-      const int chunk = 4 * half + c;
-      *reinterpret_cast<uint4*>(row + ((chunk ^ (r & 7)) << 4)) = o;
-    }
-  }
 }
 
 }  // namespace
@@ -305,7 +251,6 @@ bool q_make_tmap(CUtensorMap* m, int kind, const void* ptr, uint64_t d0, uint64_
   return true;
 }
 
-struct QMaps { CUtensorMap wq, wq2, s, b, s2, b2, x; };
 
 template <int BN, bool DUAL, typename OutT, int BITS>
 cudaError_t q_launch_one(const QMaps& t, const GemmParams& p, int group_kblocks, dim3 grid, cudaStream_t stream) {
@@ -344,6 +289,10 @@ cudaError_t q_dispatch(bool dual, bool fp32, int bn, const QMaps& t, const GemmP
 
 }  // namespace
 
+bool gemm_q_make_tmap(CUtensorMap* m, int kind, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld_elems, uint32_t b0, uint32_t b1) {
+  return q_make_tmap(m, kind, ptr, d0, d1, ld_elems, b0, b1);
+}
+
 bool gemm_q_supported(int bits, int group, int k) {
   return (bits == 4 || bits == 8) && (group == 64 || group == 128) && (k % 64) == 0 && (k % group) == 0;
 }
@@ -354,6 +303,7 @@ cudaError_t gemm_q_launch(const GemmArgs& a, cudaStream_t stream) {
   const bool grouped = a.expert_offsets != nullptr;
   const int bn = a.bn > 0 ? a.bn : gemm_pick_bn(a.max_rows);
   int splits = a.splits > 0 ? a.splits : 1;
+  if (splits == 1 && a.persistent) return gemm_q_persistent_launch(a, stream);
   const int kb_total = a.k / kBlockK;
   if (splits > kb_total) splits = kb_total;
   if (grouped && (a.n % kTileM) != 0) return cudaErrorInvalidValue;
