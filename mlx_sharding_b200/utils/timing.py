@@ -28,7 +28,37 @@ class ClockSampler:
         self._stop = threading.Event()
         self._thr: Optional[threading.Thread] = None
 
+    def _poll_nvml(self) -> bool:
+        """Fast path: NVML bindings (no process spawn) — ~1 ms per sample."""
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            try:  # CUDA device index -> physical GPU (CUDA_VISIBLE_DEVICES may reorder / hide devices)
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(self.idx).uuid)
+                h = nv.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:  # noqa: BLE001
+                h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = dict(hw_slowdown=0x8, sw_power_cap=0x4, sw_thermal=0x20, hw_thermal=0x40)
+        except Exception:  # noqa: BLE001
+            return False
+        while not self._stop.is_set():
+            try:
+                r = int(get_reasons(h))
+                on = lambda k: "Active" if r & bits[k] else "Not Active"
+                self.samples.append(dict(sm=float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), sm_max=sm_max,
+                                         power=nv.nvmlDeviceGetPowerUsage(h) / 1000.0, active=hex(r), hw_slowdown=on("hw_slowdown"),
+                                         hw_thermal=on("hw_thermal"), sw_thermal=on("sw_thermal"), sw_power_cap=on("sw_power_cap")))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(min(self.period, 0.02))
+        return True
+
     def _poll(self):
+        if self._poll_nvml():
+            return
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={_QUERY}", "--format=csv,noheader,nounits", "-i",
