@@ -112,6 +112,11 @@ class DeepseekV2Stage(StageModel):
                                    c.norm_topk_prob)
             if "s_gate" in w:
                 h = O.linear(O.gated_up(normed, w["s_gate"], w["s_up"], "silu"), w["s_down"], residual=h)
+            ep = getattr(self, "ep_layers", None)
+            if ep is not None and i in ep:
+                # expert-parallel mode (parallel/ep.py): routed experts are sharded over the ranks of the NVSwitch
+                # domain, tokens travel through the fused dispatch / return kernels
+                return ep[i].forward(normed, idx, wts, residual=h)
             return O.moe_experts(normed, idx, wts, w["e_gate"], w["e_up"], w["e_down"], "silu", residual=h,
                                  **self._final_kwargs(i, T))
         return O.linear(O.gated_up(normed, w["gate"], w["up"], "silu"), w["down"], residual=h,

@@ -86,6 +86,12 @@ def _qpack(W: LinearWeight):
         rows = W.wq.numel() // W.wq.shape[-1]
         ng = K // W.group_size
         wq = W.wq.reshape(rows, W.wq.shape[-1]).contiguous()
+        if W.bits == 4:
+            # load-time re-pack (same bits, kernel-friendly order): nibble j <- code 2j, nibble 4+j <- code 2j+1, so the
+            # kernel's (w >> 4i) & 0x000F000F yields the adjacent pair (v_2i, v_2i+1) directly
+            from ..utils import quant as _q
+
+            wq = _q.repack_int4_pairs(wq).contiguous()
         st = W.scales.reshape(rows, ng).t().contiguous()
         bt = W.biases.reshape(rows, ng).t().contiguous()
         qt = (wq, st, bt)

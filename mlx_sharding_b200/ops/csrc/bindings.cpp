@@ -136,6 +136,9 @@ Tensor grouped_linear(const Tensor& x, const Tensor& w, const c10::optional<Tens
   if (w2.has_value()) { check_bf16(*w2, "w2"); TORCH_CHECK(w2->is_contiguous() && w2->sizes() == w.sizes()); a.w2 = w2->data_ptr(); }
   a.m = (int)R; a.n = (int)N; a.k = (int)K; a.max_rows = (int)std::min<int64_t>(max_rows, R);
   a.num_experts = (int)E; a.expert_offsets = expert_offsets.data_ptr<int>();
+  // token tile sized for ~2x the average rows per expert (not the worst case): less padding in the MMA N dimension and
+  // smaller token-tile loads; experts with more rows simply take further tiles of the persistent tile list
+  a.bn = b200::gemm_pick_bn((int)std::min<int64_t>(a.max_rows, std::max<int64_t>(16, 2 * ((R + E - 1) / E))));
   a.out = out.data_ptr(); a.ld_out = N; a.out_fp32 = out_fp32; a.act = (int)act; a.splits = 1;
   LAUNCH_OK(b200::gemm_launch(a, cur_stream()));
   return out;
@@ -212,6 +215,9 @@ Tensor grouped_linear_q(const Tensor& x, const Tensor& wq, const Tensor& scales_
   }
   a.m = (int)R; a.n = (int)N; a.k = (int)K; a.max_rows = (int)std::min<int64_t>(max_rows, R);
   a.num_experts = (int)E; a.expert_offsets = expert_offsets.data_ptr<int>();
+  // token tile sized for ~2x the average rows per expert (not the worst case): less padding in the MMA N dimension and
+  // smaller token-tile loads; experts with more rows simply take further tiles of the persistent tile list
+  a.bn = b200::gemm_pick_bn((int)std::min<int64_t>(a.max_rows, std::max<int64_t>(16, 2 * ((R + E - 1) / E))));
   a.out = out.data_ptr(); a.ld_out = N; a.out_fp32 = out_fp32; a.act = (int)act; a.splits = 1;
   LAUNCH_OK(b200::gemm_q_launch(a, cur_stream()));
   return out;

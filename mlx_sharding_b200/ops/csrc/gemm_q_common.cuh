@@ -8,10 +8,9 @@ namespace gemm {
 
 // One thread dequantises half a row of the k-block: 32 weights = 4 chunks of 8 (chunks 4*half .. 4*half+3).
 //
-// int4 fast path (2.5 ALU ops / weight instead of ~5.5): nibbles i and i+4 of a word are isolated together with
+// int4 fast path (2 ALU ops / weight instead of ~5.5): nibbles i and i+4 of a (load-time re-packed) word are isolated together with
 // (w >> 4i) & 0x000F000F, OR-ed with 0x4300'4300 they are the bf16 pair (128 + q_i, 128 + q_{i+4}) exactly; one HSUB2
-// removes the 128 and one HFMA2.BF16 produces bf16(s*q + b) with a *single* rounding; two PRMTs per word pair put
-// the results back in K order.  int8 keeps the fp32 magic-number path (8-bit codes do not fit the bf16 mantissa).
+// removes the 128 and one HFMA2.BF16 produces bf16(s*q + b) with a *single* rounding.  int8 keeps the fp32 magic-number path (8-bit codes do not fit the bf16 mantissa).
 template <int BITS>
 __device__ __forceinline__ void dequant_half_row(const uint8_t* packed_row, float s, float b, uint8_t* a_tile, int r, int half) {
   uint8_t* row = a_tile + r * 128;
@@ -32,10 +31,9 @@ __device__ __forceinline__ void dequant_half_row(const uint8_t* packed_row, floa
         x[i] = *reinterpret_cast<uint32_t*>(&q);
       }
       uint4 o;
-      o.x = __byte_perm(x[0], x[1], 0x5410);  // (v0, v1)
-      o.y = __byte_perm(x[2], x[3], 0x5410);  // (v2, v3)
-      o.z = __byte_perm(x[0], x[1], 0x7632);  // (v4, v5)
-      o.w = __byte_perm(x[2], x[3], 0x7632);  // (v6, v7)
+      // the loader re-packs every word so that nibble j holds v_{2j} and nibble 4+j holds v_{2j+1} (same bits, TMA/UMMA
+      // friendly order — ops/b200.py::_qpack): the masked pairs come out already in K order, no PRMT needed
+      o.x = x[0]; o.y = x[1]; o.z = x[2]; o.w = x[3];
       const int chunk = 4 * half + c;
       // 128B swizzle (Swizzle<3,4,3>): 16-byte chunk index XOR (row mod 8)
       *reinterpret_cast<uint4*>(row + ((chunk ^ (r & 7)) << 4)) = o;

@@ -117,3 +117,20 @@ class ExpertParallelMoE:
         if key not in cls._ident:
             cls._ident[key] = torch.arange(n, dtype=torch.int32, device=device)
         return cls._ident[key]
+
+
+def enable_expert_parallel(model, max_tokens: int = 256, group=None) -> EPBuffers:
+    """Switch a DeepSeek-V2 stage model (every rank holding the *same* layers, data-parallel over tokens) to
+    expert-parallel execution: each MoE layer keeps only its ``E / world`` local experts and routes tokens through the
+    fused all-to-all.  The full expert banks are dropped from this rank afterwards (1/world of the MoE memory)."""
+    cfg = model.cfg
+    bufs = EPBuffers(cfg.hidden_size, max_tokens, cfg.num_experts_per_tok, group=group)
+    model.ep_layers = {}
+    for i, w in model.layer_weights.items():
+        if "router" not in w:
+            continue
+        model.ep_layers[i] = ExpertParallelMoE(bufs, w["e_gate"], w["e_up"], w["e_down"], cfg.n_routed_experts)
+        for k in ("e_gate", "e_up", "e_down"):
+            w[k] = None  # free the un-sharded bank
+    torch.cuda.empty_cache()
+    return bufs

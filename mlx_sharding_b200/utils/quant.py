@@ -91,3 +91,16 @@ def dequantize(wq: torch.Tensor, scales: torch.Tensor, biases: torch.Tensor, gro
 
 def quantized_in_features(wq: torch.Tensor, bits: int) -> int:
     return wq.shape[-1] * (32 // bits)
+
+
+def repack_int4_pairs(wq: torch.Tensor) -> torch.Tensor:
+    """Kernel-friendly nibble order for the in-kernel dequant GEMM (same bits, different order): nibble ``j`` of each
+    word <- code ``2j``, nibble ``4 + j`` <- code ``2j + 1``, so ``(w >> 4i) & 0x000F000F`` isolates the adjacent pair
+    ``(v_2i, v_2i+1)`` as two 16-bit lanes.  Works word-wise (no per-code expansion)."""
+    w = _as_u32(wq)
+    out = torch.zeros_like(w)
+    for j in range(4):
+        out |= ((w >> (8 * j)) & 0xF) << (4 * j)
+        out |= ((w >> (8 * j + 4)) & 0xF) << (16 + 4 * j)
+    out = torch.where(out >= 2 ** 31, out - 2 ** 32, out)
+    return out.to(torch.int32)
