@@ -48,6 +48,7 @@ def parse_args(argv=None):
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-graphs", action="store_true")
     p.add_argument("--page-size", type=int, default=64)
+    p.add_argument("--whole-layers", action="store_true", help="stage boundaries only between layers (reference-style split)")
     return p.parse_args(argv)
 
 
@@ -131,14 +132,15 @@ def main(argv=None):
 
     cfgd = model_config(args.model, args.layers)
     cfg = ModelConfig.from_dict(cfgd)
-    spec = balanced_split(cfg, world)[rank]
-    t0 = time.time()
     qcfg = dict(group_size=64, bits=args.quant) if args.quant else None
-    model = random_model(cfgd, spec.start_layer, spec.end_layer, dtype=torch.bfloat16, device=dev, backend=backend, seed=1,
-                         quantization=qcfg)
+    cfg.quantization = qcfg  # the partitioner's byte model follows the weight format
+    # stage boundaries may fall between the attention and the MLP block of a layer (finer balance than whole layers)
+    spec = balanced_split(cfg, world, half_layers=not args.whole_layers)[rank]
+    t0 = time.time()
+    model = random_model(cfgd, dtype=torch.bfloat16, device=dev, backend=backend, seed=1, quantization=qcfg, spec=spec)
     torch.cuda.synchronize()
     log = lambda *a: print(f"[rank {rank}]", *a, file=sys.stderr, flush=True)
-    log(f"layers [{spec.start_layer},{spec.end_layer}) weights {model.weight_bytes() / 1e9:.2f} GB built in {time.time() - t0:.1f}s")
+    log(f"layers {spec.describe()} weights {model.weight_bytes() / 1e9:.2f} GB built in {time.time() - t0:.1f}s")
 
     G, B, S, PS = (args.groups or world), args.batch, args.prompt_len, args.page_size
     total_steps = args.warmup + args.steps
@@ -268,7 +270,8 @@ def main(argv=None):
                        "cuda_graphs": loop.use_graphs, "kv_page_size": PS,
                        "weights": f"mlx-affine-int{args.quant}-g64 (in-kernel dequant)" if args.quant else "bf16",
                        "l2": "weights streamed per step (31 GB/stage-set) far exceed the 126 MB L2; no explicit flush",
-                       "layers": [spec.start_layer, spec.end_layer] if world == 1 else "cost-balanced"},
+                       "layers": [spec.start_layer, spec.end_layer] if world == 1 else
+                       ("cost-balanced, whole layers" if args.whole_layers else "cost-balanced, half-layer (attention | MLP) boundaries")},
             "ttft_p50_ms": round(ttft_p50 * 1e3, 3),
             "ttft_note": f"p50 wall time, one {S}-token prompt through all {world} stage(s) to its first sampled token",
             "ttft_microbatch_ms": round(ttft_batch * 1e3, 2),

@@ -37,20 +37,28 @@ class ShardSpec:
     start_layer: int
     end_layer: int
     num_layers: int
+    # Half-layer boundaries (no reference counterpart; used by ``parallel.partition.balanced_split(half_layers=True)``).
+    # A decoder layer is two residual blocks (attention, MLP) that only exchange the residual stream ``h``, so a
+    # stage boundary may also fall *between* them: ``skip_first_attn`` = the attention block of ``start_layer`` ran
+    # on the previous stage; ``defer_last_mlp`` = the MLP block of ``end_layer - 1`` runs on the next stage.
+    skip_first_attn: bool = False
+    defer_last_mlp: bool = False
 
     def __post_init__(self):
         if not (0 <= self.start_layer < self.end_layer <= self.num_layers):
             raise ValueError(
                 f"invalid layer range [{self.start_layer}, {self.end_layer}) for {self.num_layers} layers"
             )
+        if self.skip_first_attn and self.defer_last_mlp and self.num_local_layers == 1:
+            raise ValueError("empty stage: both blocks of its only layer live elsewhere")
 
     @property
     def is_first(self) -> bool:
-        return self.start_layer == 0
+        return self.start_layer == 0 and not self.skip_first_attn
 
     @property
     def is_last(self) -> bool:
-        return self.end_layer == self.num_layers
+        return self.end_layer == self.num_layers and not self.defer_last_mlp
 
     @property
     def num_local_layers(self) -> int:
@@ -61,6 +69,25 @@ class ShardSpec:
 
     def layers(self):
         return range(self.start_layer, self.end_layer)
+
+    def runs_attn(self, i: int) -> bool:
+        return self.owns_layer(i) and not (self.skip_first_attn and i == self.start_layer)
+
+    def runs_mlp(self, i: int) -> bool:
+        return self.owns_layer(i) and not (self.defer_last_mlp and i == self.end_layer - 1)
+
+    def attn_layers(self):
+        """Layers whose attention block (and therefore KV cache) lives on this stage."""
+        return [i for i in self.layers() if self.runs_attn(i)]
+
+    @property
+    def num_kv_layers(self) -> int:
+        return len(self.attn_layers())
+
+    def describe(self) -> str:
+        a = f"{self.start_layer}{'.5' if self.skip_first_attn else ''}"
+        b = f"{self.end_layer - 1}.5" if self.defer_last_mlp else f"{self.end_layer}"
+        return f"[{a}, {b})"
 
     @staticmethod
     def even_split(num_layers: int, num_stages: int):

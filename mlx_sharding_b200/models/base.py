@@ -101,6 +101,7 @@ class StageModel:
         # fused stage boundary (parallel/p2p_fused.py): when set to (out_rows_tensor, flag_ptr) the last
         # kernel of the last local layer stores straight into that (peer-mapped) buffer and bumps the flag
         self.boundary = None
+        self.boundary_fused = False
 
     # reference-compatible surface ------------------------------------------------------------
     @property
@@ -122,7 +123,7 @@ class StageModel:
 
     def kv_geometry(self):
         """(local_layers, kv_heads, d_k, d_v) for the paged cache."""
-        return self.spec.num_local_layers, self.cfg.kv_heads, self.cfg.qk_head_dim, self.cfg.v_dim
+        return self.spec.num_kv_layers, self.cfg.kv_heads, self.cfg.qk_head_dim, self.cfg.v_dim
 
     # weights ---------------------------------------------------------------------------------
     def _lin(self, sd, prefix) -> LinearWeight:
@@ -135,7 +136,7 @@ class StageModel:
         """Filter a full checkpoint to this stage (reference ``Model.sanitize``)."""
         from ..utils.checkpoint import key_in_shard
 
-        return {k: v for k, v in sd.items() if key_in_shard(k, self.spec, self.cfg.tie_word_embeddings)}
+        return {k: v for k, v in sd.items() if key_in_shard(k, self.spec, self.cfg.tie_word_embeddings, self.cfg.model_type)}
 
     def load_state(self, sd: Dict[str, torch.Tensor], strict: bool = True):
         sd = self.sanitize(dict(sd))
@@ -145,7 +146,8 @@ class StageModel:
             for k in [k for k in sd if k.startswith("model.embed_tokens")]:
                 sd.pop(k)
         for i in self.spec.layers():
-            self.layer_weights[i] = self._load_layer(sd, i)
+            # half-layer stage boundary: the other block's tensors belong to the neighbouring stage (sanitize dropped them)
+            self.layer_weights[i] = self._load_layer(sd, i, self.spec.runs_attn(i), self.spec.runs_mlp(i))
         if self.spec.is_last:
             self.norm_w = self._vec(sd, "model.norm.weight")
             if self.cfg.tie_word_embeddings:
@@ -164,7 +166,7 @@ class StageModel:
     def _post_load(self):
         pass
 
-    def _load_layer(self, sd, i) -> dict:
+    def _load_layer(self, sd, i, attn: bool = True, mlp: bool = True) -> dict:
         raise NotImplementedError
 
     def _make_rope(self) -> RopeSpec:
@@ -198,14 +200,25 @@ class StageModel:
     def embed(self, ids: torch.Tensor) -> torch.Tensor:
         return self.ops.embed(ids, self.embed_tokens, 1.0, self.dtype)
 
-    def layer_forward(self, i: int, h: torch.Tensor, meta: BatchMeta, kpool, vpool) -> torch.Tensor:
+    def attn_block(self, i: int, h: torch.Tensor, meta: BatchMeta, kpool, vpool) -> torch.Tensor:
+        """``h + attention(norm(h))`` of layer ``i`` (appends this step's K/V to the paged pool)."""
         raise NotImplementedError
 
-    def _final_kwargs(self, i: int, T: int) -> dict:
-        """Extra kwargs for the last op of layer ``i``: the fused P2P store + signal on a stage boundary."""
-        if self.boundary is None or self.spec.is_last or i != self.spec.end_layer - 1:
+    def mlp_block(self, i: int, h: torch.Tensor, meta: BatchMeta) -> torch.Tensor:
+        """``h + mlp(norm(h))`` of layer ``i``."""
+        raise NotImplementedError
+
+    def layer_forward(self, i: int, h: torch.Tensor, meta: BatchMeta, kpool, vpool) -> torch.Tensor:
+        return self.mlp_block(i, self.attn_block(i, h, meta, kpool, vpool), meta)
+
+    def _final_kwargs(self, i: int, T: int, block: str = "mlp") -> dict:
+        """Extra kwargs for the last op of ``block`` of layer ``i``: when that op is the last kernel of this stage and a
+        fused boundary is armed, it stores straight into the next stage's inbox and bumps its flag."""
+        sp = self.spec
+        if self.boundary is None or sp.is_last or i != sp.end_layer - 1 or (block == "attn") != sp.defer_last_mlp:
             return {}
         out, flag_ptr = self.boundary
+        self.boundary_fused = True
         return dict(out=out[:T], signal=(flag_ptr, 0))
 
     def head(self, h: torch.Tensor, meta: BatchMeta, all_logits: bool = False) -> torch.Tensor:
@@ -228,8 +241,14 @@ class StageModel:
             h = self.embed(x)
         else:
             h = x.to(self.dtype)
-        for li, i in enumerate(self.spec.layers()):
-            h = self.layer_forward(i, h, meta, kv.k[li], kv.v[li])
+        sp, li = self.spec, 0
+        self.boundary_fused = False  # set by _final_kwargs when the stage's last kernel took the fused hand-off
+        for i in sp.layers():
+            if sp.runs_attn(i):
+                h = self.attn_block(i, h, meta, kv.k[li], kv.v[li])
+                li += 1
+            if sp.runs_mlp(i):
+                h = self.mlp_block(i, h, meta)
         if self.spec.is_last:
             return self.head(h, meta, all_logits)
         return h

@@ -51,24 +51,25 @@ class DeepseekV2Stage(StageModel):
             sd[f"{prefix}.switch_mlp.{proj}.{kind}"] = torch.stack([d[e] for e in range(n)])
         return sd
 
-    def _load_layer(self, sd, i) -> dict:
+    def _load_layer(self, sd, i, attn=True, mlp=True) -> dict:
         c = self.cfg
         p = f"model.layers.{i}"
         a = p + ".self_attn"
-        w = dict(
-            in_ln=self._vec(sd, p + ".input_layernorm.weight"),
-            post_ln=self._vec(sd, p + ".post_attention_layernorm.weight"),
-            kv_a_ln=self._vec(sd, a + ".kv_a_layernorm.weight"),
-            kv_b=self._lin(sd, a + ".kv_b_proj"),
-            o=self._lin(sd, a + ".o_proj"),
-        )
-        kv_a = self._lin(sd, a + ".kv_a_proj_with_mqa")
-        if c.q_lora_rank is None:
-            w["qkv_a"] = LinearWeight.concat([self._lin(sd, a + ".q_proj"), kv_a])
-        else:
-            w["q_a_kv_a"] = LinearWeight.concat([self._lin(sd, a + ".q_a_proj"), kv_a])
-            w["q_a_ln"] = self._vec(sd, a + ".q_a_layernorm.weight")
-            w["q_b"] = self._lin(sd, a + ".q_b_proj")
+        w = {}
+        if attn:
+            w.update(in_ln=self._vec(sd, p + ".input_layernorm.weight"),
+                     kv_a_ln=self._vec(sd, a + ".kv_a_layernorm.weight"),
+                     kv_b=self._lin(sd, a + ".kv_b_proj"), o=self._lin(sd, a + ".o_proj"))
+            kv_a = self._lin(sd, a + ".kv_a_proj_with_mqa")
+            if c.q_lora_rank is None:
+                w["qkv_a"] = LinearWeight.concat([self._lin(sd, a + ".q_proj"), kv_a])
+            else:
+                w["q_a_kv_a"] = LinearWeight.concat([self._lin(sd, a + ".q_a_proj"), kv_a])
+                w["q_a_ln"] = self._vec(sd, a + ".q_a_layernorm.weight")
+                w["q_b"] = self._lin(sd, a + ".q_b_proj")
+        if not mlp:
+            return w
+        w["post_ln"] = self._vec(sd, p + ".post_attention_layernorm.weight")
         m = p + ".mlp"
         if c.is_moe_layer(i):
             w["router"] = sd.pop(m + ".gate.weight").to(device=self.device, dtype=self.dtype)
@@ -82,7 +83,7 @@ class DeepseekV2Stage(StageModel):
                 w[n] = self._lin(sd, f"{m}.{n}_proj")
         return w
 
-    def layer_forward(self, i, h, meta: BatchMeta, kpool, vpool):
+    def attn_block(self, i, h, meta: BatchMeta, kpool, vpool):
         O, c, w = self.ops, self.cfg, self.layer_weights[i]
         T = h.shape[0]
         nh, nope, rd, vd, lr = (c.num_attention_heads, c.qk_nope_head_dim, c.qk_rope_head_dim,
@@ -104,7 +105,11 @@ class DeepseekV2Stage(StageModel):
         # rope(q_pe), rope(k_pe) and the cache append K=[k_nope|k_pe], V: one fused launch
         O.mla_rope_kv_write(q, k_pe, kv, kpool, vpool, meta, self.rope, nope, vd)
         attn = O.paged_attention(q, kpool, vpool, meta, c.attn_scale, 0.0)
-        h = O.linear(attn.reshape(T, nh * vd), w["o"], residual=h)
+        return O.linear(attn.reshape(T, nh * vd), w["o"], residual=h, **self._final_kwargs(i, T, "attn"))
+
+    def mlp_block(self, i, h, meta: BatchMeta):
+        O, c, w = self.ops, self.cfg, self.layer_weights[i]
+        T = h.shape[0]
         normed = O.rmsnorm(h, w["post_ln"], c.rms_norm_eps)
         if "router" in w:
             idx, wts = O.moe_route(normed, w["router"], c.num_experts_per_tok, c.topk_method,
@@ -118,9 +123,9 @@ class DeepseekV2Stage(StageModel):
                 # domain, tokens travel through the fused dispatch / return kernels
                 return ep[i].forward(normed, idx, wts, residual=h)
             return O.moe_experts(normed, idx, wts, w["e_gate"], w["e_up"], w["e_down"], "silu", residual=h,
-                                 **self._final_kwargs(i, T))
+                                 **self._final_kwargs(i, T, "mlp"))
         return O.linear(O.gated_up(normed, w["gate"], w["up"], "silu"), w["down"], residual=h,
-                        **self._final_kwargs(i, T))
+                        **self._final_kwargs(i, T, "mlp"))
 
 
 Model = DeepseekV2Stage

@@ -18,25 +18,33 @@ class Gemma2Stage(LlamaStage):
     act = "gelu_tanh"
     gemma = True
 
-    def _load_layer(self, sd, i) -> dict:
-        w = super()._load_layer(sd, i)
+    PRE_MLP_NORM = "pre_feedforward_layernorm"
+
+    def _load_layer(self, sd, i, attn=True, mlp=True) -> dict:
+        w = super()._load_layer(sd, i, attn, mlp)
         p = f"model.layers.{i}"
-        w["pre_ffn_ln"] = self._vec(sd, p + ".pre_feedforward_layernorm.weight")
-        w["post_ffn_ln"] = self._vec(sd, p + ".post_feedforward_layernorm.weight")
+        if attn:
+            w["post_ln"] = self._vec(sd, p + ".post_attention_layernorm.weight")
+        if mlp:
+            w["post_ffn_ln"] = self._vec(sd, p + ".post_feedforward_layernorm.weight")
         return w
 
     def embed(self, ids):
         # reference gemma2.py:42-43: h = embed(ids) * sqrt(hidden_size)
         return self.ops.embed(ids, self.embed_tokens, math.sqrt(self.cfg.hidden_size), self.dtype)
 
-    def layer_forward(self, i, h, meta, kpool, vpool):
+    def attn_block(self, i, h, meta, kpool, vpool):
         O, c, w = self.ops, self.cfg, self.layer_weights[i]
         eps = c.rms_norm_eps
         normed = O.rmsnorm(h, w["in_ln"], eps, True)
         attn = self._attention(w, normed, meta, kpool, vpool)
         a = O.linear(attn, w["o"])
-        h = O.rmsnorm(a, w["post_ln"], eps, True, residual=h)
-        normed = O.rmsnorm(h, w["pre_ffn_ln"], eps, True)
+        return O.rmsnorm(a, w["post_ln"], eps, True, residual=h)
+
+    def mlp_block(self, i, h, meta):
+        O, c, w = self.ops, self.cfg, self.layer_weights[i]
+        eps = c.rms_norm_eps
+        normed = O.rmsnorm(h, w["mlp_ln"], eps, True)
         act = O.gated_up(normed, w["gate"], w["up"], self.act)
         m = O.linear(act, w["down"])
         return O.rmsnorm(m, w["post_ffn_ln"], eps, True, residual=h)

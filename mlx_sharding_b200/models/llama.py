@@ -20,23 +20,23 @@ class LlamaStage(StageModel):
     arch = "llama"
     act = "silu"
     gemma = False
+    PRE_MLP_NORM = "post_attention_layernorm"   # checkpoint name of the norm in front of the MLP block
 
     def _make_rope(self):
         return llama_rope_spec(self.cfg)
 
-    def _load_layer(self, sd, i) -> dict:
+    def _load_layer(self, sd, i, attn=True, mlp=True) -> dict:
         p = f"model.layers.{i}"
         a = p + ".self_attn"
-        q, k, v = (self._lin(sd, f"{a}.{n}_proj") for n in ("q", "k", "v"))
-        w = dict(
-            in_ln=self._vec(sd, p + ".input_layernorm.weight"),
-            post_ln=self._vec(sd, p + ".post_attention_layernorm.weight"),
-            qkv=LinearWeight.concat([q, k, v]),
-            o=self._lin(sd, a + ".o_proj"),
-            gate=self._lin(sd, p + ".mlp.gate_proj"),
-            up=self._lin(sd, p + ".mlp.up_proj"),
-            down=self._lin(sd, p + ".mlp.down_proj"),
-        )
+        w = {}
+        if attn:
+            q, k, v = (self._lin(sd, f"{a}.{n}_proj") for n in ("q", "k", "v"))
+            w.update(in_ln=self._vec(sd, p + ".input_layernorm.weight"), qkv=LinearWeight.concat([q, k, v]),
+                     o=self._lin(sd, a + ".o_proj"))
+        if mlp:
+            w.update(mlp_ln=self._vec(sd, f"{p}.{self.PRE_MLP_NORM}.weight"),
+                     gate=self._lin(sd, p + ".mlp.gate_proj"), up=self._lin(sd, p + ".mlp.up_proj"),
+                     down=self._lin(sd, p + ".mlp.down_proj"))
         return w
 
     def _attention(self, w, normed: torch.Tensor, meta: BatchMeta, kpool, vpool) -> torch.Tensor:
@@ -54,14 +54,17 @@ class LlamaStage(StageModel):
                                  float(c.attn_logit_softcapping or 0.0) if self.gemma else 0.0)
         return attn.reshape(T, nh * hd)
 
-    def layer_forward(self, i, h, meta, kpool, vpool):
+    def attn_block(self, i, h, meta, kpool, vpool):
         O, c, w = self.ops, self.cfg, self.layer_weights[i]
         normed = O.rmsnorm(h, w["in_ln"], c.rms_norm_eps)
         attn = self._attention(w, normed, meta, kpool, vpool)
-        h = O.linear(attn, w["o"], residual=h)
-        normed = O.rmsnorm(h, w["post_ln"], c.rms_norm_eps)
+        return O.linear(attn, w["o"], residual=h, **self._final_kwargs(i, h.shape[0], "attn"))
+
+    def mlp_block(self, i, h, meta):
+        O, c, w = self.ops, self.cfg, self.layer_weights[i]
+        normed = O.rmsnorm(h, w["mlp_ln"], c.rms_norm_eps)
         act = O.gated_up(normed, w["gate"], w["up"], self.act)
-        return O.linear(act, w["down"], residual=h, **self._final_kwargs(i, h.shape[0]))
+        return O.linear(act, w["down"], residual=h, **self._final_kwargs(i, h.shape[0], "mlp"))
 
 
 Model = LlamaStage

@@ -115,8 +115,8 @@ class DecodeLoop:
                 self.p2p.send_tokens(toks, g)
             else:
                 st.tokens.copy_(toks)
-        elif self.transport == "fused" and m.arch == "gemma2":
-            self.p2p.send_hidden(out, g)  # Gemma-2 ends in a norm: un-fused copy + signal
+        elif self.transport == "fused" and not m.boundary_fused:
+            self.p2p.send_hidden(out, g)  # the stage's last kernel has no fused epilogue (Gemma-2 ends in a norm): copy + signal
         if self.dev.type == "cuda" and m.backend_name == "b200":
             O.C().advance_meta(st.positions, st.context_lens, st.slot_mapping, st.block_tables, self.page_size)
         else:

@@ -46,13 +46,24 @@ def get_model_path(path_or_hf_repo: str) -> str:
         ) from e
 
 
-def key_in_shard(key: str, spec: ShardSpec, tied_embeddings: bool = False) -> bool:
-    """True if checkpoint tensor ``key`` belongs to stage ``spec``."""
+def is_attn_key(key: str, model_type: str = "") -> bool:
+    """True if a per-layer tensor belongs to the layer's *attention* block (else: its MLP block).  Gemma-2's
+    ``post_attention_layernorm`` normalises the attention output; for Llama / DeepSeek that name is the pre-MLP norm."""
+    if ".self_attn." in key or ".input_layernorm." in key:
+        return True
+    return model_type == "gemma2" and ".post_attention_layernorm." in key
+
+
+def key_in_shard(key: str, spec: ShardSpec, tied_embeddings: bool = False, model_type: str = "") -> bool:
+    """True if checkpoint tensor ``key`` belongs to stage ``spec`` (half-layer boundaries included)."""
     if "rotary_emb.inv_freq" in key:
         return False
     m = _LAYER_RE.match(key)
     if m:
-        return spec.owns_layer(int(m.group(1)))
+        i = int(m.group(1))
+        if not spec.owns_layer(i):
+            return False
+        return spec.runs_attn(i) if is_attn_key(key, model_type) else spec.runs_mlp(i)
     if key.startswith("model.embed_tokens"):
         return spec.is_first or (spec.is_last and tied_embeddings)
     if key.startswith("model.norm") or key.startswith("lm_head"):
@@ -77,8 +88,8 @@ def iter_safetensors(model_path: str, keep: Optional[Callable[[str], bool]] = No
 
 
 def load_shard_tensors(model_path: str, spec: ShardSpec, tied: bool = False,
-                       device: str = "cpu") -> Dict[str, torch.Tensor]:
-    return dict(iter_safetensors(model_path, lambda k: key_in_shard(k, spec, tied), device=device))
+                       device: str = "cpu", model_type: str = "") -> Dict[str, torch.Tensor]:
+    return dict(iter_safetensors(model_path, lambda k: key_in_shard(k, spec, tied, model_type), device=device))
 
 
 def save_safetensors(path: str, tensors: Dict[str, torch.Tensor]):
@@ -190,13 +201,19 @@ def random_state_dict(cfg: ModelConfig, spec: Optional[ShardSpec] = None, dtype=
     for i in spec.layers():
         p = f"model.layers.{i}"
         s0 = 100 + i * 50
-        yield from norm(p + ".input_layernorm", H, s0)
-        yield from norm(p + ".post_attention_layernorm", H, s0 + 1)
-        if cfg.model_type == "gemma2":
+        ra, rm = spec.runs_attn(i), spec.runs_mlp(i)
+        gem = cfg.model_type == "gemma2"
+        if ra:
+            yield from norm(p + ".input_layernorm", H, s0)
+        if (ra if gem else rm):
+            yield from norm(p + ".post_attention_layernorm", H, s0 + 1)
+        if gem and rm:
             yield from norm(p + ".pre_feedforward_layernorm", H, s0 + 2)
             yield from norm(p + ".post_feedforward_layernorm", H, s0 + 3)
         a = p + ".self_attn"
-        if cfg.model_type == "deepseek_v2":
+        if not ra:
+            pass
+        elif cfg.model_type == "deepseek_v2":
             nh = cfg.num_attention_heads
             qd = cfg.qk_nope_head_dim + cfg.qk_rope_head_dim
             if cfg.q_lora_rank is None:
@@ -217,6 +234,8 @@ def random_state_dict(cfg: ModelConfig, spec: Optional[ShardSpec] = None, dtype=
             yield from lin(a + ".v_proj", cfg.num_key_value_heads * hd, H, s0 + 6, bias=cfg.attention_bias)
             yield from lin(a + ".o_proj", H, cfg.num_attention_heads * hd, s0 + 7, bias=cfg.attention_bias)
         m = p + ".mlp"
+        if not rm:
+            continue
         if cfg.is_moe_layer(i):
             E, I = cfg.n_routed_experts, cfg.moe_intermediate_size
             gen.manual_seed(seed * 1000003 + s0 + 11)

@@ -21,35 +21,37 @@ log = logging.getLogger(__name__)
 
 
 def load_model(path_or_hf_repo: str, start_layer: Optional[int] = None, end_layer: Optional[int] = None,
-               dtype: Optional[torch.dtype] = None, device: Optional[str] = None, backend: Optional[str] = None):
+               dtype: Optional[torch.dtype] = None, device: Optional[str] = None, backend: Optional[str] = None,
+               spec=None):
+    """``spec`` (a ``ShardSpec``, e.g. from ``parallel.partition.balanced_split``) overrides the layer bounds."""
     model_path = get_model_path(path_or_hf_repo)
     cfg = ModelConfig.from_path(model_path)
-    spec = cfg.shard(start_layer, end_layer)
+    spec = spec or cfg.shard(start_layer, end_layer)
     device = device or ("cuda" if torch.cuda.is_available() else "cpu")
     if dtype is None:
         dtype = torch.bfloat16 if torch.device(device).type == "cuda" else torch.float32
     model = build_stage(cfg, spec, dtype, device, backend)
     tied = cfg.tie_word_embeddings
     # HF-style per-expert keys also belong to the layer range, key_in_shard handles them by prefix
-    sd = dict(iter_safetensors(model_path, lambda k: key_in_shard(k, spec, tied)))
+    sd = dict(iter_safetensors(model_path, lambda k: key_in_shard(k, spec, tied, cfg.model_type)))
     if not sd:
         raise ValueError(f"no tensors for layers [{spec.start_layer}, {spec.end_layer}) in {model_path}")
     model.load_state(sd)
-    log.info("loaded %s layers [%d,%d) of %s (%.2f GB) on %s", cfg.model_type, spec.start_layer, spec.end_layer,
+    log.info("loaded %s layers %s of %s (%.2f GB) on %s", cfg.model_type, spec.describe(),
              model_path, model.weight_bytes() / 1e9, device)
     return model
 
 
 def random_model(config: dict, start_layer: Optional[int] = None, end_layer: Optional[int] = None,
                  dtype=torch.bfloat16, device="cpu", backend: Optional[str] = None, seed: int = 0,
-                 quantization: Optional[dict] = None):
+                 quantization: Optional[dict] = None, spec=None):
     """Random-init stage directly on ``device`` (no disk round trip) — used by the benchmarks on the
     offline GPU box; key layout and shapes are identical to an mlx-community checkpoint."""
     config = dict(config)
     if quantization is not None:
         config["quantization"] = dict(quantization)
     cfg = ModelConfig.from_dict(config)
-    spec = cfg.shard(start_layer, end_layer)
+    spec = spec or cfg.shard(start_layer, end_layer)
     model = build_stage(cfg, spec, dtype, device, backend)
     sd = dict(random_state_dict(cfg, spec, dtype=dtype, device=device, seed=seed, quantization=quantization))
     model.load_state(sd)

@@ -17,12 +17,20 @@ from mlx_sharding_b200.parallel.pipeline import StageExecutor  # noqa: E402
 from mlx_sharding_b200.utils.loader import random_model  # noqa: E402
 
 
-def run(cfgd, transport, steps=6, B=16, S=24, PS=16):
+def _half_layer_specs(L, world):
+    """Every interior boundary falls between the attention and the MLP block of a layer."""
+    cuts = [0] + [2 * (L * r // world) + 1 for r in range(1, world)] + [2 * L]
+    return [ShardSpec(a // 2, (b + 1) // 2, L, skip_first_attn=bool(a % 2), defer_last_mlp=bool(b % 2))
+            for a, b in zip(cuts[:-1], cuts[1:])]
+
+
+def run(cfgd, transport, steps=6, B=16, S=24, PS=16, half=False):
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = torch.device("cuda", torch.cuda.current_device())
     cfg = ModelConfig.from_dict(cfgd)
-    spec = ShardSpec.even_split(cfg.num_hidden_layers, world)[rank]
-    model = random_model(cfgd, spec.start_layer, spec.end_layer, device=dev, backend="b200", seed=3)
+    L = cfg.num_hidden_layers
+    spec = (_half_layer_specs(L, world) if half else ShardSpec.even_split(L, world))[rank]
+    model = random_model(cfgd, device=dev, backend="b200", seed=3, spec=spec)
     G = world
     pages_per_seq = (S + steps + 4 + PS - 1) // PS
     stage = StageExecutor(model, G * B * pages_per_seq + 1, PS)
@@ -103,7 +111,7 @@ if __name__ == "__main__":
     arch, transport = sys.argv[1], sys.argv[2]
     cfgd = GPU_DSV2 if arch == "dsv2" else GPU_LLAMA
     steps, B, S = 6, 16, 24
-    prompts, hist = run(cfgd, transport, steps, B, S)
+    prompts, hist = run(cfgd, transport, steps, B, S, half=len(sys.argv) > 3 and sys.argv[3] == "half")
     if dist.get_rank() == 0:
         ref = single_gpu_tokens(cfgd, prompts, steps, B, S)
         bad = 0

@@ -124,6 +124,40 @@ def test_sharded_equals_unsharded(C):
         assert torch.allclose(x, y, atol=1e-5)
 
 
+@pytest.mark.parametrize("C", [TINY_LLAMA, TINY_GEMMA2, TINY_DSV2], ids=lambda c: c["model_type"])
+def test_half_layer_boundaries_equal_unsharded(C):
+    """A stage boundary may fall between the attention and the MLP block of a layer (ShardSpec.skip_first_attn /
+    defer_last_mlp): stages load only their block's tensors and keep KV only for their attention blocks."""
+    from mlx_sharding_b200.config import ShardSpec
+    from mlx_sharding_b200.parallel.partition import balanced_split
+
+    cfg, sd, full = _ours(C)
+    L = cfg.num_hidden_layers
+    specs = [ShardSpec(0, 2, L, defer_last_mlp=True), ShardSpec(1, 3, L, skip_first_attn=True, defer_last_mlp=True),
+             ShardSpec(2, 3, L, skip_first_attn=True), ShardSpec(3, 4, L)]
+    parts = [build_stage(cfg, sp, torch.float32).load_state(sd) for sp in specs]
+    assert [m.kv_geometry()[0] for m in parts] == [2, 1, 0, 1]
+    assert not parts[0].spec.is_last and parts[-1].spec.is_last and not parts[1].spec.is_first
+    assert "o" not in parts[2].layer_weights[2] and ("down" in parts[2].layer_weights[2] or "e_down" in parts[2].layer_weights[2])
+    a = run_sequence(full, TOKS, 3)
+    b = run_sequence(parts, TOKS, 3, chunk=5)
+    for x, y in zip(a, b):
+        assert torch.allclose(x, y, atol=1e-5)
+    # stage-local random init generates exactly the tensors the stage consumes
+    for sp in specs:
+        build_stage(cfg, sp, torch.float32).load_state(dict(random_state_dict(cfg, sp, dtype=torch.float32)))
+    # the partitioner's half-layer plan covers every block exactly once and is never worse than whole layers
+    from mlx_sharding_b200.parallel.partition import stage_cost
+    for n in (2, 3, 5):
+        plan = balanced_split(cfg, n, half_layers=True)
+        units = [(i, blk) for sp in plan for i in sp.layers() for blk in ("a", "m")
+                 if (sp.runs_attn(i) if blk == "a" else sp.runs_mlp(i))]
+        assert units == [(i, blk) for i in range(L) for blk in ("a", "m")]
+        assert plan[0].is_first and plan[-1].is_last and sum(sp.is_last for sp in plan) == 1
+        whole = balanced_split(cfg, n)
+        assert max(stage_cost(cfg, sp) for sp in plan) <= max(stage_cost(cfg, sp) for sp in whole) + 1e-12
+
+
 def test_dsv2_unstacked_experts_are_stacked():
     """HF-style per-expert keys are stacked into switch_mlp.* (reference deepseek_v2.py:101-111)."""
     cfg = ModelConfig.from_dict(TINY_DSV2)
