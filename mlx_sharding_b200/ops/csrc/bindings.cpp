@@ -506,12 +506,14 @@ void ep_dispatch(const Tensor& x, const Tensor& idx, int64_t experts_per_rank, i
                                      cur_stream()));
 }
 std::vector<Tensor> ep_regroup(int64_t flag_ptr, int64_t counter_ptr, int64_t error_ptr, int64_t recv_count_ptr, int64_t recv_meta_ptr,
-                               int64_t recv_x_ptr, int64_t world, int64_t cap, int64_t E_local, int64_t H, int64_t device) {
+                               int64_t recv_x_ptr, int64_t world, int64_t cap, int64_t E_local, int64_t H, int64_t device,
+                               int64_t rows_bound) {
   auto dev = torch::Device(torch::kCUDA, (int)device);
   const c10::cuda::CUDAGuard guard(dev);
   auto io = torch::dtype(torch::kInt32).device(dev);
-  const int64_t R = world * cap;
-  Tensor offs = torch::empty({E_local + 1}, io), row_perm = torch::empty({R}, io), total = torch::empty({1}, io);
+  // rows_bound (>0): the caller's bound on the rows all sources can send this step; sizes the expert-ordered temporaries
+  const int64_t R = rows_bound > 0 ? std::min<int64_t>(world * cap, rows_bound) : world * cap;
+  Tensor offs = torch::empty({E_local + 1}, io), row_perm = torch::empty({world * cap}, io), total = torch::empty({1}, io);
   Tensor perm_src = torch::empty({R, 2}, io);
   Tensor x_perm = torch::empty({R, H}, torch::dtype(torch::kBFloat16).device(dev));
   LAUNCH_OK(b200::ep_regroup_launch(reinterpret_cast<const uint32_t*>(flag_ptr), reinterpret_cast<uint32_t*>(counter_ptr),
@@ -574,7 +576,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("copy_signal", &copy_signal);
   m.def("advance_meta", &advance_meta);
   m.def("ep_dispatch", &ep_dispatch);
-  m.def("ep_regroup", &ep_regroup);
+  m.def("ep_regroup", &ep_regroup, py::arg("flag_ptr"), py::arg("counter_ptr"), py::arg("error_ptr"), py::arg("recv_count_ptr"),
+        py::arg("recv_meta_ptr"), py::arg("recv_x_ptr"), py::arg("world"), py::arg("cap"), py::arg("E_local"), py::arg("H"),
+        py::arg("device"), py::arg("rows_bound") = 0);
   m.def("ep_return", &ep_return);
   m.def("ep_wait_all", &ep_wait_all);
   m.def("init_scratch", &init_scratch);

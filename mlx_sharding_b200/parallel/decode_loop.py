@@ -65,12 +65,14 @@ class DecodeLoop:
     """Steady-state decode of ``num_groups`` micro-batch groups on this stage."""
 
     def __init__(self, stage, num_groups: int, batch: int, max_blocks: int, transport: str = "auto",
-                 use_graphs: bool = True):
+                 use_graphs: bool = True, standalone: bool = False):
+        """``standalone``: this rank runs the *whole* layer stack on its own sequences (data-parallel attention +
+        expert-parallel MoE, ``parallel/ep.py``) — there is no stage hand-off even though ``torch.distributed`` is up."""
         self.stage = stage
         self.model = stage.model
         self.dev = self.model.device
-        self.rank = dist.get_rank() if dist.is_initialized() else 0
-        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() and not standalone else 0
+        self.world = dist.get_world_size() if dist.is_initialized() and not standalone else 1
         self.G, self.B = num_groups, batch
         self.page_size = stage.kv.page_size
         self.groups = [GroupState(batch, max_blocks, self.page_size, self.dev) for _ in range(num_groups)]

@@ -85,21 +85,25 @@ class ExpertParallelMoE:
         self.act = b200.ACT_IDS[act]
 
     def forward(self, x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor] = None,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, peer_tokens: Optional[int] = None) -> torch.Tensor:
+        """``peer_tokens``: upper bound of the tokens *any* rank routes in this step (default: this rank's own ``T`` —
+        ranks stepping in lockstep with equal batch shapes); only sizes the temporaries of the local expert GEMMs."""
         b, C = self.b, self.b.C
         T, k = idx.shape
         assert T * k <= b.cap, "token batch exceeds the EP buffer capacity"
         W = b.world
         st = b.state
+        Tmax = max(T, peer_tokens or 0)
         # 1) dispatch my pairs to the owners of their experts (remote stores + count/flag publication)
         C.ep_dispatch(x, idx, self.E_local, b.rank, b.cap, b.t_recv_x, b.t_recv_meta, b.t_recv_count, b.t_recv_flag,
                       st[:W], st[W:W + 1])
         # 2) wait for every source, bucket what I received by local expert
         offs, total, x_perm, perm_src = C.ep_regroup(b.base + b.off_flags, st[W + 2:W + 3].data_ptr(), st[-1:].data_ptr(),
                                                      b.base + b.off_recv_count, b.base + b.off_recv_meta,
-                                                     b.base + b.off_recv_x, W, b.cap, self.E_local, b.H, b.dev)
+                                                     b.base + b.off_recv_x, W, b.cap, self.E_local, b.H, b.dev,
+                                                     min(W * b.cap, W * Tmax * k))
         # 3) my experts: grouped swap-AB tcgen05 GEMMs on the received rows
-        max_rows = min(W * T, x_perm.shape[0])  # upper bound of rows one expert can receive (every rank sends <= T)
+        max_rows = min(W * Tmax, x_perm.shape[0])  # upper bound of rows one expert can receive (every rank sends <= Tmax)
         h = C.grouped_linear(x_perm, self.wg, self.wu, offs, max_rows, self.act, False)
         y = C.grouped_linear(h, self.wd, None, offs, max_rows, 0, True)
         # 4) push every output row back to the rank / pair it came from

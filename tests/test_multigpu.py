@@ -28,3 +28,9 @@ def test_pipeline_parity(arch, transport, port):
 def test_expert_parallel_moe():
     out = _torchrun("ep_parity.py", [], port=29574)
     assert "EP_OK" in out, out[-3000:]
+
+
+def test_expert_parallel_whole_model():
+    """Data-parallel attention + expert-parallel MoE for every layer, graph-captured decode loop (bench.py --parallelism ep)."""
+    out = _torchrun("ep_model_parity.py", [], port=29576)
+    assert "EP_MODEL_OK" in out, out[-3000:]
