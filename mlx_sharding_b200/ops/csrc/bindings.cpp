@@ -72,6 +72,15 @@ int sm_count() {
   return n;
 }
 
+// Token tile of the grouped (MoE) GEMMs: ~2x the average rows per expert but never below 64 — measured on B200
+// (profiles/results.md, DeepSeek-V2-Lite decode): tiles of 16 / 32 tokens are *slower* than 64 even when experts hold ~6
+// rows, and 256-token tiles lose to 64 / 128 at 24 rows per expert.  MLXB200_GROUPED_BN=<n> overrides (tuning).
+int grouped_bn(int64_t max_rows, int64_t R, int64_t E) {
+  static const int forced = [] { const char* e = std::getenv("MLXB200_GROUPED_BN"); return e ? std::atoi(e) : 0; }();
+  if (forced > 0) return b200::gemm_pick_bn((int)std::min<int64_t>(max_rows, forced));
+  return b200::gemm_pick_bn((int)std::min<int64_t>(max_rows, std::max<int64_t>(64, 2 * ((R + E - 1) / E))));
+}
+
 int auto_splits(int rows, int n, int k, bool grouped) {
   if (grouped || rows > 256) return 1;
   const int tiles = (n + 127) / 128;
@@ -138,7 +147,7 @@ Tensor grouped_linear(const Tensor& x, const Tensor& w, const c10::optional<Tens
   a.num_experts = (int)E; a.expert_offsets = expert_offsets.data_ptr<int>();
   // token tile sized for ~2x the average rows per expert (not the worst case): less padding in the MMA N dimension and
   // smaller token-tile loads; experts with more rows simply take further tiles of the persistent tile list
-  a.bn = b200::gemm_pick_bn((int)std::min<int64_t>(a.max_rows, std::max<int64_t>(16, 2 * ((R + E - 1) / E))));
+  a.bn = grouped_bn(a.max_rows, R, E);
   a.out = out.data_ptr(); a.ld_out = N; a.out_fp32 = out_fp32; a.act = (int)act; a.splits = 1;
   LAUNCH_OK(b200::gemm_launch(a, cur_stream()));
   return out;
@@ -217,7 +226,7 @@ Tensor grouped_linear_q(const Tensor& x, const Tensor& wq, const Tensor& scales_
   a.num_experts = (int)E; a.expert_offsets = expert_offsets.data_ptr<int>();
   // token tile sized for ~2x the average rows per expert (not the worst case): less padding in the MMA N dimension and
   // smaller token-tile loads; experts with more rows simply take further tiles of the persistent tile list
-  a.bn = b200::gemm_pick_bn((int)std::min<int64_t>(a.max_rows, std::max<int64_t>(16, 2 * ((R + E - 1) / E))));
+  a.bn = grouped_bn(a.max_rows, R, E);
   a.out = out.data_ptr(); a.ld_out = N; a.out_fp32 = out_fp32; a.act = (int)act; a.splits = 1;
   LAUNCH_OK(b200::gemm_q_launch(a, cur_stream()));
   return out;

@@ -76,7 +76,9 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   static_assert(STAGES >= 2, "ring too small");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024 B alignment by *pointer arithmetic* on the __shared__ array: an integer round-trip loses the address space and
+  // turns every LDS/STS below into a generic LD.E/ST.E (checked with cuobjdump -sass)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   OutT* stg = reinterpret_cast<OutT*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + p_staging_bytes(BN, sizeof(OutT)));
   uint64_t* empty_bar = full_bar + STAGES;

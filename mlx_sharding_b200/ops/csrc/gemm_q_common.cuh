@@ -18,14 +18,17 @@ __device__ __forceinline__ void dequant_half_row(const uint8_t* packed_row, floa
     const uint4 v = reinterpret_cast<const uint4*>(packed_row)[half];  // 4 words = 32 codes
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     const __nv_bfloat162 s2 = __float2bfloat162_rn(s), b2 = __float2bfloat162_rn(b);
-    const uint32_t magic = 0x43004300u;
+    uint32_t magic, mask4;  // kept in registers (asm volatile-free movs) so the and-or below stays a single LOP3
+    asm("mov.b32 %0, 0x43004300;" : "=r"(magic));
+    asm("mov.b32 %0, 0x000F000F;" : "=r"(mask4));
     const __nv_bfloat162 c128 = *reinterpret_cast<const __nv_bfloat162*>(&magic);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint32_t x[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const uint32_t m = ((w[c] >> (4 * i)) & 0x000F000Fu) | magic;  // (128 + q_i, 128 + q_{i+4})
+        uint32_t m;  // (128 + q_i, 128 + q_{i+4}): one LOP3 ((a & b) | c, LUT 0xEA) with both constants in registers
+        asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(m) : "r"(w[c] >> (4 * i)), "r"(mask4), "r"(magic));
         __nv_bfloat162 q = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&m), c128);
         q = __hfma2(s2, q, b2);
         x[i] = *reinterpret_cast<uint32_t*>(&q);

@@ -88,7 +88,9 @@ gemm_q_persistent_kernel(const __grid_constant__ CUtensorMap tmap_wq, const __gr
   static_assert(STAGES >= 2, "ring too small");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024 B alignment by *pointer arithmetic* on the __shared__ array: an integer round-trip loses the address space and
+  // turns every LDS/STS below into a generic LD.E/ST.E (checked with cuobjdump -sass)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_ring = smem;                                        // [DQ][D][16 KB]   (1024-aligned)
   uint8_t* ring = a_ring + DQ * D * kATileBytes;                 // [STAGES][STAGE_BYTES]
   OutT* stg = reinterpret_cast<OutT*>(ring + STAGES * STAGE_BYTES);
