@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--tokens", type=int, default=64, help="tokens per rank per step")
     ap.add_argument("--layers", type=int, default=8, help="chained MoE blocks inside the timed graph")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--breakdown", action="store_true", help="also print an eager per-phase timing of one EP block (CUDA events)")
     args = ap.parse_args()
     lr = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(lr)
@@ -83,9 +84,44 @@ def main():
         dist.barrier()
         return max_over_ranks(e0.elapsed_time(e1)) * 1e3 / (args.iters * L), out
 
+    if args.breakdown:
+        # eager, event-timed phases of one EP block on this rank (launch gaps included; flag waits show up in regroup / wait)
+        ep, (_, _, _, gate) = eps[0], banks[0]
+        b, C, W = bufs, bufs.C, world
+        st = b.state
+        names = ["route", "dispatch", "regroup(wait+bucket)", "gate_up", "down", "return", "wait_all", "combine"]
+        acc = [0.0] * len(names)
+        n_it = 20
+        for it in range(n_it + 3):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+            dist.barrier()
+            evs[0].record()
+            idx, w = b200.moe_route(x0, gate, k); evs[1].record()
+            C.ep_dispatch(x0, idx, ep.E_local, b.rank, b.cap, b.t_recv_x, b.t_recv_meta, b.t_recv_count, b.t_recv_flag, st[:W], st[W:W + 1]); evs[2].record()
+            offs, total, x_perm, perm_src = C.ep_regroup(b.base + b.off_flags, st[W + 2:W + 3].data_ptr(), st[-1:].data_ptr(), b.base + b.off_recv_count,
+                                                         b.base + b.off_recv_meta, b.base + b.off_recv_x, W, b.cap, ep.E_local, b.H, b.dev, W * T * k); evs[3].record()
+            h = C.grouped_linear(x_perm, ep.wg, ep.wu, offs, min(W * T, x_perm.shape[0]), ep.act, False); evs[4].record()
+            y = C.grouped_linear(h, ep.wd, None, offs, min(W * T, x_perm.shape[0]), 0, True); evs[5].record()
+            C.ep_return(y, perm_src, total, b.t_ret_y, b.t_ret_flag, st[W + 1:W + 2]); evs[6].record()
+            C.ep_wait_all(b.base + b.off_flags + 128, st[W + 3:W + 4].data_ptr(), W, st[-1:].data_ptr()); evs[7].record()
+            C.moe_combine(b.ret_y, ep._identity(T * k, x0.device), w, x0, None, int(k), 0, 0); evs[8].record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                for i in range(len(names)):
+                    acc[i] += evs[i].elapsed_time(evs[i + 1]) * 1e3 / n_it
+        print(f"[rank {rank}] eager EP block phases (us): " + ", ".join(f"{n} {v:.1f}" for n, v in zip(names, acc)) + f"  total {sum(acc):.1f}",
+              file=sys.stderr, flush=True)
+        dist.barrier()
+
     us_local, out_l = timed(run_local)
     us_ep, out_e = timed(run_ep)
-    err = (out_l.float() - out_e.float()).abs().max().item()
+    # correctness on ONE block (the chained blocks of the timed graphs are not normalised, their values overflow)
+    (Wg, Wu, Wd, gate) = banks[0]
+    idx, w = b200.moe_route(x0, gate, k)
+    ref1 = b200.moe_experts(x0, idx, w, Wg, Wu, Wd, "silu", residual=x0)
+    got1 = eps[0].forward(x0, idx, w, residual=x0)
+    torch.cuda.synchronize()
+    err = (ref1.float() - got1.float()).abs().max().item()
     bank_bytes = 3 * E * I * H * 2
     nvl_bytes = T * k * (world - 1) / world * (H * 2 + H * 4)          # dispatch bf16 + return fp32, remote share
     peaks = {}
