@@ -89,22 +89,24 @@ def main():
         ep, (_, _, _, gate) = eps[0], banks[0]
         b, C, W = bufs, bufs.C, world
         st = b.state
-        names = ["route", "dispatch", "regroup(wait+bucket)", "gate_up", "down", "return", "wait_all", "combine"]
+        names = ["route", "dispatch", "regroup(wait+bucket)", "gate_up", "down(+fused return)", "combine(+wait)"]
         acc = [0.0] * len(names)
         n_it = 20
+        exp_rows = T * k
         for it in range(n_it + 3):
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
             dist.barrier()
             evs[0].record()
             idx, w = b200.moe_route(x0, gate, k); evs[1].record()
-            C.ep_dispatch(x0, idx, ep.E_local, b.rank, b.cap, b.t_recv_x, b.t_recv_meta, b.t_recv_count, b.t_recv_flag, st[:W], st[W:W + 1]); evs[2].record()
-            offs, total, x_perm, perm_src = C.ep_regroup(b.base + b.off_flags, st[W + 2:W + 3].data_ptr(), st[-1:].data_ptr(), b.base + b.off_recv_count,
-                                                         b.base + b.off_recv_meta, b.base + b.off_recv_x, W, b.cap, ep.E_local, b.H, b.dev, W * T * k); evs[3].record()
-            h = C.grouped_linear(x_perm, ep.wg, ep.wu, offs, min(W * T, x_perm.shape[0]), ep.act, False); evs[4].record()
-            y = C.grouped_linear(h, ep.wd, None, offs, min(W * T, x_perm.shape[0]), 0, True); evs[5].record()
-            C.ep_return(y, perm_src, total, b.t_ret_y, b.t_ret_flag, st[W + 1:W + 2]); evs[6].record()
-            C.ep_wait_all(b.base + b.off_flags + 128, st[W + 3:W + 4].data_ptr(), W, st[-1:].data_ptr()); evs[7].record()
-            C.moe_combine(b.ret_y, ep._identity(T * k, x0.device), w, x0, None, int(k), 0, 0); evs[8].record()
+            C.ep_dispatch(x0, idx, ep.E_local, b.rank, b.cap, b.t_recv_x, b.t_recv_meta, b.t_recv_count, b.t_recv_flag, st[:W], st[W:W + 1],
+                          st[W + 3:W + 4]); evs[2].record()
+            offs, total, x_perm, perm_src, row_dst = C.ep_regroup(b.base + b.off_flags, st[W + 2:W + 3].data_ptr(), st[-1:].data_ptr(),
+                                                                  b.base + b.off_recv_count, b.base + b.off_recv_meta, b.base + b.off_recv_x, W,
+                                                                  b.cap, ep.E_local, b.H, b.dev, W * T * k, b.t_ret_y); evs[3].record()
+            mr = min(W * T, x_perm.shape[0])
+            h = C.grouped_linear(x_perm, ep.wg, ep.wu, offs, mr, ep.act, False, None, None, None, exp_rows); evs[4].record()
+            C.grouped_linear(h, ep.wd, None, offs, mr, 0, True, row_dst, b.ret_flags_dev, st[W + 1:W + 2], exp_rows); evs[5].record()
+            C.ep_combine(b.base + b.off_flags + 128, st[W + 3:W + 4], st[-1:].data_ptr(), b.ret_y, w, x0, None); evs[6].record()
             torch.cuda.synchronize()
             if it >= 3:
                 for i in range(len(names)):

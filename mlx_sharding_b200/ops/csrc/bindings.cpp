@@ -131,13 +131,17 @@ Tensor linear(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& w2,
 }
 
 Tensor grouped_linear(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& w2, const Tensor& expert_offsets,
-                      int64_t max_rows, int64_t act, bool out_fp32) {
+                      int64_t max_rows, int64_t act, bool out_fp32, const c10::optional<Tensor>& row_dst,
+                      const c10::optional<Tensor>& signal_peers, const c10::optional<Tensor>& done_counter, int64_t expected_rows) {
   check_bf16(x, "x"); check_bf16(w, "w"); check_rows(x, "x");
   TORCH_CHECK(w.dim() == 3 && w.is_contiguous(), "w must be contiguous [E, N, K]");
   const c10::cuda::CUDAGuard guard(x.device());
   const int64_t R = x.size(0), K = x.size(1), E = w.size(0), N = w.size(1);
   TORCH_CHECK(w.size(2) == K && expert_offsets.numel() == E + 1 && expert_offsets.scalar_type() == torch::kInt32);
-  Tensor out = torch::empty({R, N}, x.options().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16));
+  // EP return path (parallel/ep.py): every output row goes to the address in row_dst[row] (the source rank's return buffer, peer
+  // memory) and all `signal_peers` flags are bumped once every tile is stored — the un-fused return kernel disappears
+  const bool ep_ret = row_dst.has_value();
+  Tensor out = torch::empty({ep_ret ? 0 : R, N}, x.options().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16));
   if (R == 0) return out;
   b200::GemmArgs a;
   a.x = x.data_ptr(); a.x_rows = R; a.ld_x = x.stride(0);
@@ -145,9 +149,18 @@ Tensor grouped_linear(const Tensor& x, const Tensor& w, const c10::optional<Tens
   if (w2.has_value()) { check_bf16(*w2, "w2"); TORCH_CHECK(w2->is_contiguous() && w2->sizes() == w.sizes()); a.w2 = w2->data_ptr(); }
   a.m = (int)R; a.n = (int)N; a.k = (int)K; a.max_rows = (int)std::min<int64_t>(max_rows, R);
   a.num_experts = (int)E; a.expert_offsets = expert_offsets.data_ptr<int>();
+  if (ep_ret) {
+    TORCH_CHECK(signal_peers.has_value() && done_counter.has_value() && row_dst->scalar_type() == torch::kInt64 &&
+                signal_peers->scalar_type() == torch::kInt64 && row_dst->numel() >= R && row_dst->is_contiguous(), "bad EP return arguments");
+    a.row_dst = reinterpret_cast<const unsigned long long*>(row_dst->data_ptr<int64_t>());
+    a.signal_peers = reinterpret_cast<const unsigned long long*>(signal_peers->data_ptr<int64_t>());
+    a.num_signal_peers = (int)signal_peers->numel();
+    a.done_counter = reinterpret_cast<unsigned int*>(done_counter->data_ptr<int>());
+  }
   // token tile sized for ~2x the average rows per expert (not the worst case): less padding in the MMA N dimension and
   // smaller token-tile loads; experts with more rows simply take further tiles of the persistent tile list
-  a.bn = grouped_bn(a.max_rows, R, E);
+  // expected_rows (>0): the caller's estimate of the rows actually present when x is an over-sized buffer (EP receive side)
+  a.bn = grouped_bn(a.max_rows, expected_rows > 0 ? expected_rows : R, E);
   a.out = out.data_ptr(); a.ld_out = N; a.out_fp32 = out_fp32; a.act = (int)act; a.splits = 1;
   LAUNCH_OK(b200::gemm_launch(a, cur_stream()));
   return out;
@@ -503,7 +516,7 @@ std::vector<unsigned long long> to_u64(const std::vector<int64_t>& v) {
 }
 void ep_dispatch(const Tensor& x, const Tensor& idx, int64_t experts_per_rank, int64_t my_rank, int64_t cap,
                  std::vector<int64_t> recv_x, std::vector<int64_t> recv_meta, std::vector<int64_t> recv_count,
-                 std::vector<int64_t> recv_flag, Tensor send_counts, Tensor done_counter) {
+                 std::vector<int64_t> recv_flag, Tensor send_counts, Tensor done_counter, const c10::optional<Tensor>& ret_expected) {
   check_bf16(x, "x"); check_rows(x, "x");
   TORCH_CHECK(idx.scalar_type() == torch::kInt32 && idx.is_contiguous() && idx.dim() == 2);
   const c10::cuda::CUDAGuard guard(x.device());
@@ -512,11 +525,12 @@ void ep_dispatch(const Tensor& x, const Tensor& idx, int64_t experts_per_rank, i
   LAUNCH_OK(b200::ep_dispatch_launch(x.data_ptr(), x.stride(0), idx.data_ptr<int>(), (int)idx.numel(), (int)idx.size(1), (int)x.size(1),
                                      (int)experts_per_rank, world, (int)my_rank, (int)cap, a.data(), b.data(), c.data(), d.data(),
                                      send_counts.data_ptr<int>(), reinterpret_cast<unsigned int*>(done_counter.data_ptr<int>()),
+                                     ret_expected.has_value() ? reinterpret_cast<uint32_t*>(ret_expected->data_ptr<int>()) : nullptr,
                                      cur_stream()));
 }
 std::vector<Tensor> ep_regroup(int64_t flag_ptr, int64_t counter_ptr, int64_t error_ptr, int64_t recv_count_ptr, int64_t recv_meta_ptr,
                                int64_t recv_x_ptr, int64_t world, int64_t cap, int64_t E_local, int64_t H, int64_t device,
-                               int64_t rows_bound) {
+                               int64_t rows_bound, std::vector<int64_t> ret_y) {
   auto dev = torch::Device(torch::kCUDA, (int)device);
   const c10::cuda::CUDAGuard guard(dev);
   auto io = torch::dtype(torch::kInt32).device(dev);
@@ -525,13 +539,32 @@ std::vector<Tensor> ep_regroup(int64_t flag_ptr, int64_t counter_ptr, int64_t er
   Tensor offs = torch::empty({E_local + 1}, io), row_perm = torch::empty({world * cap}, io), total = torch::empty({1}, io);
   Tensor perm_src = torch::empty({R, 2}, io);
   Tensor x_perm = torch::empty({R, H}, torch::dtype(torch::kBFloat16).device(dev));
+  // destination address of every expert-ordered row for the fused return (down-projection epilogue -> source's return buffer)
+  Tensor row_dst = torch::empty({ret_y.empty() ? 0 : R}, torch::dtype(torch::kInt64).device(dev));
+  auto ry = to_u64(ret_y);
   LAUNCH_OK(b200::ep_regroup_launch(reinterpret_cast<const uint32_t*>(flag_ptr), reinterpret_cast<uint32_t*>(counter_ptr),
                                     reinterpret_cast<uint32_t*>(error_ptr), reinterpret_cast<const int*>(recv_count_ptr),
                                     reinterpret_cast<const void*>(recv_meta_ptr), reinterpret_cast<const void*>(recv_x_ptr), (int)world,
                                     (int)cap, (int)E_local, (int)H, offs.data_ptr<int>(), row_perm.data_ptr<int>(), total.data_ptr<int>(),
-                                    x_perm.data_ptr(), perm_src.data_ptr(), cur_stream()));
+                                    x_perm.data_ptr(), perm_src.data_ptr(), ret_y.empty() ? nullptr : ry.data(),
+                                    ret_y.empty() ? nullptr : reinterpret_cast<unsigned long long*>(row_dst.data_ptr<int64_t>()),
+                                    cur_stream()));
   ++g_launches;
-  return {offs, total, x_perm, perm_src};
+  return {offs, total, x_perm, perm_src, row_dst};
+}
+Tensor ep_combine(int64_t flag_ptr, const Tensor& expected, int64_t error_ptr, const Tensor& ret_y, const Tensor& wts,
+                  const c10::optional<Tensor>& residual, const c10::optional<Tensor>& out_) {
+  TORCH_CHECK(ret_y.scalar_type() == torch::kFloat32 && ret_y.is_contiguous() && wts.scalar_type() == torch::kFloat32 && wts.is_contiguous());
+  const c10::cuda::CUDAGuard guard(ret_y.device());
+  const int64_t T = wts.size(0), k = wts.size(1), H = ret_y.size(1);
+  Tensor out = out_.has_value() ? *out_ : torch::empty({T, H}, ret_y.options().dtype(torch::kBFloat16));
+  TORCH_CHECK(out.stride(1) == 1 && out.size(0) >= T && T * k <= ret_y.size(0));
+  if (residual.has_value()) { check_bf16(*residual, "residual"); check_rows(*residual, "residual"); }
+  LAUNCH_OK(b200::ep_combine_launch(reinterpret_cast<const uint32_t*>(flag_ptr), reinterpret_cast<const uint32_t*>(expected.data_ptr<int>()),
+                                    reinterpret_cast<uint32_t*>(error_ptr), ret_y.data_ptr<float>(), wts.data_ptr<float>(),
+                                    residual.has_value() ? residual->data_ptr() : nullptr, residual.has_value() ? residual->stride(0) : 0,
+                                    out.data_ptr(), out.stride(0), (int)T, (int)k, (int)H, cur_stream()));
+  return out;
 }
 void ep_return(const Tensor& y_perm, const Tensor& perm_src, const Tensor& total_rows, std::vector<int64_t> ret_y,
                std::vector<int64_t> ret_flag, Tensor done_counter) {
@@ -555,7 +588,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("bias") = py::none(), py::arg("act") = 0, py::arg("softcap") = 0.0, py::arg("out_fp32") = false,
         py::arg("out") = py::none(), py::arg("splits") = 0, py::arg("signal_flag_ptr") = 0, py::arg("signal_value") = 0);
   m.def("grouped_linear", &grouped_linear, py::arg("x"), py::arg("w"), py::arg("w2") = py::none(), py::arg("expert_offsets"),
-        py::arg("max_rows"), py::arg("act") = 0, py::arg("out_fp32") = false);
+        py::arg("max_rows"), py::arg("act") = 0, py::arg("out_fp32") = false, py::arg("row_dst") = py::none(),
+        py::arg("signal_peers") = py::none(), py::arg("done_counter") = py::none(), py::arg("expected_rows") = 0);
   m.def("linear_q", &linear_q);
   m.def("grouped_linear_q", &grouped_linear_q);
   m.def("gemm_q_supported", &gemm_q_supported);
@@ -584,10 +618,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("set_flag", &set_flag);
   m.def("copy_signal", &copy_signal);
   m.def("advance_meta", &advance_meta);
-  m.def("ep_dispatch", &ep_dispatch);
+  m.def("ep_dispatch", &ep_dispatch, py::arg("x"), py::arg("idx"), py::arg("experts_per_rank"), py::arg("my_rank"), py::arg("cap"),
+        py::arg("recv_x"), py::arg("recv_meta"), py::arg("recv_count"), py::arg("recv_flag"), py::arg("send_counts"),
+        py::arg("done_counter"), py::arg("ret_expected") = py::none());
   m.def("ep_regroup", &ep_regroup, py::arg("flag_ptr"), py::arg("counter_ptr"), py::arg("error_ptr"), py::arg("recv_count_ptr"),
         py::arg("recv_meta_ptr"), py::arg("recv_x_ptr"), py::arg("world"), py::arg("cap"), py::arg("E_local"), py::arg("H"),
-        py::arg("device"), py::arg("rows_bound") = 0);
+        py::arg("device"), py::arg("rows_bound") = 0, py::arg("ret_y") = std::vector<int64_t>());
+  m.def("ep_combine", &ep_combine, py::arg("flag_ptr"), py::arg("expected"), py::arg("error_ptr"), py::arg("ret_y"), py::arg("wts"),
+        py::arg("residual") = py::none(), py::arg("out") = py::none());
   m.def("ep_return", &ep_return);
   m.def("ep_wait_all", &ep_wait_all);
   m.def("init_scratch", &init_scratch);

@@ -39,7 +39,8 @@ __global__ void ep_dispatch_kernel(const __nv_bfloat16* __restrict__ x, long lon
                                    PeerTable recv_meta,   // per dst: base of [world][cap] int2
                                    PeerTable recv_count,  // per dst: base of [world] int
                                    PeerTable recv_flag,   // per dst: uint32 flag (counting)
-                                   int* __restrict__ send_counts, unsigned int* __restrict__ done_counter) {
+                                   int* __restrict__ send_counts, unsigned int* __restrict__ done_counter,
+                                   uint32_t* __restrict__ ret_expected /* += world: arrivals the combine of this step waits for */) {
   pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const int warps_per_cta = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,7 +77,10 @@ __global__ void ep_dispatch_kernel(const __nv_bfloat16* __restrict__ x, long lon
       __threadfence_system();
       atomicAdd_system(reinterpret_cast<unsigned int*>(recv_flag.p[r]), 1u);
     }
-    if (threadIdx.x == 0) *done_counter = 0u;
+    if (threadIdx.x == 0) {
+      *done_counter = 0u;
+      if (ret_expected != nullptr) *ret_expected += (uint32_t)world;
+    }
   }
 }
 
@@ -127,7 +131,8 @@ ep_regroup_offsets_kernel(const uint32_t* flag, uint32_t* local_counter, uint32_
 // gather received rows into expert-contiguous order; remember where each permuted row came from
 __global__ void ep_regroup_gather_kernel(const __nv_bfloat16* __restrict__ recv_x, const int2* __restrict__ recv_meta,
                                          const int* __restrict__ recv_count, const int* __restrict__ row_perm, int world, int cap,
-                                         int H, __nv_bfloat16* __restrict__ x_perm, int2* __restrict__ perm_src /*(src rank, src pair)*/) {
+                                         int H, __nv_bfloat16* __restrict__ x_perm, int2* __restrict__ perm_src /*(src rank, src pair)*/,
+                                         PeerTable ret_y, unsigned long long* __restrict__ row_dst /*fp32 return row of each permuted row*/) {
   pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const int nvec = H / 8;
   const int s = blockIdx.y;
@@ -137,7 +142,12 @@ __global__ void ep_regroup_gather_kernel(const __nv_bfloat16* __restrict__ recv_
     const int row = row_perm[(size_t)s * cap + j];
     reinterpret_cast<uint4*>(x_perm + (size_t)row * H)[v] =
         __ldcv(reinterpret_cast<const uint4*>(recv_x + ((size_t)s * cap + j) * H) + v);
-    if (v == 0) perm_src[row] = make_int2(s, recv_meta[(size_t)s * cap + j].y);
+    if (v == 0) {
+      const int pair = recv_meta[(size_t)s * cap + j].y;
+      perm_src[row] = make_int2(s, pair);
+      // where the down-projection epilogue stores this row: the source rank's return buffer, at the pair's index
+      if (row_dst != nullptr) row_dst[row] = ret_y.p[s] + (unsigned long long)pair * (unsigned long long)H * sizeof(float);
+    }
   }
 }
 
@@ -187,6 +197,61 @@ __global__ void ep_wait_all_kernel(const uint32_t* flag, uint32_t* local_counter
   __threadfence_system();
 }
 
+// source side, fused: wait until every rank's down-projection has stored its share of my pairs into my return buffer,
+// then the weighted combine (+ residual).  `expected` was advanced by this step's dispatch kernel (stream order).
+__global__ void ep_combine_kernel(const uint32_t* flag, const uint32_t* __restrict__ expected_ptr, uint32_t* error_flag,
+                                  unsigned long long timeout_ns, const float* __restrict__ ret_y, const float* __restrict__ wts,
+                                  const __nv_bfloat16* __restrict__ residual, long long ld_res, __nv_bfloat16* __restrict__ out,
+                                  long long ld_out, int T, int top_k, int H) {
+  pdl_sync();
+  if (threadIdx.x == 0) {
+    const uint32_t expected = *reinterpret_cast<const volatile uint32_t*>(expected_ptr);
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    while (true) {
+      const uint32_t v = ld_acquire_sys(flag);
+      if ((int32_t)(v - expected) >= 0) break;
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) { if (error_flag) atomicExch(error_flag, 1u); break; }
+      __nanosleep(32);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const int nvec = H / 8;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)T * nvec) return;
+  const int v = i % nvec;
+  const int t = i / nvec;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int k = 0; k < top_k; ++k) {
+    const float w = wts[(size_t)t * top_k + k];
+    const float4* src = reinterpret_cast<const float4*>(ret_y + ((size_t)t * top_k + k) * H + v * 8);
+    const float4 a = __ldcv(src), b = __ldcv(src + 1);   // rows were written by peers: never from a stale L1 line
+    acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
+    acc[4] += w * b.x; acc[5] += w * b.y; acc[6] += w * b.z; acc[7] += w * b.w;
+  }
+  if (residual != nullptr) {
+    const uint4 r = reinterpret_cast<const uint4*>(residual + (size_t)t * ld_res)[v];
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[2 * j] += __uint_as_float(rr[j] << 16);
+      acc[2 * j + 1] += __uint_as_float(rr[j] & 0xffff0000u);
+    }
+  }
+  uint4 o;
+  __nv_bfloat162 h;
+  h = __floats2bfloat162_rn(acc[0], acc[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(acc[2], acc[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(acc[4], acc[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(acc[6], acc[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+  reinterpret_cast<uint4*>(out + (size_t)t * ld_out)[v] = o;
+}
+
 constexpr unsigned long long kTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
 
 PeerTable make_table(const unsigned long long* v, int world) {
@@ -200,20 +265,21 @@ PeerTable make_table(const unsigned long long* v, int world) {
 cudaError_t ep_dispatch_launch(const void* x, long long ld_x, const int* idx, int npairs, int top_k, int H, int experts_per_rank,
                                int world, int my_rank, int cap, const unsigned long long* recv_x, const unsigned long long* recv_meta,
                                const unsigned long long* recv_count, const unsigned long long* recv_flag, int* send_counts,
-                               unsigned int* done_counter, cudaStream_t s) {
+                               unsigned int* done_counter, uint32_t* ret_expected, cudaStream_t s) {
   if (world > kMaxWorld || (H % 8)) return cudaErrorInvalidValue;
   int grid = (npairs + 7) / 8;
   if (grid < 1) grid = 1;
   if (grid > 592) grid = 592;
   (void)launch_pdl(ep_dispatch_kernel, dim3(grid), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(x), ld_x, idx, npairs, top_k, H, experts_per_rank, world,
                                           my_rank, cap, make_table(recv_x, world), make_table(recv_meta, world),
-                                          make_table(recv_count, world), make_table(recv_flag, world), send_counts, done_counter);
+                                          make_table(recv_count, world), make_table(recv_flag, world), send_counts, done_counter, ret_expected);
   return cudaGetLastError();
 }
 
 cudaError_t ep_regroup_launch(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag, const int* recv_count,
                               const void* recv_meta, const void* recv_x, int world, int cap, int E_local, int H, int* expert_offsets,
-                              int* row_perm, int* total_rows, void* x_perm, void* perm_src, cudaStream_t s) {
+                              int* row_perm, int* total_rows, void* x_perm, void* perm_src, const unsigned long long* ret_y,
+                              unsigned long long* row_dst, cudaStream_t s) {
   if (E_local > 256 || world > kMaxWorld) return cudaErrorInvalidValue;
   (void)launch_pdl(ep_regroup_offsets_kernel, dim3(1), dim3(1024), 0, s, flag, local_counter, error_flag, kTimeoutNs, recv_count,
                                                static_cast<const int2*>(recv_meta), world, cap, E_local, expert_offsets, row_perm,
@@ -222,7 +288,8 @@ cudaError_t ep_regroup_launch(const uint32_t* flag, uint32_t* local_counter, uin
   if (e != cudaSuccess) return e;
   dim3 grid(64, world);
   (void)launch_pdl(ep_regroup_gather_kernel, dim3(grid), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(recv_x), static_cast<const int2*>(recv_meta), recv_count,
-                                                row_perm, world, cap, H, static_cast<__nv_bfloat16*>(x_perm), static_cast<int2*>(perm_src));
+                                                row_perm, world, cap, H, static_cast<__nv_bfloat16*>(x_perm), static_cast<int2*>(perm_src),
+                                                ret_y != nullptr ? make_table(ret_y, world) : PeerTable{}, row_dst);
   return cudaGetLastError();
 }
 
@@ -235,6 +302,17 @@ cudaError_t ep_return_launch(const float* y_perm, const void* perm_src, const in
   if (grid > 592) grid = 592;
   (void)launch_pdl(ep_return_kernel, dim3(grid), dim3(256), 0, s, y_perm, static_cast<const int2*>(perm_src), total_rows, H, world, make_table(ret_y, world),
                                         make_table(ret_flag, world), done_counter);
+  return cudaGetLastError();
+}
+
+cudaError_t ep_combine_launch(const uint32_t* flag, const uint32_t* expected_ptr, uint32_t* error_flag, const float* ret_y,
+                              const float* wts, const void* residual, long long ld_res, void* out, long long ld_out, int T, int top_k,
+                              int H, cudaStream_t s) {
+  if (T == 0) return cudaSuccess;
+  if (H % 8) return cudaErrorInvalidValue;
+  const long long total = (long long)T * (H / 8);
+  (void)launch_pdl(ep_combine_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, flag, expected_ptr, error_flag, kTimeoutNs,
+                   ret_y, wts, static_cast<const __nv_bfloat16*>(residual), ld_res, static_cast<__nv_bfloat16*>(out), ld_out, T, top_k, H);
   return cudaGetLastError();
 }
 

@@ -61,6 +61,22 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmParams& p, int t, int 
 
 }  // namespace
 
+// One thread per finished tile: the last arrival raises the consumer flag(s) with system scope.  (Every CTA fenced its own
+// stores before arriving, so the flag is ordered after all tiles.)
+__device__ __forceinline__ void publish_tile_done(const GemmParams& p) {
+  const unsigned int done = atomicAdd(p.done_counter, 1u) + 1u;
+  if (done != p.signal_tiles) return;
+  *p.done_counter = 0u;
+  __threadfence_system();
+  if (p.signal_peers != nullptr) {
+    for (int i = 0; i < p.num_signal_peers; ++i) atomicAdd_system(reinterpret_cast<unsigned int*>(__ldg(p.signal_peers + i)), 1u);
+  } else if (p.signal_value == 0u) {
+    atomicAdd_system(p.signal_flag, 1u);
+  } else {
+    st_release_sys(p.signal_flag, p.signal_value);
+  }
+}
+
 template <int BN, bool DUAL, typename OutT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_w2,
@@ -110,7 +126,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
-  if (!pdl_early) pdl_wait();
+  // PDL: let the successor's CTAs become resident now (their pre-wait prologue / weight prefetch overlaps this kernel)
   pdl_launch_dependents();
 
   const int kb_total = (p.k + kBlockK - 1) / kBlockK;
@@ -118,11 +134,35 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   if (warp == 0) {
     // ============================================================== TMA producer
     if (lane == 0) {
+      // Weights never depend on a predecessor kernel: the first ring-full of weight tiles is requested *before*
+      // griddepcontrol.wait (HBM latency overlaps the predecessor's tail); the activation tiles follow after it.
+      // (un-grouped launches only: iteration i <-> tile blockIdx.x + (i / kb_total) * gridDim.x, k-block i % kb_total)
+      uint32_t pre = 0;
+      if (!pdl_early) {
+        for (; pre < (uint32_t)STAGES; ++pre) {
+          const int t = blockIdx.x + (int)(pre / kb_total) * gridDim.x;
+          if (t >= num_tiles) break;
+          const TileInfo ti = decode_tile(p, t, tiles_n, tiles_m, BN);
+          uint8_t* st = smem + pre * STAGE_BYTES;
+          const int kc = (int)(pre % kb_total) * kBlockK;
+          mbar_arrive_expect_tx(&full_bar[pre], STAGE_BYTES);
+          tma_load_2d(st, &tmap_w, &full_bar[pre], kc, ti.w_row, kEvictFirst);
+          if (DUAL) tma_load_2d(st + kATileBytes, &tmap_w2, &full_bar[pre], kc, ti.w_row, kEvictFirst);
+        }
+        pdl_wait();
+        for (uint32_t i = 0; i < pre; ++i) {
+          const int t = blockIdx.x + (int)(i / kb_total) * gridDim.x;
+          const TileInfo ti = decode_tile(p, t, tiles_n, tiles_m, BN);
+          tma_load_2d(smem + i * STAGE_BYTES + kATileBytes * (DUAL ? 2 : 1), &tmap_x, &full_bar[i], (int)(i % kb_total) * kBlockK,
+                      ti.row_base, kEvictLast);
+        }
+      }
       uint32_t it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const TileInfo ti = decode_tile(p, t, tiles_n, tiles_m, BN);
         if (ti.rows_valid <= 0) continue;
         for (int kb = 0; kb < kb_total; ++kb, ++it) {
+          if (it < pre) continue;  // issued above
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = smem + s * STAGE_BYTES;
@@ -170,6 +210,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
     }
   } else {
     // ============================================================== epilogue warps (128 threads)
+    if (!pdl_early) pdl_wait();  // residual / out are ordered after the predecessor
     const int q = warp & 3;
     const int f_local = q * 32 + lane;
     const int et = threadIdx.x - 64;
@@ -177,7 +218,10 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
     uint32_t tc = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const TileInfo ti = decode_tile(p, t, tiles_n, tiles_m, BN);
-      if (ti.rows_valid <= 0) continue;
+      if (ti.rows_valid <= 0) {
+        if (p.signal_peers != nullptr && et == 0) publish_tile_done(p);  // empty tiles are counted too (EP return)
+        continue;
+      }
       const uint32_t ab = tc % NUM_ACC, aph = (tc / NUM_ACC) & 1;
       mbar_wait(&tfull_bar[ab], aph);
       tc_fence_after();
@@ -240,13 +284,16 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
 #pragma unroll
               for (int j = 0; j < 4; ++j) { vals[2 * j] += bf16_lo(w4[j]); vals[2 * j + 1] += bf16_hi(w4[j]); }
             }
+            // destination row: [row] of `out`, or (EP return) wherever the row's owner wants it — possibly peer memory
+            OutT* orow = p.row_dst != nullptr ? reinterpret_cast<OutT*>(__ldg(p.row_dst + row))
+                                              : reinterpret_cast<OutT*>(p.out) + row * p.ld_out;
             if (sizeof(OutT) == 2) {
               uint4 o;
               o.x = pack_bf16(vals[0], vals[1]); o.y = pack_bf16(vals[2], vals[3]);
               o.z = pack_bf16(vals[4], vals[5]); o.w = pack_bf16(vals[6], vals[7]);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ld_out + f0) = o;
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(orow) + f0) = o;
             } else {
-              float* o = reinterpret_cast<float*>(p.out) + row * p.ld_out + f0;
+              float* o = reinterpret_cast<float*>(orow) + f0;
               *reinterpret_cast<float4*>(o) = make_float4(vals[0], vals[1], vals[2], vals[3]);
               *reinterpret_cast<float4*>(o + 4) = make_float4(vals[4], vals[5], vals[6], vals[7]);
             }
@@ -254,19 +301,11 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
         }
         named_bar_sync(1, kEpiThreads);  // staging buffer free for the next chunk / tile
       }
-      if (p.signal_flag != nullptr) {
-        // fused stage boundary: count finished tiles; the last one publishes the peer's flag
+      if (p.signal_flag != nullptr || p.signal_peers != nullptr) {
+        // fused stage boundary / EP return: count finished tiles; the last one publishes the peer flag(s)
         __threadfence_system();
         named_bar_sync(1, kEpiThreads);
-        if (et == 0) {
-          const unsigned int done = atomicAdd(p.done_counter, 1u) + 1u;
-          if (done == p.signal_tiles) {
-            *p.done_counter = 0u;
-            __threadfence_system();
-            if (p.signal_value == 0u) atomicAdd_system(p.signal_flag, 1u);
-            else st_release_sys(p.signal_flag, p.signal_value);
-          }
-        }
+        if (et == 0) publish_tile_done(p);
       }
       ++tc;
     }
@@ -346,6 +385,7 @@ cudaError_t gemm_persistent_launch(const GemmArgs& a, cudaStream_t stream) {
   if (!gemm_make_tmap(&tx, a.x, a.x_rows, a.k, a.ld_x, bn)) return cudaErrorUnknown;
 
   GemmParams p;
+  p.row_dst = nullptr; p.signal_peers = nullptr; p.num_signal_peers = 0;
   p.m = a.m; p.n = a.n; p.k = a.k; p.splits = 1; p.cluster_splitk = 0;
   p.expert_offsets = a.expert_offsets;
   p.out = a.out; p.ld_out = a.ld_out;
@@ -357,6 +397,11 @@ cudaError_t gemm_persistent_launch(const GemmArgs& a, cudaStream_t stream) {
   const int tiles_m = (a.max_rows + bn - 1) / bn;
   const int num_tiles = tiles_n * tiles_m * (grouped ? a.num_experts : 1);
   p.signal_tiles = a.signal_tiles > 0 ? a.signal_tiles : static_cast<unsigned int>(tiles_n * tiles_m);
+  if (a.signal_peers != nullptr) {
+    // EP return: every tile of the grid (empty experts included) is counted, then all peers are signalled
+    p.row_dst = a.row_dst; p.signal_peers = a.signal_peers; p.num_signal_peers = a.num_signal_peers;
+    p.signal_tiles = static_cast<unsigned int>(num_tiles);
+  }
   if (a.out_fp32) return p_dispatch_bn<false, float>(bn, tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, stream);
   if (dual) return p_dispatch_bn<true, __nv_bfloat16>(bn, tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, stream);
   return p_dispatch_bn<false, __nv_bfloat16>(bn, tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, stream);

@@ -102,13 +102,26 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
-  if (!pdl_early) pdl_wait();
+  // PDL: let the successor's CTAs become resident now (their pre-wait prologue / weight prefetch overlaps this kernel)
   pdl_launch_dependents();
 
   if (warp == 0) {
     // ============================================================== TMA producer
     if (lane == 0) {
-      for (int i = 0; i < num_kb; ++i) {
+      // Weights never depend on a predecessor kernel: the first ring-full of weight tiles is requested *before*
+      // griddepcontrol.wait, so their HBM latency overlaps the predecessor's tail; the activation tiles follow after it.
+      const int pre = pdl_early ? 0 : (num_kb < STAGES ? num_kb : STAGES);
+      for (int i = 0; i < pre; ++i) {
+        uint8_t* st = smem + i * STAGE_BYTES;
+        const int kc = (kb_begin + i) * kBlockK;
+        mbar_arrive_expect_tx(&full_bar[i], STAGE_BYTES);
+        tma_load_2d(st, &tmap_w, &full_bar[i], kc, w_row, kEvictFirst);
+        if (DUAL) tma_load_2d(st + kATileBytes, &tmap_w2, &full_bar[i], kc, w_row, kEvictFirst);
+      }
+      if (!pdl_early) pdl_wait();
+      for (int i = 0; i < pre; ++i)
+        tma_load_2d(smem + i * STAGE_BYTES + kATileBytes * (DUAL ? 2 : 1), &tmap_x, &full_bar[i], (kb_begin + i) * kBlockK, row_base, kEvictLast);
+      for (int i = pre; i < num_kb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
@@ -150,6 +163,7 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     }
   } else {
     // ============================================================== epilogue warps (128 threads)
+    if (!pdl_early) pdl_wait();  // residual / split-K workspace / out are ordered after the predecessor
     if (p.cluster_splitk)
       gemm::cluster_epilogue_store_partial<BN, DUAL>(smem, tmem_base, tmem_full_bar, warp, lane, num_kb);
     else
@@ -311,6 +325,7 @@ cudaError_t gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   if (!make_tmap(&tx, a.x, a.x_rows, a.k, a.ld_x, bn)) return cudaErrorUnknown;
 
   GemmParams p;
+  p.row_dst = nullptr; p.signal_peers = nullptr; p.num_signal_peers = 0;
   p.m = a.m; p.n = a.n; p.k = a.k; p.splits = splits;
   // DSMEM (cluster) split-K when the fp32 partial tile fits the idle stage ring and the cluster is portable
   p.cluster_splitk = (a.cluster_splitk && splits > 1 && splits <= 8 && bn * (dual ? 2 : 1) <= 128) ? 1 : 0;

@@ -27,6 +27,10 @@ struct GemmParams {
   unsigned int* done_counter;
   unsigned int signal_tiles;
   int cluster_splitk;  // 1: the `splits` CTAs of a tile form a cluster and reduce through DSMEM
+  // Expert-parallel return path fused into the grouped down-projection (gemm_persistent.cu only):
+  const unsigned long long* row_dst;       // per output row: address of its destination row (may be peer memory); overrides out
+  const unsigned long long* signal_peers;  // `num_signal_peers` flag addresses, each bumped (+1, .sys) after ALL tiles are stored
+  int num_signal_peers;
 };
 
 // Host-side launch description.  Y[rows, n] = X[rows, k] * W[n, k]^T, bf16 in, fp32 accumulate.
@@ -57,6 +61,9 @@ struct GemmArgs {
   uint32_t signal_value = 0;
   unsigned int* done_counter = nullptr;   // zero-initialised device counter
   unsigned int signal_tiles = 0;          // 0 = all tiles of the grid
+  const unsigned long long* row_dst = nullptr;       // EP return: per-row destination addresses (device array)
+  const unsigned long long* signal_peers = nullptr;  // EP return: device table of peer flag addresses
+  int num_signal_peers = 0;
   // MLX affine-quantised weights (gemm_q_launch): w / w2 point at the packed uint32 codes [rows, k*bits/32];
   // scales / biases are pre-transposed to [k/group, rows] bf16 at load time (TMA-friendly)
   bool persistent = true;                 // splits == 1: persistent kernel (gemm_persistent.cu)

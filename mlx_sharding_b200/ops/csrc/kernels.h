@@ -87,10 +87,14 @@ cudaError_t advance_meta_launch(int* positions, int* context_lens, int* slots, c
 cudaError_t ep_dispatch_launch(const void* x, long long ld_x, const int* idx, int npairs, int top_k, int H, int experts_per_rank,
                                int world, int my_rank, int cap, const unsigned long long* recv_x, const unsigned long long* recv_meta,
                                const unsigned long long* recv_count, const unsigned long long* recv_flag, int* send_counts,
-                               unsigned int* done_counter, cudaStream_t s);
+                               unsigned int* done_counter, uint32_t* ret_expected, cudaStream_t s);
 cudaError_t ep_regroup_launch(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag, const int* recv_count,
                               const void* recv_meta, const void* recv_x, int world, int cap, int E_local, int H, int* expert_offsets,
-                              int* row_perm, int* total_rows, void* x_perm, void* perm_src, cudaStream_t s);
+                              int* row_perm, int* total_rows, void* x_perm, void* perm_src, const unsigned long long* ret_y,
+                              unsigned long long* row_dst, cudaStream_t s);
+cudaError_t ep_combine_launch(const uint32_t* flag, const uint32_t* expected_ptr, uint32_t* error_flag, const float* ret_y,
+                              const float* wts, const void* residual, long long ld_res, void* out, long long ld_out, int T, int top_k,
+                              int H, cudaStream_t s);
 cudaError_t ep_return_launch(const float* y_perm, const void* perm_src, const int* total_rows, int max_rows, int H, int world,
                              const unsigned long long* ret_y, const unsigned long long* ret_flag, unsigned int* done_counter,
                              cudaStream_t s);

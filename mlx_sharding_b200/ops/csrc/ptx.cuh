@@ -144,7 +144,10 @@ B200_DEVICE void named_bar_sync(uint32_t id, uint32_t nthreads) {
 // blocks be scheduled while this grid is still running.
 B200_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 B200_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-B200_DEVICE void pdl_sync() { pdl_wait(); pdl_launch_dependents(); }
+// Small kernels: release the successor first (its CTAs become resident and run their pre-wait prologue — for the GEMMs that is
+// barrier init, TMEM alloc and the first ring-full of *weight* TMA loads), then wait for the predecessor.  Nothing before the
+// wait may touch memory a predecessor writes; completion of grid i+1 implies completion of grid i, so the chain stays ordered.
+B200_DEVICE void pdl_sync() { pdl_launch_dependents(); pdl_wait(); }
 
 B200_DEVICE float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 B200_DEVICE float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }

@@ -58,9 +58,11 @@ class EPBuffers:
         self.t_recv_flag = [p + self.off_flags for p in self.peer]
         self.t_ret_y = [p + self.off_ret_y for p in self.peer]
         self.t_ret_flag = [p + self.off_flags + 128 for p in self.peer]
-        # device-resident local state: [send_counts(world) | done counters(2) | arrival counters(2) | error]
+        # device-resident local state: [send_counts(world) | dispatch done ctr | down-GEMM tile ctr | regroup arrivals seen |
+        #                               return arrivals expected | ... | error]
         self.state = torch.zeros(W + 8, dtype=torch.int32, device="cuda")
         self.ret_y = self.C.tensor_from_ptr(self.base + self.off_ret_y, [cap, H], "float32", self.dev)
+        self.ret_flags_dev = torch.tensor(self.t_ret_flag, dtype=torch.int64, device="cuda")   # every source's return flag
         dist.barrier(group=group)
 
     def error(self) -> bool:
@@ -94,24 +96,22 @@ class ExpertParallelMoE:
         W = b.world
         st = b.state
         Tmax = max(T, peer_tokens or 0)
-        # 1) dispatch my pairs to the owners of their experts (remote stores + count/flag publication)
+        # 1) dispatch my pairs to the owners of their experts (remote stores + count/flag publication); also advances the
+        #    arrival target of this step's combine (st[W+3] += world)
         C.ep_dispatch(x, idx, self.E_local, b.rank, b.cap, b.t_recv_x, b.t_recv_meta, b.t_recv_count, b.t_recv_flag,
-                      st[:W], st[W:W + 1])
-        # 2) wait for every source, bucket what I received by local expert
-        offs, total, x_perm, perm_src = C.ep_regroup(b.base + b.off_flags, st[W + 2:W + 3].data_ptr(), st[-1:].data_ptr(),
-                                                     b.base + b.off_recv_count, b.base + b.off_recv_meta,
-                                                     b.base + b.off_recv_x, W, b.cap, self.E_local, b.H, b.dev,
-                                                     min(W * b.cap, W * Tmax * k))
-        # 3) my experts: grouped swap-AB tcgen05 GEMMs on the received rows
+                      st[:W], st[W:W + 1], st[W + 3:W + 4])
+        # 2) wait for every source, bucket what I received by local expert; row_dst[r] = where row r's output must go
+        offs, total, x_perm, perm_src, row_dst = C.ep_regroup(
+            b.base + b.off_flags, st[W + 2:W + 3].data_ptr(), st[-1:].data_ptr(), b.base + b.off_recv_count,
+            b.base + b.off_recv_meta, b.base + b.off_recv_x, W, b.cap, self.E_local, b.H, b.dev, min(W * b.cap, W * Tmax * k), b.t_ret_y)
+        # 3) my experts: grouped swap-AB tcgen05 GEMMs on the received rows; the down-projection epilogue stores every output
+        #    row straight into its source rank's return buffer (peer memory) and the last tile bumps all sources' flags
         max_rows = min(W * Tmax, x_perm.shape[0])  # upper bound of rows one expert can receive (every rank sends <= Tmax)
-        h = C.grouped_linear(x_perm, self.wg, self.wu, offs, max_rows, self.act, False)
-        y = C.grouped_linear(h, self.wd, None, offs, max_rows, 0, True)
-        # 4) push every output row back to the rank / pair it came from
-        C.ep_return(y, perm_src, total, b.t_ret_y, b.t_ret_flag, st[W + 1:W + 2])
-        # 5) wait for all my pairs to come home, weighted combine (+ residual)
-        C.ep_wait_all(b.base + b.off_flags + 128, st[W + 3:W + 4].data_ptr(), W, st[-1:].data_ptr())
-        pair_row = self._identity(T * k, x.device)
-        return C.moe_combine(b.ret_y, pair_row, w, residual, out, int(k), 0, 0)
+        exp_rows = Tmax * k  # balanced routing: every rank receives about as many pairs as it sends (sizes the token tile)
+        h = C.grouped_linear(x_perm, self.wg, self.wu, offs, max_rows, self.act, False, None, None, None, exp_rows)
+        C.grouped_linear(h, self.wd, None, offs, max_rows, 0, True, row_dst, b.ret_flags_dev, st[W + 1:W + 2], exp_rows)
+        # 4) wait for all my pairs to come home + weighted combine (+ residual): one kernel
+        return C.ep_combine(b.base + b.off_flags + 128, st[W + 3:W + 4], st[-1:].data_ptr(), b.ret_y, w, residual, out)
 
     _ident = {}
 
