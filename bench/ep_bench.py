@@ -98,10 +98,10 @@ def main():
             dist.barrier()
             evs[0].record()
             idx, w = b200.moe_route(x0, gate, k); evs[1].record()
-            C.ep_dispatch(x0, idx, ep.E_local, b.rank, b.cap, b.t_recv_x, b.t_recv_meta, b.t_recv_count, b.t_recv_flag, st[:W], st[W:W + 1],
+            C.ep_dispatch(x0, idx, ep.E_local, b.rank, b.cap, b.t_recv_x, b.t_recv_meta, b.t_recv_count, st[W + 4:W + 5], st[:W], st[W:W + 1],
                           st[W + 3:W + 4]); evs[2].record()
-            offs, total, x_perm, perm_src, row_dst = C.ep_regroup(b.base + b.off_flags, st[W + 2:W + 3].data_ptr(), st[-1:].data_ptr(),
-                                                                  b.base + b.off_recv_count, b.base + b.off_recv_meta, b.base + b.off_recv_x, W,
+            offs, total, x_perm, perm_src, row_dst = C.ep_regroup(b.base + b.off_recv_count, st[W + 2:W + 3].data_ptr(), st[-1:].data_ptr(),
+                                                                  b.base + b.off_recv_meta, b.base + b.off_recv_x, W,
                                                                   b.cap, ep.E_local, b.H, b.dev, W * T * k, b.t_ret_y); evs[3].record()
             mr = min(W * T, x_perm.shape[0])
             h = C.grouped_linear(x_perm, ep.wg, ep.wu, offs, mr, ep.act, False, None, None, None, exp_rows); evs[4].record()

@@ -515,20 +515,21 @@ std::vector<unsigned long long> to_u64(const std::vector<int64_t>& v) {
   return o;
 }
 void ep_dispatch(const Tensor& x, const Tensor& idx, int64_t experts_per_rank, int64_t my_rank, int64_t cap,
-                 std::vector<int64_t> recv_x, std::vector<int64_t> recv_meta, std::vector<int64_t> recv_count,
-                 std::vector<int64_t> recv_flag, Tensor send_counts, Tensor done_counter, const c10::optional<Tensor>& ret_expected) {
+                 std::vector<int64_t> recv_x, std::vector<int64_t> recv_meta, std::vector<int64_t> recv_words, Tensor send_seq,
+                 Tensor send_counts, Tensor done_counter, const c10::optional<Tensor>& ret_expected) {
   check_bf16(x, "x"); check_rows(x, "x");
   TORCH_CHECK(idx.scalar_type() == torch::kInt32 && idx.is_contiguous() && idx.dim() == 2);
   const c10::cuda::CUDAGuard guard(x.device());
   const int world = (int)recv_x.size();
-  auto a = to_u64(recv_x), b = to_u64(recv_meta), c = to_u64(recv_count), d = to_u64(recv_flag);
+  auto a = to_u64(recv_x), b = to_u64(recv_meta), c = to_u64(recv_words);
   LAUNCH_OK(b200::ep_dispatch_launch(x.data_ptr(), x.stride(0), idx.data_ptr<int>(), (int)idx.numel(), (int)idx.size(1), (int)x.size(1),
-                                     (int)experts_per_rank, world, (int)my_rank, (int)cap, a.data(), b.data(), c.data(), d.data(),
-                                     send_counts.data_ptr<int>(), reinterpret_cast<unsigned int*>(done_counter.data_ptr<int>()),
+                                     (int)experts_per_rank, world, (int)my_rank, (int)cap, a.data(), b.data(), c.data(),
+                                     reinterpret_cast<uint32_t*>(send_seq.data_ptr<int>()), send_counts.data_ptr<int>(),
+                                     reinterpret_cast<unsigned int*>(done_counter.data_ptr<int>()),
                                      ret_expected.has_value() ? reinterpret_cast<uint32_t*>(ret_expected->data_ptr<int>()) : nullptr,
                                      cur_stream()));
 }
-std::vector<Tensor> ep_regroup(int64_t flag_ptr, int64_t counter_ptr, int64_t error_ptr, int64_t recv_count_ptr, int64_t recv_meta_ptr,
+std::vector<Tensor> ep_regroup(int64_t recv_words_ptr, int64_t counter_ptr, int64_t error_ptr, int64_t recv_meta_ptr,
                                int64_t recv_x_ptr, int64_t world, int64_t cap, int64_t E_local, int64_t H, int64_t device,
                                int64_t rows_bound, std::vector<int64_t> ret_y) {
   auto dev = torch::Device(torch::kCUDA, (int)device);
@@ -537,13 +538,13 @@ std::vector<Tensor> ep_regroup(int64_t flag_ptr, int64_t counter_ptr, int64_t er
   // rows_bound (>0): the caller's bound on the rows all sources can send this step; sizes the expert-ordered temporaries
   const int64_t R = rows_bound > 0 ? std::min<int64_t>(world * cap, rows_bound) : world * cap;
   Tensor offs = torch::empty({E_local + 1}, io), row_perm = torch::empty({world * cap}, io), total = torch::empty({1}, io);
-  Tensor perm_src = torch::empty({R, 2}, io);
+  Tensor perm_src = torch::empty({R, 2}, io), counts = torch::empty({world}, io);
   Tensor x_perm = torch::empty({R, H}, torch::dtype(torch::kBFloat16).device(dev));
   // destination address of every expert-ordered row for the fused return (down-projection epilogue -> source's return buffer)
   Tensor row_dst = torch::empty({ret_y.empty() ? 0 : R}, torch::dtype(torch::kInt64).device(dev));
   auto ry = to_u64(ret_y);
-  LAUNCH_OK(b200::ep_regroup_launch(reinterpret_cast<const uint32_t*>(flag_ptr), reinterpret_cast<uint32_t*>(counter_ptr),
-                                    reinterpret_cast<uint32_t*>(error_ptr), reinterpret_cast<const int*>(recv_count_ptr),
+  LAUNCH_OK(b200::ep_regroup_launch(reinterpret_cast<const unsigned long long*>(recv_words_ptr), reinterpret_cast<uint32_t*>(counter_ptr),
+                                    reinterpret_cast<uint32_t*>(error_ptr), counts.data_ptr<int>(),
                                     reinterpret_cast<const void*>(recv_meta_ptr), reinterpret_cast<const void*>(recv_x_ptr), (int)world,
                                     (int)cap, (int)E_local, (int)H, offs.data_ptr<int>(), row_perm.data_ptr<int>(), total.data_ptr<int>(),
                                     x_perm.data_ptr(), perm_src.data_ptr(), ret_y.empty() ? nullptr : ry.data(),
@@ -619,9 +620,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("copy_signal", &copy_signal);
   m.def("advance_meta", &advance_meta);
   m.def("ep_dispatch", &ep_dispatch, py::arg("x"), py::arg("idx"), py::arg("experts_per_rank"), py::arg("my_rank"), py::arg("cap"),
-        py::arg("recv_x"), py::arg("recv_meta"), py::arg("recv_count"), py::arg("recv_flag"), py::arg("send_counts"),
+        py::arg("recv_x"), py::arg("recv_meta"), py::arg("recv_words"), py::arg("send_seq"), py::arg("send_counts"),
         py::arg("done_counter"), py::arg("ret_expected") = py::none());
-  m.def("ep_regroup", &ep_regroup, py::arg("flag_ptr"), py::arg("counter_ptr"), py::arg("error_ptr"), py::arg("recv_count_ptr"),
+  m.def("ep_regroup", &ep_regroup, py::arg("recv_words_ptr"), py::arg("counter_ptr"), py::arg("error_ptr"),
         py::arg("recv_meta_ptr"), py::arg("recv_x_ptr"), py::arg("world"), py::arg("cap"), py::arg("E_local"), py::arg("H"),
         py::arg("device"), py::arg("rows_bound") = 0, py::arg("ret_y") = std::vector<int64_t>());
   m.def("ep_combine", &ep_combine, py::arg("flag_ptr"), py::arg("expected"), py::arg("error_ptr"), py::arg("ret_y"), py::arg("wts"),

@@ -37,8 +37,8 @@ __global__ void ep_dispatch_kernel(const __nv_bfloat16* __restrict__ x, long lon
                                    int top_k, int H, int experts_per_rank, int world, int my_rank, int cap,
                                    PeerTable recv_x,      // per dst: base of [world][cap][H] bf16 (its receive regions)
                                    PeerTable recv_meta,   // per dst: base of [world][cap] int2
-                                   PeerTable recv_count,  // per dst: base of [world] int
-                                   PeerTable recv_flag,   // per dst: uint32 flag (counting)
+                                   PeerTable recv_count,  // per dst: base of [world] u64 words (count << 32 | step sequence)
+                                   uint32_t* __restrict__ send_seq,  // my step sequence number (device resident)
                                    int* __restrict__ send_counts, unsigned int* __restrict__ done_counter,
                                    uint32_t* __restrict__ ret_expected /* += world: arrivals the combine of this step waits for */) {
   pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
@@ -61,7 +61,9 @@ __global__ void ep_dispatch_kernel(const __nv_bfloat16* __restrict__ x, long lon
       }
     }
   }
-  // publish: last CTA writes the row counts into every destination and raises its flag
+  // publish: the last CTA tells every destination how many rows it got from me.  Count and step sequence number travel in ONE
+  // 64-bit word written with st.release.sys (every CTA fenced its row stores before arriving on done_counter), so the
+  // receiver needs no separate flag and the sender no second fence / atomic round trip.
   __threadfence_system();
   __syncthreads();
   __shared__ bool last;
@@ -69,15 +71,17 @@ __global__ void ep_dispatch_kernel(const __nv_bfloat16* __restrict__ x, long lon
   __syncthreads();
   if (last) {
     __threadfence_system();
+    const uint32_t seq = *send_seq + 1u;
     for (int r = threadIdx.x; r < world; r += blockDim.x) {
       int c = __ldcg(&send_counts[r]);
       if (c > cap) c = cap;
-      reinterpret_cast<int*>(recv_count.p[r])[my_rank] = c;
       send_counts[r] = 0;
-      __threadfence_system();
-      atomicAdd_system(reinterpret_cast<unsigned int*>(recv_flag.p[r]), 1u);
+      st_release_sys_u64(reinterpret_cast<unsigned long long*>(recv_count.p[r]) + my_rank,
+                         (static_cast<unsigned long long>(static_cast<uint32_t>(c)) << 32) | seq);
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
+      *send_seq = seq;
       *done_counter = 0u;
       if (ret_expected != nullptr) *ret_expected += (uint32_t)world;
     }
@@ -87,31 +91,36 @@ __global__ void ep_dispatch_kernel(const __nv_bfloat16* __restrict__ x, long lon
 // ---------------------------------------------------------------------------------------------- regroup
 // single CTA: wait for all sources, bucket received rows by local expert
 __global__ void __launch_bounds__(1024)
-ep_regroup_offsets_kernel(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag, unsigned long long timeout_ns,
-                          const int* __restrict__ recv_count, const int2* __restrict__ recv_meta, int world, int cap,
+ep_regroup_offsets_kernel(const unsigned long long* recv_words, uint32_t* local_counter, uint32_t* error_flag, unsigned long long timeout_ns,
+                          int* __restrict__ recv_count_out, const int2* __restrict__ recv_meta, int world, int cap,
                           int E_local, int* __restrict__ expert_offsets, int* __restrict__ row_perm /*[world*cap]*/,
                           int* __restrict__ total_rows) {
   pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   __shared__ int cnt[256], cur[256];
   __shared__ int counts[kMaxWorld];
-  if (threadIdx.x == 0) {
-    // every source bumps the flag once per step: wait until `world` more arrivals than we have consumed
-    const uint32_t expected = atomicAdd(local_counter, (uint32_t)world) + (uint32_t)world;
-    unsigned long long t0;
+  __shared__ uint32_t expected_s;
+  if (threadIdx.x == 0) expected_s = *local_counter + 1u;   // my own step sequence number
+  __syncthreads();
+  if (threadIdx.x < world) {
+    // source `threadIdx.x` publishes (count << 32 | seq) once its rows are visible: poll until it carries this step's seq
+    const uint32_t expected = expected_s;
+    const unsigned long long* word = recv_words + threadIdx.x;
+    unsigned long long t0, v;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
     while (true) {
-      const uint32_t v = ld_acquire_sys(flag);
-      if ((int32_t)(v - expected) >= 0) break;
+      v = ld_acquire_sys_u64(word);
+      if (static_cast<uint32_t>(v) == expected) break;
       unsigned long long t1;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-      if (t1 - t0 > timeout_ns) { if (error_flag) atomicExch(error_flag, 1u); break; }
+      if (t1 - t0 > timeout_ns) { if (error_flag) atomicExch(error_flag, 1u); v = 0; break; }
       __nanosleep(32);
     }
+    counts[threadIdx.x] = static_cast<int>(v >> 32);
+    recv_count_out[threadIdx.x] = counts[threadIdx.x];   // plain copy for the gather kernel
     __threadfence_system();
   }
+  if (threadIdx.x == 0) *local_counter = expected_s;
   for (int e = threadIdx.x; e < E_local; e += blockDim.x) cnt[e] = 0;
-  __syncthreads();
-  if (threadIdx.x < world) counts[threadIdx.x] = __ldcv(&recv_count[threadIdx.x]);
   __syncthreads();
   for (int s = 0; s < world; ++s)
     for (int j = threadIdx.x; j < counts[s]; j += blockDim.x) atomicAdd(&cnt[__ldcv(&recv_meta[(size_t)s * cap + j].x)], 1);
@@ -264,7 +273,7 @@ PeerTable make_table(const unsigned long long* v, int world) {
 
 cudaError_t ep_dispatch_launch(const void* x, long long ld_x, const int* idx, int npairs, int top_k, int H, int experts_per_rank,
                                int world, int my_rank, int cap, const unsigned long long* recv_x, const unsigned long long* recv_meta,
-                               const unsigned long long* recv_count, const unsigned long long* recv_flag, int* send_counts,
+                               const unsigned long long* recv_count, uint32_t* send_seq, int* send_counts,
                                unsigned int* done_counter, uint32_t* ret_expected, cudaStream_t s) {
   if (world > kMaxWorld || (H % 8)) return cudaErrorInvalidValue;
   int grid = (npairs + 7) / 8;
@@ -272,22 +281,22 @@ cudaError_t ep_dispatch_launch(const void* x, long long ld_x, const int* idx, in
   if (grid > 592) grid = 592;
   (void)launch_pdl(ep_dispatch_kernel, dim3(grid), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(x), ld_x, idx, npairs, top_k, H, experts_per_rank, world,
                                           my_rank, cap, make_table(recv_x, world), make_table(recv_meta, world),
-                                          make_table(recv_count, world), make_table(recv_flag, world), send_counts, done_counter, ret_expected);
+                                          make_table(recv_count, world), send_seq, send_counts, done_counter, ret_expected);
   return cudaGetLastError();
 }
 
-cudaError_t ep_regroup_launch(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag, const int* recv_count,
+cudaError_t ep_regroup_launch(const unsigned long long* recv_words, uint32_t* local_counter, uint32_t* error_flag, int* recv_count,
                               const void* recv_meta, const void* recv_x, int world, int cap, int E_local, int H, int* expert_offsets,
                               int* row_perm, int* total_rows, void* x_perm, void* perm_src, const unsigned long long* ret_y,
                               unsigned long long* row_dst, cudaStream_t s) {
   if (E_local > 256 || world > kMaxWorld) return cudaErrorInvalidValue;
-  (void)launch_pdl(ep_regroup_offsets_kernel, dim3(1), dim3(1024), 0, s, flag, local_counter, error_flag, kTimeoutNs, recv_count,
+  (void)launch_pdl(ep_regroup_offsets_kernel, dim3(1), dim3(1024), 0, s, recv_words, local_counter, error_flag, kTimeoutNs, recv_count,
                                                static_cast<const int2*>(recv_meta), world, cap, E_local, expert_offsets, row_perm,
                                                total_rows);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   dim3 grid(64, world);
-  (void)launch_pdl(ep_regroup_gather_kernel, dim3(grid), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(recv_x), static_cast<const int2*>(recv_meta), recv_count,
+  (void)launch_pdl(ep_regroup_gather_kernel, dim3(grid), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(recv_x), static_cast<const int2*>(recv_meta), static_cast<const int*>(recv_count),
                                                 row_perm, world, cap, H, static_cast<__nv_bfloat16*>(x_perm), static_cast<int2*>(perm_src),
                                                 ret_y != nullptr ? make_table(ret_y, world) : PeerTable{}, row_dst);
   return cudaGetLastError();

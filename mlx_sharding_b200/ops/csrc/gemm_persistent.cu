@@ -61,10 +61,11 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmParams& p, int t, int 
 
 }  // namespace
 
-// One thread per finished tile: the last arrival raises the consumer flag(s) with system scope.  (Every CTA fenced its own
-// stores before arriving, so the flag is ordered after all tiles.)
-__device__ __forceinline__ void publish_tile_done(const GemmParams& p) {
-  const unsigned int done = atomicAdd(p.done_counter, 1u) + 1u;
+// One thread per CTA, once, after the CTA's last tile (a system fence per *tile* would stall the epilogue on an NVLink round
+// trip each time when `out` is peer memory): reports how many tiles of the grid this CTA covered; the arrival that completes
+// the grid raises the consumer flag(s) with system scope.  Every CTA fences its own stores before arriving.
+__device__ __forceinline__ void publish_tiles_done(const GemmParams& p, unsigned int n) {
+  const unsigned int done = atomicAdd(p.done_counter, n) + n;
   if (done != p.signal_tiles) return;
   *p.done_counter = 0u;
   __threadfence_system();
@@ -215,11 +216,11 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
     const int f_local = q * 32 + lane;
     const int et = threadIdx.x - 64;
     constexpr int kVec = 8, kChunks = kTileM / kVec, kRowsPerIter = kEpiThreads / kChunks;
-    uint32_t tc = 0;
+    uint32_t tc = 0, my_tiles = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const TileInfo ti = decode_tile(p, t, tiles_n, tiles_m, BN);
       if (ti.rows_valid <= 0) {
-        if (p.signal_peers != nullptr && et == 0) publish_tile_done(p);  // empty tiles are counted too (EP return)
+        ++my_tiles;  // empty tiles are counted too (EP return: signal_tiles = whole grid)
         continue;
       }
       const uint32_t ab = tc % NUM_ACC, aph = (tc / NUM_ACC) & 1;
@@ -301,13 +302,14 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
         }
         named_bar_sync(1, kEpiThreads);  // staging buffer free for the next chunk / tile
       }
-      if (p.signal_flag != nullptr || p.signal_peers != nullptr) {
-        // fused stage boundary / EP return: count finished tiles; the last one publishes the peer flag(s)
-        __threadfence_system();
-        named_bar_sync(1, kEpiThreads);
-        if (et == 0) publish_tile_done(p);
-      }
+      ++my_tiles;
       ++tc;
+    }
+    if (p.signal_flag != nullptr || p.signal_peers != nullptr) {
+      // fused stage boundary / EP return: `out` rows went to peer memory; fence once, then report this CTA's tiles
+      __threadfence_system();
+      named_bar_sync(1, kEpiThreads);
+      if (et == 0) publish_tiles_done(p, p.signal_peers != nullptr ? my_tiles : tc);
     }
     tc_fence_before();
   }

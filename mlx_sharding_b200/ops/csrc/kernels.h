@@ -86,9 +86,9 @@ cudaError_t advance_meta_launch(int* positions, int* context_lens, int* slots, c
 // ---- ep.cu (expert-parallel all-to-all over peer memory)
 cudaError_t ep_dispatch_launch(const void* x, long long ld_x, const int* idx, int npairs, int top_k, int H, int experts_per_rank,
                                int world, int my_rank, int cap, const unsigned long long* recv_x, const unsigned long long* recv_meta,
-                               const unsigned long long* recv_count, const unsigned long long* recv_flag, int* send_counts,
+                               const unsigned long long* recv_count, uint32_t* send_seq, int* send_counts,
                                unsigned int* done_counter, uint32_t* ret_expected, cudaStream_t s);
-cudaError_t ep_regroup_launch(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag, const int* recv_count,
+cudaError_t ep_regroup_launch(const unsigned long long* recv_words, uint32_t* local_counter, uint32_t* error_flag, int* recv_count,
                               const void* recv_meta, const void* recv_x, int world, int cap, int E_local, int H, int* expert_offsets,
                               int* row_perm, int* total_rows, void* x_perm, void* perm_src, const unsigned long long* ret_y,
                               unsigned long long* row_dst, cudaStream_t s);

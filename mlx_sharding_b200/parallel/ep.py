@@ -37,7 +37,7 @@ class EPBuffers:
         self.off_recv_x = 0
         self.off_recv_meta = self.off_recv_x + W * cap * H * 2
         self.off_recv_count = self.off_recv_meta + W * cap * 8
-        self.off_ret_y = (self.off_recv_count + W * 4 + 255) // 256 * 256
+        self.off_ret_y = (self.off_recv_count + W * 8 + 255) // 256 * 256     # recv_count: one u64 (count << 32 | step seq) per source
         self.off_flags = self.off_ret_y + cap * H * 4
         total = self.off_flags + 256
         self.base, handle = self.C.ipc_alloc(total)
@@ -58,8 +58,8 @@ class EPBuffers:
         self.t_recv_flag = [p + self.off_flags for p in self.peer]
         self.t_ret_y = [p + self.off_ret_y for p in self.peer]
         self.t_ret_flag = [p + self.off_flags + 128 for p in self.peer]
-        # device-resident local state: [send_counts(world) | dispatch done ctr | down-GEMM tile ctr | regroup arrivals seen |
-        #                               return arrivals expected | ... | error]
+        # device-resident local state: [send_counts(world) | dispatch done ctr | down-GEMM tile ctr | regroup step seq seen |
+        #                               return arrivals expected | dispatch step seq | ... | error]
         self.state = torch.zeros(W + 8, dtype=torch.int32, device="cuda")
         self.ret_y = self.C.tensor_from_ptr(self.base + self.off_ret_y, [cap, H], "float32", self.dev)
         self.ret_flags_dev = torch.tensor(self.t_ret_flag, dtype=torch.int64, device="cuda")   # every source's return flag
@@ -98,11 +98,11 @@ class ExpertParallelMoE:
         Tmax = max(T, peer_tokens or 0)
         # 1) dispatch my pairs to the owners of their experts (remote stores + count/flag publication); also advances the
         #    arrival target of this step's combine (st[W+3] += world)
-        C.ep_dispatch(x, idx, self.E_local, b.rank, b.cap, b.t_recv_x, b.t_recv_meta, b.t_recv_count, b.t_recv_flag,
+        C.ep_dispatch(x, idx, self.E_local, b.rank, b.cap, b.t_recv_x, b.t_recv_meta, b.t_recv_count, st[W + 4:W + 5],
                       st[:W], st[W:W + 1], st[W + 3:W + 4])
         # 2) wait for every source, bucket what I received by local expert; row_dst[r] = where row r's output must go
         offs, total, x_perm, perm_src, row_dst = C.ep_regroup(
-            b.base + b.off_flags, st[W + 2:W + 3].data_ptr(), st[-1:].data_ptr(), b.base + b.off_recv_count,
+            b.base + b.off_recv_count, st[W + 2:W + 3].data_ptr(), st[-1:].data_ptr(),
             b.base + b.off_recv_meta, b.base + b.off_recv_x, W, b.cap, self.E_local, b.H, b.dev, min(W * b.cap, W * Tmax * k), b.t_ret_y)
         # 3) my experts: grouped swap-AB tcgen05 GEMMs on the received rows; the down-projection epilogue stores every output
         #    row straight into its source rank's return buffer (peer memory) and the last tile bumps all sources' flags
