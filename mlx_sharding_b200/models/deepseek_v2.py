@@ -14,6 +14,7 @@ B200 design notes:
 """
 from __future__ import annotations
 
+import os
 import re
 from typing import Dict
 
@@ -27,6 +28,7 @@ _EXPERT_RE = re.compile(r"^(model\.layers\.\d+\.mlp)\.experts\.(\d+)\.(gate_proj
 
 class DeepseekV2Stage(StageModel):
     arch = "deepseek_v2"
+    overlap_shared_experts = os.environ.get("MLXB200_OVERLAP_SHARED", "1") != "0"
 
     @property
     def head_dim(self):
@@ -112,18 +114,29 @@ class DeepseekV2Stage(StageModel):
         T = h.shape[0]
         normed = O.rmsnorm(h, w["post_ln"], c.rms_norm_eps)
         if "router" in w:
+            join = None
+            if "s_gate" in w:
+                # shared experts: h += down(silu(gate x) * up x).  Independent of the routed path until the final combine, so the
+                # CUDA backend runs the two GEMMs on a side stream (a parallel branch of the decode graph) while the main
+                # stream does router -> permutation / expert all-to-all -> expert GEMMs; the combine joins them.
+                if self.overlap_shared_experts and hasattr(O, "run_aside") and self.backend_name == "b200":
+                    hs, h_in = torch.empty_like(h), h   # result buffer allocated before the fork
+                    join = O.run_aside(lambda: O.linear(O.gated_up(normed, w["s_gate"], w["s_up"], "silu"), w["s_down"],
+                                                        residual=h_in, out=hs))
+                    h = hs
+                else:
+                    h = O.linear(O.gated_up(normed, w["s_gate"], w["s_up"], "silu"), w["s_down"], residual=h)
             idx, wts = O.moe_route(normed, w["router"], c.num_experts_per_tok, c.topk_method,
                                    c.n_group or 1, c.topk_group or 1, c.routed_scaling_factor,
                                    c.norm_topk_prob)
-            if "s_gate" in w:
-                h = O.linear(O.gated_up(normed, w["s_gate"], w["s_up"], "silu"), w["s_down"], residual=h)
             ep = getattr(self, "ep_layers", None)
             if ep is not None and i in ep:
                 # expert-parallel mode (parallel/ep.py): routed experts are sharded over the ranks of the NVSwitch
                 # domain, tokens travel through the fused dispatch / return kernels
-                return ep[i].forward(normed, idx, wts, residual=h)
+                return ep[i].forward(normed, idx, wts, residual=h, join=join)
+            kw = dict(join=join) if join is not None else {}
             return O.moe_experts(normed, idx, wts, w["e_gate"], w["e_up"], w["e_down"], "silu", residual=h,
-                                 **self._final_kwargs(i, T, "mlp"))
+                                 **kw, **self._final_kwargs(i, T, "mlp"))
         return O.linear(O.gated_up(normed, w["gate"], w["up"], "silu"), w["down"], residual=h,
                         **self._final_kwargs(i, T, "mlp"))
 

@@ -181,9 +181,43 @@ def moe_route(x, gate_w, top_k: int, method: str = "greedy", n_group: int = 1, t
     return idx, w
 
 
+class _Join:
+    """Handle of work forked onto the side stream by :func:`run_aside`; ``wait()`` joins it into the current stream."""
+
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+        C().pdl_skip_next()  # the joining kernel depends on two streams: plain dependencies, no programmatic edge
+
+
+_side_streams = {}
+
+
+def run_aside(fn) -> _Join:
+    """Run ``fn()`` on this device's side stream, forked from the current stream (event record / wait, so it is also legal
+    inside CUDA-graph capture and becomes a parallel branch of the graph).  Used to run the shared-expert GEMMs of a
+    DeepSeek MoE block concurrently with the router / permutation / expert all-to-all, which do not depend on them.
+    ``fn`` must write its result into a tensor allocated *before* the fork."""
+    cur = torch.cuda.current_stream()
+    side = _side_streams.get(cur.device.index)
+    if side is None:
+        side = _side_streams[cur.device.index] = torch.cuda.Stream(device=cur.device)
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    side.wait_event(fork)
+    with torch.cuda.stream(side):
+        C().pdl_skip_next()  # first side kernel depends on the other stream
+        fn()
+        done = torch.cuda.Event()
+        done.record(side)
+    return _Join(done)
+
+
 def moe_experts(x, idx, w, Wg: LinearWeight, Wu: LinearWeight, Wd: LinearWeight, act: str = "silu",
                 extra: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-                out: Optional[torch.Tensor] = None, signal: Optional[Tuple[int, int]] = None):
+                out: Optional[torch.Tensor] = None, signal: Optional[Tuple[int, int]] = None, join: Optional[_Join] = None):
     """router output -> permute -> grouped dual GEMM (act(gate)*up) -> grouped down GEMM (fp32) ->
     weighted combine (+ residual [+ P2P store & flag])."""
     c = C()
@@ -205,6 +239,8 @@ def moe_experts(x, idx, w, Wg: LinearWeight, Wu: LinearWeight, Wd: LinearWeight,
     if extra is not None:
         residual = extra if residual is None else residual + extra
     flag, val = signal if signal is not None else (0, 0)
+    if join is not None:
+        join.wait()  # ``residual`` is produced on the side stream (shared experts)
     return c.moe_combine(y, pair_row, w, residual, out, int(k), int(flag), int(val))
 
 

@@ -198,7 +198,10 @@ Tensor linear_q(const Tensor& x, const Tensor& wq, const Tensor& scales_t, const
   if (residual.has_value()) { check_bf16(*residual, "residual"); check_rows(*residual, "residual"); a.residual = residual->data_ptr(); a.ld_res = residual->stride(0); }
   if (bias.has_value()) { check_bf16(*bias, "bias"); a.bias = bias->data_ptr(); }
   a.act = (int)act; a.softcap = (float)softcap;
-  int sp = splits > 0 ? (int)splits : 1;  // quantised weights: 3.5x fewer bytes per tile, the persistent kernel needs no split-K
+  // quantised weights: 3.5x fewer bytes per tile, so batches of >= 64 tokens use the persistent kernel un-split; tiny decode
+  // batches are latency-bound per tile like the bf16 path and take the same split-K heuristic (MLXB200_Q_SPLITK=0 disables)
+  static const bool q_splitk = [] { const char* e = std::getenv("MLXB200_Q_SPLITK"); return !(e && e[0] == '0'); }();
+  int sp = splits > 0 ? (int)splits : ((q_splitk && T <= 32) ? auto_splits((int)T, (int)N, (int)K, false) : 1);
   a.splits = sp;
   auto& sc = scratch();
   Tensor ctr = sc.get_counters(x.device());
@@ -631,5 +634,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ep_wait_all", &ep_wait_all);
   m.def("init_scratch", &init_scratch);
   m.def("launch_count", []() { return g_launches; });
+  m.def("pdl_skip_next", []() { b200::pdl_skip_next(); });
   m.def("sm_arch", []() { return std::string("sm_100a"); });
 }

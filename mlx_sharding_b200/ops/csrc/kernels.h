@@ -83,6 +83,9 @@ cudaError_t copy_signal_launch(const void* src, void* dst, size_t bytes, uint32_
 cudaError_t advance_meta_launch(int* positions, int* context_lens, int* slots, const int* block_tables, int max_blocks,
                                 int page, int B, cudaStream_t s);
 
+// ---- launch.h: the next kernel launched by this host thread gets plain (non-programmatic) dependencies
+void pdl_skip_next();
+
 // ---- ep.cu (expert-parallel all-to-all over peer memory)
 cudaError_t ep_dispatch_launch(const void* x, long long ld_x, const int* idx, int npairs, int top_k, int H, int experts_per_rank,
                                int world, int my_rank, int cap, const unsigned long long* recv_x, const unsigned long long* recv_meta,

@@ -27,6 +27,19 @@ inline bool pdl_enabled() {
   return v != 0;
 }
 
+// One-shot opt-out for the next launch of this host thread: the first kernel after a cross-stream fork / join has a
+// dependency that is not its same-stream predecessor, so it is launched with plain (full) dependencies.
+inline bool& pdl_skip_next_flag() {
+  static thread_local bool skip = false;
+  return skip;
+}
+inline bool pdl_use_now() {
+  bool& skip = pdl_skip_next_flag();
+  const bool use = pdl_enabled() && !skip;
+  skip = false;
+  return use;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -38,7 +51,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = pdl_use_now() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -64,7 +77,7 @@ inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 
     attr[n].val.clusterDim.z = cluster_z;
     ++n;
   }
-  if (pdl_enabled()) {
+  if (pdl_use_now()) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;

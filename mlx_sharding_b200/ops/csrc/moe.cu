@@ -36,7 +36,7 @@ __device__ __forceinline__ void warp_argmax(float& v, int& i) {
 // TOKS tokens per CTA share every router-weight read: 8 for prefill-sized batches, 1 for decode batches
 // (more CTAs; the 256 KB router matrix is L2 resident).
 template <int kRouteToks>
-__global__ void __launch_bounds__(kRouteThreads)
+__global__ void __launch_bounds__(kRouteToks == 1 ? 1024 : kRouteThreads)
 moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv_bfloat16* __restrict__ gw, int T, int H,
                  int E, int top_k, int n_group, int topk_group, float scaling, int norm_topk, int* __restrict__ idx,
                  float* __restrict__ wts) {
@@ -47,14 +47,14 @@ moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv
   const int t0 = blockIdx.x * kRouteToks;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = H / 8;
-  for (int i = threadIdx.x; i < kRouteToks * nvec; i += kRouteThreads) {
+  for (int i = threadIdx.x; i < kRouteToks * nvec; i += blockDim.x) {
     const int tk = i / nvec, v = i % nvec;
     uint4 r = make_uint4(0, 0, 0, 0);
     if (t0 + tk < T) r = reinterpret_cast<const uint4*>(x + (size_t)(t0 + tk) * ld_x)[v];
     reinterpret_cast<uint4*>(xs + (size_t)tk * H)[v] = r;
   }
   __syncthreads();
-  for (int e = warp; e < E; e += kRouteThreads / 32) {
+  for (int e = warp; e < E; e += blockDim.x / 32) {
     float acc[kRouteToks];
 #pragma unroll
     for (int k = 0; k < kRouteToks; ++k) acc[k] = 0.f;
@@ -267,7 +267,8 @@ cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, 
   if (T <= 1024) {
     const size_t smem = (size_t)H * 2 + (size_t)E * 4;
     if (smem > 48 * 1024) return cudaErrorInvalidValue;
-    (void)launch_pdl(moe_route_kernel<1>, dim3(T), dim3(kRouteThreads), smem, s, xx, ld_x, gw, T, H, E, top_k, n_group, topk_group, scaling,
+    // one token per CTA, 32 warps: each warp owns <= 2 experts, so the whole router row set costs two L2 round trips
+    (void)launch_pdl(moe_route_kernel<1>, dim3(T), dim3(E >= 64 ? 1024 : (E >= 32 ? 512 : kRouteThreads)), smem, s, xx, ld_x, gw, T, H, E, top_k, n_group, topk_group, scaling,
                                                        norm_topk ? 1 : 0, idx, wts);
   } else {
     constexpr int TOKS = 8;

@@ -122,4 +122,6 @@ cudaError_t advance_meta_launch(int* positions, int* context_lens, int* slots, c
   return cudaGetLastError();
 }
 
+void pdl_skip_next() { pdl_skip_next_flag() = true; }
+
 }  // namespace b200

@@ -192,9 +192,15 @@ def moe_route(x: torch.Tensor, gate_w: torch.Tensor, top_k: int, method: str = "
 
 
 # ------------------------------------------------------------------------------------------ K11
+def run_aside(fn):
+    """Backend hook: independent work that the CUDA backend forks onto a side stream runs inline here."""
+    fn()
+    return None
+
+
 def moe_experts(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, Wg: LinearWeight, Wu: LinearWeight,
                 Wd: LinearWeight, act: str = "silu", extra: Optional[torch.Tensor] = None,
-                residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+                residual: Optional[torch.Tensor] = None, join=None) -> torch.Tensor:
     """``y[t] = sum_k w[t,k] * down_e(act(gate_e x) * up_e x) (+ extra[t]) (+ residual[t])``.
     Intermediate activations are rounded to the activation dtype exactly where the kernels round."""
     T, H = x.shape

@@ -87,7 +87,7 @@ class ExpertParallelMoE:
         self.act = b200.ACT_IDS[act]
 
     def forward(self, x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor] = None,
-                out: Optional[torch.Tensor] = None, peer_tokens: Optional[int] = None) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, peer_tokens: Optional[int] = None, join=None) -> torch.Tensor:
         """``peer_tokens``: upper bound of the tokens *any* rank routes in this step (default: this rank's own ``T`` —
         ranks stepping in lockstep with equal batch shapes); only sizes the temporaries of the local expert GEMMs."""
         b, C = self.b, self.b.C
@@ -111,6 +111,8 @@ class ExpertParallelMoE:
         h = C.grouped_linear(x_perm, self.wg, self.wu, offs, max_rows, self.act, False, None, None, None, exp_rows)
         C.grouped_linear(h, self.wd, None, offs, max_rows, 0, True, row_dst, b.ret_flags_dev, st[W + 1:W + 2], exp_rows)
         # 4) wait for all my pairs to come home + weighted combine (+ residual): one kernel
+        if join is not None:
+            join.wait()  # ``residual`` (shared-expert branch) is produced on the side stream
         return C.ep_combine(b.base + b.off_flags + 128, st[W + 3:W + 4], st[-1:].data_ptr(), b.ret_y, w, residual, out)
 
     _ident = {}
