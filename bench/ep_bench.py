@@ -100,7 +100,7 @@ def main():
             idx, w = b200.moe_route(x0, gate, k); evs[1].record()
             C.ep_dispatch(x0, idx, ep.E_local, b.rank, b.cap, b.t_recv_x, b.t_recv_meta, b.t_recv_count, st[W + 4:W + 5], st[:W], st[W:W + 1],
                           st[W + 3:W + 4]); evs[2].record()
-            offs, total, x_perm, perm_src, row_dst = C.ep_regroup(b.base + b.off_recv_count, st[W + 2:W + 3].data_ptr(), st[-1:].data_ptr(),
+            offs, total, x_perm, row_dst = C.ep_regroup(b.base + b.off_recv_count, st[W + 2:W + 3].data_ptr(), st[-1:].data_ptr(),
                                                                   b.base + b.off_recv_meta, b.base + b.off_recv_x, W,
                                                                   b.cap, ep.E_local, b.H, b.dev, W * T * k, b.t_ret_y); evs[3].record()
             mr = min(W * T, x_perm.shape[0])

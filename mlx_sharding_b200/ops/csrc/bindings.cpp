@@ -541,7 +541,7 @@ std::vector<Tensor> ep_regroup(int64_t recv_words_ptr, int64_t counter_ptr, int6
   // rows_bound (>0): the caller's bound on the rows all sources can send this step; sizes the expert-ordered temporaries
   const int64_t R = rows_bound > 0 ? std::min<int64_t>(world * cap, rows_bound) : world * cap;
   Tensor offs = torch::empty({E_local + 1}, io), row_perm = torch::empty({world * cap}, io), total = torch::empty({1}, io);
-  Tensor perm_src = torch::empty({R, 2}, io), counts = torch::empty({world}, io);
+  Tensor counts = torch::empty({world}, io);
   Tensor x_perm = torch::empty({R, H}, torch::dtype(torch::kBFloat16).device(dev));
   // destination address of every expert-ordered row for the fused return (down-projection epilogue -> source's return buffer)
   Tensor row_dst = torch::empty({ret_y.empty() ? 0 : R}, torch::dtype(torch::kInt64).device(dev));
@@ -550,11 +550,11 @@ std::vector<Tensor> ep_regroup(int64_t recv_words_ptr, int64_t counter_ptr, int6
                                     reinterpret_cast<uint32_t*>(error_ptr), counts.data_ptr<int>(),
                                     reinterpret_cast<const void*>(recv_meta_ptr), reinterpret_cast<const void*>(recv_x_ptr), (int)world,
                                     (int)cap, (int)E_local, (int)H, offs.data_ptr<int>(), row_perm.data_ptr<int>(), total.data_ptr<int>(),
-                                    x_perm.data_ptr(), perm_src.data_ptr(), ret_y.empty() ? nullptr : ry.data(),
+                                    x_perm.data_ptr(), ret_y.empty() ? nullptr : ry.data(),
                                     ret_y.empty() ? nullptr : reinterpret_cast<unsigned long long*>(row_dst.data_ptr<int64_t>()),
                                     cur_stream()));
   ++g_launches;
-  return {offs, total, x_perm, perm_src, row_dst};
+  return {offs, total, x_perm, row_dst};
 }
 Tensor ep_combine(int64_t flag_ptr, const Tensor& expected, int64_t error_ptr, const Tensor& ret_y, const Tensor& wts,
                   const c10::optional<Tensor>& residual, const c10::optional<Tensor>& out_) {
@@ -570,20 +570,6 @@ Tensor ep_combine(int64_t flag_ptr, const Tensor& expected, int64_t error_ptr, c
                                     out.data_ptr(), out.stride(0), (int)T, (int)k, (int)H, cur_stream()));
   return out;
 }
-void ep_return(const Tensor& y_perm, const Tensor& perm_src, const Tensor& total_rows, std::vector<int64_t> ret_y,
-               std::vector<int64_t> ret_flag, Tensor done_counter) {
-  TORCH_CHECK(y_perm.scalar_type() == torch::kFloat32 && y_perm.is_contiguous());
-  const c10::cuda::CUDAGuard guard(y_perm.device());
-  auto a = to_u64(ret_y), b = to_u64(ret_flag);
-  LAUNCH_OK(b200::ep_return_launch(y_perm.data_ptr<float>(), perm_src.data_ptr(), total_rows.data_ptr<int>(), (int)y_perm.size(0),
-                                   (int)y_perm.size(1), (int)ret_y.size(), a.data(), b.data(),
-                                   reinterpret_cast<unsigned int*>(done_counter.data_ptr<int>()), cur_stream()));
-}
-void ep_wait_all(int64_t flag_ptr, int64_t counter_ptr, int64_t world, int64_t error_ptr) {
-  LAUNCH_OK(b200::ep_wait_all_launch(reinterpret_cast<const uint32_t*>(flag_ptr), reinterpret_cast<uint32_t*>(counter_ptr), (int)world,
-                                     reinterpret_cast<uint32_t*>(error_ptr), cur_stream()));
-}
-
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -630,8 +616,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("device"), py::arg("rows_bound") = 0, py::arg("ret_y") = std::vector<int64_t>());
   m.def("ep_combine", &ep_combine, py::arg("flag_ptr"), py::arg("expected"), py::arg("error_ptr"), py::arg("ret_y"), py::arg("wts"),
         py::arg("residual") = py::none(), py::arg("out") = py::none());
-  m.def("ep_return", &ep_return);
-  m.def("ep_wait_all", &ep_wait_all);
   m.def("init_scratch", &init_scratch);
   m.def("launch_count", []() { return g_launches; });
   m.def("pdl_skip_next", []() { b200::pdl_skip_next(); });

@@ -6,17 +6,19 @@
 //
 //   dispatch  : every (token, k) pair whose expert lives on rank r is written *directly* into r's receive
 //               region for this source (peer-mapped memory, 16 B stores), together with a (local expert,
-//               source pair) record; the last CTA publishes the per-destination row counts and bumps each
-//               destination's flag (release.sys).
-//   regroup   : the destination buckets what it received by local expert (offsets + gather) so the swap-AB
-//               grouped tcgen05 GEMMs run on contiguous rows.
-//   return    : each expert-output row is pushed straight back into the source rank's return buffer at the
-//               pair's original index; the last CTA bumps the sources' flags.  The source then finishes with
-//               the ordinary weighted combine (+ residual) over its own pairs.
+//               source pair) record; the last CTA publishes (row count << 32 | step sequence) to each destination
+//               as one 64-bit st.release.sys.
+//   regroup   : the destination polls the W words (ld.acquire.sys), buckets what it received by local expert
+//               (offsets + gather) so the swap-AB grouped tcgen05 GEMMs run on contiguous rows, and records for
+//               every row the address of its slot in the source rank's return buffer.
+//   return    : there is no return kernel — the grouped down-projection's epilogue (gemm_persistent.cu, GemmParams::
+//               row_dst / signal_peers) stores each fp32 output row straight to that address and the CTA completing the
+//               grid bumps every source's flag.
+//   combine   : the source waits (in-kernel) for all W arrivals, then does the weighted combine (+ residual).
 //
-// Counting flags + device-resident arrival counters make every step CUDA-graph replay safe.  Buffer reuse
-// is race-free by construction: a source only dispatches layer l+1 after it has combined layer l, which
-// requires every destination to have regrouped (consumed) layer l.
+// Sequence numbers / counting flags + device-resident expectations make every step CUDA-graph replay safe.  Buffer
+// reuse is race-free by construction: a source only dispatches layer l+1 after it has combined layer l, which
+// requires every destination to have regrouped (consumed) layer l and returned its rows.
 #include "kernels.h"
 #include "launch.h"
 #include "ptx.cuh"
@@ -140,8 +142,8 @@ ep_regroup_offsets_kernel(const unsigned long long* recv_words, uint32_t* local_
 // gather received rows into expert-contiguous order; remember where each permuted row came from
 __global__ void ep_regroup_gather_kernel(const __nv_bfloat16* __restrict__ recv_x, const int2* __restrict__ recv_meta,
                                          const int* __restrict__ recv_count, const int* __restrict__ row_perm, int world, int cap,
-                                         int H, __nv_bfloat16* __restrict__ x_perm, int2* __restrict__ perm_src /*(src rank, src pair)*/,
-                                         PeerTable ret_y, unsigned long long* __restrict__ row_dst /*fp32 return row of each permuted row*/) {
+                                         int H, __nv_bfloat16* __restrict__ x_perm, PeerTable ret_y,
+                                         unsigned long long* __restrict__ row_dst /*fp32 return row of each permuted row*/) {
   pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const int nvec = H / 8;
   const int s = blockIdx.y;
@@ -153,59 +155,14 @@ __global__ void ep_regroup_gather_kernel(const __nv_bfloat16* __restrict__ recv_
         __ldcv(reinterpret_cast<const uint4*>(recv_x + ((size_t)s * cap + j) * H) + v);
     if (v == 0) {
       const int pair = recv_meta[(size_t)s * cap + j].y;
-      perm_src[row] = make_int2(s, pair);
       // where the down-projection epilogue stores this row: the source rank's return buffer, at the pair's index
       if (row_dst != nullptr) row_dst[row] = ret_y.p[s] + (unsigned long long)pair * (unsigned long long)H * sizeof(float);
     }
   }
 }
 
-// ---------------------------------------------------------------------------------------------- return
-// one warp per permuted row: push the fp32 expert output back to its source rank
-__global__ void ep_return_kernel(const float* __restrict__ y_perm, const int2* __restrict__ perm_src, const int* __restrict__ total_rows,
-                                 int H, int world, PeerTable ret_y /*per src: [pairs][H] fp32*/, PeerTable ret_flag,
-                                 unsigned int* __restrict__ done_counter) {
-  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
-  const int warps_per_cta = blockDim.x >> 5;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = *total_rows;
-  const int nvec = H / 4;
-  for (int r = blockIdx.x * warps_per_cta + warp; r < n; r += gridDim.x * warps_per_cta) {
-    const int2 sp = perm_src[r];
-    const float4* src = reinterpret_cast<const float4*>(y_perm + (size_t)r * H);
-    float4* dst = reinterpret_cast<float4*>(ret_y.p[sp.x]) + (size_t)sp.y * nvec;
-    for (int v = lane; v < nvec; v += 32) dst[v] = src[v];
-  }
-  __threadfence_system();
-  __syncthreads();
-  __shared__ bool last;
-  if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) + 1u == gridDim.x);
-  __syncthreads();
-  if (last) {
-    __threadfence_system();
-    for (int r = threadIdx.x; r < world; r += blockDim.x) atomicAdd_system(reinterpret_cast<unsigned int*>(ret_flag.p[r]), 1u);
-    if (threadIdx.x == 0) *done_counter = 0u;
-  }
-}
-
-// source side: wait until every rank has returned its share
-__global__ void ep_wait_all_kernel(const uint32_t* flag, uint32_t* local_counter, int world, uint32_t* error_flag,
-                                   unsigned long long timeout_ns) {
-  pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
-  const uint32_t expected = atomicAdd(local_counter, (uint32_t)world) + (uint32_t)world;
-  unsigned long long t0;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
-  while (true) {
-    const uint32_t v = ld_acquire_sys(flag);
-    if ((int32_t)(v - expected) >= 0) break;
-    unsigned long long t1;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-    if (t1 - t0 > timeout_ns) { if (error_flag) atomicExch(error_flag, 1u); break; }
-    __nanosleep(32);
-  }
-  __threadfence_system();
-}
-
+// ---------------------------------------------------------------------------------------------- return + combine
+// (the return all-to-all itself is the epilogue of the grouped down-projection: gemm_persistent.cu, GemmParams::row_dst)
 // source side, fused: wait until every rank's down-projection has stored its share of my pairs into my return buffer,
 // then the weighted combine (+ residual).  `expected` was advanced by this step's dispatch kernel (stream order).
 __global__ void ep_combine_kernel(const uint32_t* flag, const uint32_t* __restrict__ expected_ptr, uint32_t* error_flag,
@@ -287,7 +244,7 @@ cudaError_t ep_dispatch_launch(const void* x, long long ld_x, const int* idx, in
 
 cudaError_t ep_regroup_launch(const unsigned long long* recv_words, uint32_t* local_counter, uint32_t* error_flag, int* recv_count,
                               const void* recv_meta, const void* recv_x, int world, int cap, int E_local, int H, int* expert_offsets,
-                              int* row_perm, int* total_rows, void* x_perm, void* perm_src, const unsigned long long* ret_y,
+                              int* row_perm, int* total_rows, void* x_perm, const unsigned long long* ret_y,
                               unsigned long long* row_dst, cudaStream_t s) {
   if (E_local > 256 || world > kMaxWorld) return cudaErrorInvalidValue;
   (void)launch_pdl(ep_regroup_offsets_kernel, dim3(1), dim3(1024), 0, s, recv_words, local_counter, error_flag, kTimeoutNs, recv_count,
@@ -297,20 +254,8 @@ cudaError_t ep_regroup_launch(const unsigned long long* recv_words, uint32_t* lo
   if (e != cudaSuccess) return e;
   dim3 grid(64, world);
   (void)launch_pdl(ep_regroup_gather_kernel, dim3(grid), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(recv_x), static_cast<const int2*>(recv_meta), static_cast<const int*>(recv_count),
-                                                row_perm, world, cap, H, static_cast<__nv_bfloat16*>(x_perm), static_cast<int2*>(perm_src),
+                                                row_perm, world, cap, H, static_cast<__nv_bfloat16*>(x_perm),
                                                 ret_y != nullptr ? make_table(ret_y, world) : PeerTable{}, row_dst);
-  return cudaGetLastError();
-}
-
-cudaError_t ep_return_launch(const float* y_perm, const void* perm_src, const int* total_rows, int max_rows, int H, int world,
-                             const unsigned long long* ret_y, const unsigned long long* ret_flag, unsigned int* done_counter,
-                             cudaStream_t s) {
-  if (H % 4) return cudaErrorInvalidValue;
-  int grid = (max_rows + 7) / 8;
-  if (grid < 1) grid = 1;
-  if (grid > 592) grid = 592;
-  (void)launch_pdl(ep_return_kernel, dim3(grid), dim3(256), 0, s, y_perm, static_cast<const int2*>(perm_src), total_rows, H, world, make_table(ret_y, world),
-                                        make_table(ret_flag, world), done_counter);
   return cudaGetLastError();
 }
 
@@ -322,11 +267,6 @@ cudaError_t ep_combine_launch(const uint32_t* flag, const uint32_t* expected_ptr
   const long long total = (long long)T * (H / 8);
   (void)launch_pdl(ep_combine_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, flag, expected_ptr, error_flag, kTimeoutNs,
                    ret_y, wts, static_cast<const __nv_bfloat16*>(residual), ld_res, static_cast<__nv_bfloat16*>(out), ld_out, T, top_k, H);
-  return cudaGetLastError();
-}
-
-cudaError_t ep_wait_all_launch(const uint32_t* flag, uint32_t* local_counter, int world, uint32_t* error_flag, cudaStream_t s) {
-  (void)launch_pdl(ep_wait_all_kernel, dim3(1), dim3(1), 0, s, flag, local_counter, world, error_flag, kTimeoutNs);
   return cudaGetLastError();
 }
 

@@ -93,14 +93,10 @@ cudaError_t ep_dispatch_launch(const void* x, long long ld_x, const int* idx, in
                                unsigned int* done_counter, uint32_t* ret_expected, cudaStream_t s);
 cudaError_t ep_regroup_launch(const unsigned long long* recv_words, uint32_t* local_counter, uint32_t* error_flag, int* recv_count,
                               const void* recv_meta, const void* recv_x, int world, int cap, int E_local, int H, int* expert_offsets,
-                              int* row_perm, int* total_rows, void* x_perm, void* perm_src, const unsigned long long* ret_y,
+                              int* row_perm, int* total_rows, void* x_perm, const unsigned long long* ret_y,
                               unsigned long long* row_dst, cudaStream_t s);
 cudaError_t ep_combine_launch(const uint32_t* flag, const uint32_t* expected_ptr, uint32_t* error_flag, const float* ret_y,
                               const float* wts, const void* residual, long long ld_res, void* out, long long ld_out, int T, int top_k,
                               int H, cudaStream_t s);
-cudaError_t ep_return_launch(const float* y_perm, const void* perm_src, const int* total_rows, int max_rows, int H, int world,
-                             const unsigned long long* ret_y, const unsigned long long* ret_flag, unsigned int* done_counter,
-                             cudaStream_t s);
-cudaError_t ep_wait_all_launch(const uint32_t* flag, uint32_t* local_counter, int world, uint32_t* error_flag, cudaStream_t s);
 
 }  // namespace b200

@@ -6,8 +6,8 @@ The reference executes all routed experts of a layer on the stage that owns the 
 domain: rank ``r`` keeps experts ``[r*E/world, (r+1)*E/world)`` (1/world of the MoE weights — the dominant
 HBM stream of a decode step) and every rank routes *its own* tokens.  Token exchange is done by the kernels
 in ``ops/csrc/ep.cu`` — dispatch rows are written straight into the owner's receive region, expert outputs
-are pushed straight back into the source's return buffer, flags use release/acquire at system scope; there
-is no NCCL call and no host involvement on the path.
+are stored straight into the source's return buffer by the down-projection GEMM epilogue, publication words /
+flags use release/acquire at system scope; there is no NCCL call and no host involvement on the path.
 
 ``forward(x, idx, w, residual)`` == ``ops.moe_experts`` on the un-sharded weights (verified in
 ``tests/test_multigpu.py``).
@@ -55,7 +55,6 @@ class EPBuffers:
         self.t_recv_x = [p + self.off_recv_x for p in self.peer]
         self.t_recv_meta = [p + self.off_recv_meta for p in self.peer]
         self.t_recv_count = [p + self.off_recv_count for p in self.peer]
-        self.t_recv_flag = [p + self.off_flags for p in self.peer]
         self.t_ret_y = [p + self.off_ret_y for p in self.peer]
         self.t_ret_flag = [p + self.off_flags + 128 for p in self.peer]
         # device-resident local state: [send_counts(world) | dispatch done ctr | down-GEMM tile ctr | regroup step seq seen |
@@ -101,7 +100,7 @@ class ExpertParallelMoE:
         C.ep_dispatch(x, idx, self.E_local, b.rank, b.cap, b.t_recv_x, b.t_recv_meta, b.t_recv_count, st[W + 4:W + 5],
                       st[:W], st[W:W + 1], st[W + 3:W + 4])
         # 2) wait for every source, bucket what I received by local expert; row_dst[r] = where row r's output must go
-        offs, total, x_perm, perm_src, row_dst = C.ep_regroup(
+        offs, total, x_perm, row_dst = C.ep_regroup(
             b.base + b.off_recv_count, st[W + 2:W + 3].data_ptr(), st[-1:].data_ptr(),
             b.base + b.off_recv_meta, b.base + b.off_recv_x, W, b.cap, self.E_local, b.H, b.dev, min(W * b.cap, W * Tmax * k), b.t_ret_y)
         # 3) my experts: grouped swap-AB tcgen05 GEMMs on the received rows; the down-projection epilogue stores every output
@@ -114,15 +113,6 @@ class ExpertParallelMoE:
         if join is not None:
             join.wait()  # ``residual`` (shared-expert branch) is produced on the side stream
         return C.ep_combine(b.base + b.off_flags + 128, st[W + 3:W + 4], st[-1:].data_ptr(), b.ret_y, w, residual, out)
-
-    _ident = {}
-
-    @classmethod
-    def _identity(cls, n, device):
-        key = (n, str(device))
-        if key not in cls._ident:
-            cls._ident[key] = torch.arange(n, dtype=torch.int32, device=device)
-        return cls._ident[key]
 
 
 def enable_expert_parallel(model, max_tokens: int = 256, group=None) -> EPBuffers:
