@@ -540,17 +540,18 @@ def main(argv=None):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
         # native chain (torchrun): rank 0 serves HTTP + the first stage, every other rank is a stage worker.
-        # Layer ranges default to an even split when neither --start-layer/--end-layer nor the config give them.
+        # Layer ranges default to a cost-balanced split when neither --start-layer/--end-layer nor the config give them.
         from ..parallel.transport import init_distributed
 
         rank, _ = init_distributed(device=args.device)
         if args.start_layer is None and args.end_layer is None and args.model is not None:
-            from ..config import ModelConfig, ShardSpec
+            from ..config import ModelConfig
+            from ..parallel.partition import balanced_split
             from ..utils.checkpoint import get_model_path
 
             cfg = ModelConfig.from_path(get_model_path(args.model))
             if cfg.start_layer is None:
-                spec = ShardSpec.even_split(cfg.num_hidden_layers, world)[rank]
+                spec = balanced_split(cfg, world)[rank]  # cost-balanced whole layers (LM head / dense layers weighted)
                 args.start_layer, args.end_layer = spec.start_layer, spec.end_layer
         if rank != 0:
             from .shard_server import serve_chain

@@ -40,7 +40,8 @@ def serve(model_path: str, start_layer=None, end_layer=None, port: int = 0, devi
 def serve_chain(model_path: str, start_layer=None, end_layer=None, device=None, dtype=None, num_pages: int = 2048,
                 page_size: int = 64):
     """Native mode: this process is rank r > 0 of the chain pipeline (see parallel/pipeline.py)."""
-    from ..config import ModelConfig, ShardSpec
+    from ..config import ModelConfig
+    from ..parallel.partition import balanced_split
     from ..parallel.pipeline import StageExecutor, worker_loop
     from ..parallel.transport import TorchDistTransport, init_distributed
     from ..utils.checkpoint import get_model_path
@@ -50,7 +51,7 @@ def serve_chain(model_path: str, start_layer=None, end_layer=None, device=None, 
     if start_layer is None and end_layer is None:
         cfg = ModelConfig.from_path(get_model_path(model_path))
         if cfg.start_layer is None:
-            spec = ShardSpec.even_split(cfg.num_hidden_layers, world)[rank]
+            spec = balanced_split(cfg, world)[rank]  # cost-balanced whole layers (LM head / dense layers weighted)
             start_layer, end_layer = spec.start_layer, spec.end_layer
     dev = device or (f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else "cpu")
     model = load_model(model_path, start_layer, end_layer, dtype=dtype, device=dev)

@@ -15,7 +15,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, C, prompts, n_new, q):
+def _worker(rank, world, port, C, prompts, n_new, q, half=False):
     import torch.distributed as dist
 
     from mlx_sharding_b200.config import ModelConfig, ShardSpec
@@ -30,7 +30,14 @@ def _worker(rank, world, port, C, prompts, n_new, q):
     torch.set_num_threads(1)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     cfg = ModelConfig.from_dict(C)
-    spec = ShardSpec.even_split(cfg.num_hidden_layers, world)[rank]
+    if half:
+        # every interior stage boundary between the attention and the MLP block of a layer (parallel/partition.py)
+        L = cfg.num_hidden_layers
+        cuts = [0] + [2 * (L * r // world) + 1 for r in range(1, world)] + [2 * L]
+        spec = ShardSpec(cuts[rank] // 2, (cuts[rank + 1] + 1) // 2, L, skip_first_attn=bool(cuts[rank] % 2),
+                         defer_last_mlp=bool(cuts[rank + 1] % 2))
+    else:
+        spec = ShardSpec.even_split(cfg.num_hidden_layers, world)[rank]
     sd = dict(random_state_dict(cfg, spec, dtype=torch.float32))
     model = build_stage(cfg, spec, torch.float32).load_state(sd)
     stage = StageExecutor(model, num_pages=32, page_size=16)
@@ -49,15 +56,15 @@ def _worker(rank, world, port, C, prompts, n_new, q):
 
 
 @pytest.mark.timeout(180)
-@pytest.mark.parametrize("world", [2, 3])
-def test_gloo_chain_matches_single_process(world):
+@pytest.mark.parametrize("world,half", [(2, False), (3, False), (3, True)])
+def test_gloo_chain_matches_single_process(world, half):
     C = dict(TINY_LLAMA, num_hidden_layers=2 if world == 2 else 3)
     prompts = [[5, 6, 7, 8], [100, 50, 3], [9] * 6]
     n_new = 5
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, C, prompts, n_new, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, C, prompts, n_new, q, half)) for r in range(world)]
     for p in procs:
         p.start()
     got = q.get(timeout=150)
