@@ -103,11 +103,12 @@ def main(argv=None):
 
             return serve_chain(args.model, args.start_layer, args.end_layer, args.device)
         if args.start_layer is None and args.end_layer is None:
-            from mlx_sharding_b200.config import ModelConfig, ShardSpec
+            from mlx_sharding_b200.config import ModelConfig
+            from mlx_sharding_b200.parallel.partition import balanced_split
 
             cfg = ModelConfig.from_path(get_model_path(args.model))
             if cfg.start_layer is None:
-                spec = ShardSpec.even_split(cfg.num_hidden_layers, world)[0]
+                spec = balanced_split(cfg, world)[0]  # same rule as server/shard_server.py::serve_chain on the other ranks
                 args.start_layer, args.end_layer = spec.start_layer, spec.end_layer
     tokenizer = load_tokenizer(get_model_path(args.model))
     model = load_model(args.model, args.start_layer, args.end_layer, device=args.device)
