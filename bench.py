@@ -363,11 +363,13 @@ def run_ep(args, world, rank, local, dev):
     chunk_seqs = max(1, 2048 // S)                      # prefill chunk: <= 2048 tokens per rank per step
     ep_tokens = max(B, chunk_seqs * S)
     t0 = time.time()
-    model = random_model(cfgd, dtype=torch.bfloat16, device=dev, backend="b200", seed=1)   # same weights on every rank
+    # same seed on every rank; of every routed-expert bank only this rank's E/world slice is kept as it is generated
+    model = random_model(cfgd, dtype=torch.bfloat16, device=dev, backend="b200", seed=1, expert_shard=(rank, world))
     bufs = enable_expert_parallel(model, max_tokens=ep_tokens)
     torch.cuda.synchronize()
     log(f"all {cfg.num_hidden_layers} layers, experts {rank * cfg.n_routed_experts // world}..{(rank + 1) * cfg.n_routed_experts // world - 1} "
-        f"of every MoE layer, weights {model.weight_bytes() / 1e9:.2f} GB (+ expert shards) built in {time.time() - t0:.1f}s")
+        f"of every MoE layer, replicated weights {model.weight_bytes() / 1e9:.2f} GB + expert shards "
+        f"{sum(e.wg.numel() + e.wu.numel() + e.wd.numel() for e in model.ep_layers.values()) * 2 / 1e9:.2f} GB built in {time.time() - t0:.1f}s")
     total_steps = args.warmup + args.steps
     e2e_steps = 0 if args.no_e2e else (total_steps + 2)
     max_len = S + total_steps + e2e_steps + 8

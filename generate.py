@@ -88,12 +88,17 @@ def main(argv=None):
     parser.add_argument("--end_layer", type=int, default=None, help="End layer index")
     parser.add_argument("--device", type=str, default=None)
     parser.add_argument("--no_chat_template", action="store_true", help="feed the raw prompt")
+    parser.add_argument("--expert_parallel", action="store_true",
+                        help="under torchrun, MoE models: every rank runs all layers (attention replicated) and holds E/world routed "
+                             "experts of every MoE layer, exchanged with the fused all-to-all (parallel/ep.py) instead of a layer pipeline")
     args = parser.parse_args(argv)
 
     from mlx_sharding_b200.utils.checkpoint import get_model_path
     from mlx_sharding_b200.utils.loader import load_model
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and args.expert_parallel:
+        return main_expert_parallel(args)
     if world > 1:
         from mlx_sharding_b200.parallel.transport import init_distributed
 
@@ -121,6 +126,45 @@ def main(argv=None):
         print(seg, end="", flush=True)
     if hasattr(engine.pipe, "shutdown"):
         engine.pipe.shutdown()
+
+
+def main_expert_parallel(args):
+    """Expert-parallel generation (BASELINE config 5 as a user path): all ranks decode the *same* request in lockstep — the
+    per-rank work is the replicated attention plus 1/world of every expert bank; rank 0 prints."""
+    import torch
+    import torch.distributed as dist
+
+    from mlx_sharding_b200.parallel.ep import enable_expert_parallel
+    from mlx_sharding_b200.parallel.pipeline import LocalPipeline, StageExecutor
+    from mlx_sharding_b200.utils.checkpoint import get_model_path
+    from mlx_sharding_b200.utils.loader import load_model
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    tokenizer = load_tokenizer(get_model_path(args.model))
+    model = load_model(args.model, device=str(dev), expert_shard=(rank, world))
+    max_prefill = 2048
+    enable_expert_parallel(model, max_tokens=max_prefill)
+    num_pages, page_size = 1024, 64
+    engine = LLMEngine(LocalPipeline([StageExecutor(model, num_pages, page_size)]), num_pages, page_size, num_groups=1,
+                       max_prefill_tokens=max_prefill)
+    prompt = args.prompt
+    if not args.no_chat_template and getattr(tokenizer, "chat_template", None):
+        prompt = tokenizer.apply_chat_template([{"role": "user", "content": args.prompt}], tokenize=False,
+                                               add_generation_prompt=True)
+    out = sys.stdout if rank == 0 else open(os.devnull, "w")
+    stdout, sys.stdout = sys.stdout, out   # stream_generate prints its statistics: rank 0 only
+    try:
+        for seg in stream_generate(engine, tokenizer, prompt, args.max_tokens):
+            print(seg, end="", flush=True)
+    finally:
+        sys.stdout = stdout
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

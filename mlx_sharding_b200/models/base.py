@@ -102,6 +102,8 @@ class StageModel:
         # kernel of the last local layer stores straight into that (peer-mapped) buffer and bumps the flag
         self.boundary = None
         self.boundary_fused = False
+        # (rank, world) when only this rank's slice of every routed-expert bank was loaded (expert parallelism)
+        self.expert_shard = None
 
     # reference-compatible surface ------------------------------------------------------------
     @property

@@ -46,11 +46,15 @@ class DeepseekV2Stage(StageModel):
             m = _EXPERT_RE.match(k)
             if m:
                 groups.setdefault((m.group(1), m.group(3), m.group(4)), {})[int(m.group(2))] = sd.pop(k)
+        n = self.cfg.n_routed_experts
+        want = list(range(n))
+        if self.expert_shard is not None:  # expert parallelism: only this rank's experts were read (utils/checkpoint.py)
+            r, world = self.expert_shard
+            want = list(range(r * n // world, (r + 1) * n // world))
         for (prefix, proj, kind), d in groups.items():
-            n = self.cfg.n_routed_experts
-            if sorted(d) != list(range(n)):
-                raise ValueError(f"{prefix}.experts.*.{proj}.{kind}: expected {n} experts, found {len(d)}")
-            sd[f"{prefix}.switch_mlp.{proj}.{kind}"] = torch.stack([d[e] for e in range(n)])
+            if sorted(d) != want:
+                raise ValueError(f"{prefix}.experts.*.{proj}.{kind}: expected experts {want[0]}..{want[-1]}, found {len(d)}")
+            sd[f"{prefix}.switch_mlp.{proj}.{kind}"] = torch.stack([d[e] for e in want])
         return sd
 
     def _load_layer(self, sd, i, attn=True, mlp=True) -> dict:

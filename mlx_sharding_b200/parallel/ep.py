@@ -118,15 +118,20 @@ class ExpertParallelMoE:
 def enable_expert_parallel(model, max_tokens: int = 256, group=None) -> EPBuffers:
     """Switch a DeepSeek-V2 stage model (every rank holding the *same* layers, data-parallel over tokens) to
     expert-parallel execution: each MoE layer keeps only its ``E / world`` local experts and routes tokens through the
-    fused all-to-all.  The full expert banks are dropped from this rank afterwards (1/world of the MoE memory)."""
+    fused all-to-all.  Models loaded with ``expert_shard=(rank, world)`` (``utils/loader.py``) already hold just their slice;
+    otherwise the full banks are sliced here and dropped from this rank afterwards (1/world of the MoE memory)."""
     cfg = model.cfg
     bufs = EPBuffers(cfg.hidden_size, max_tokens, cfg.num_experts_per_tok, group=group)
+    local = getattr(model, "expert_shard", None) is not None
+    if local:
+        assert tuple(model.expert_shard) == (bufs.rank, bufs.world), "model was loaded for a different expert shard"
     model.ep_layers = {}
     for i, w in model.layer_weights.items():
         if "router" not in w:
             continue
-        model.ep_layers[i] = ExpertParallelMoE(bufs, w["e_gate"], w["e_up"], w["e_down"], cfg.n_routed_experts)
+        model.ep_layers[i] = ExpertParallelMoE(bufs, w["e_gate"], w["e_up"], w["e_down"], cfg.n_routed_experts,
+                                               weights_are_local=local)
         for k in ("e_gate", "e_up", "e_down"):
-            w[k] = None  # free the un-sharded bank
+            w[k] = None  # the (sliced) bank lives on in the ExpertParallelMoE
     torch.cuda.empty_cache()
     return bufs

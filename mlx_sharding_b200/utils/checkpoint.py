@@ -71,6 +71,30 @@ def key_in_shard(key: str, spec: ShardSpec, tied_embeddings: bool = False, model
     return False
 
 
+_SWITCH_RE = re.compile(r"\.mlp\.switch_mlp\.(gate_proj|up_proj|down_proj)\.")
+_EXPERT_ID_RE = re.compile(r"\.mlp\.experts\.(\d+)\.")
+
+
+def shard_expert_tensors(items, num_experts: int, expert_shard: Optional[Tuple[int, int]]):
+    """Expert parallelism at load time (parallel/ep.py): of every routed-expert bank keep only the experts
+    ``[r * E / world, (r + 1) * E / world)`` of rank ``r`` — stacked ``switch_mlp.*`` tensors are sliced as they stream by
+    (so a rank never holds more than one full bank at a time), HF-style per-expert tensors of other ranks are dropped."""
+    if expert_shard is None:
+        yield from items
+        return
+    r, world = expert_shard
+    assert num_experts % world == 0, "n_routed_experts must be divisible by the expert-parallel world size"
+    lo, hi = r * num_experts // world, (r + 1) * num_experts // world
+    for k, v in items:
+        if _SWITCH_RE.search(k):
+            yield k, v[lo:hi].clone() if v.is_cuda else v[lo:hi].contiguous()
+            continue
+        m = _EXPERT_ID_RE.search(k)
+        if m is not None and not (lo <= int(m.group(1)) < hi):
+            continue
+        yield k, v
+
+
 def iter_safetensors(model_path: str, keep: Optional[Callable[[str], bool]] = None,
                      device: str = "cpu") -> Iterator[Tuple[str, torch.Tensor]]:
     """Yield ``(key, tensor)`` for every tensor of every ``*.safetensors`` under ``model_path`` that

@@ -15,15 +15,17 @@ import torch
 
 from ..config import ModelConfig
 from ..models import build_stage
-from .checkpoint import get_model_path, key_in_shard, iter_safetensors, random_state_dict
+from .checkpoint import get_model_path, key_in_shard, iter_safetensors, random_state_dict, shard_expert_tensors
 
 log = logging.getLogger(__name__)
 
 
 def load_model(path_or_hf_repo: str, start_layer: Optional[int] = None, end_layer: Optional[int] = None,
                dtype: Optional[torch.dtype] = None, device: Optional[str] = None, backend: Optional[str] = None,
-               spec=None):
-    """``spec`` (a ``ShardSpec``, e.g. from ``parallel.partition.balanced_split``) overrides the layer bounds."""
+               spec=None, expert_shard=None):
+    """``spec`` (a ``ShardSpec``, e.g. from ``parallel.partition.balanced_split``) overrides the layer bounds.
+    ``expert_shard=(rank, world)`` keeps only this rank's ``E / world`` routed experts of every MoE layer (expert
+    parallelism, ``parallel/ep.py::enable_expert_parallel``)."""
     model_path = get_model_path(path_or_hf_repo)
     cfg = ModelConfig.from_path(model_path)
     spec = spec or cfg.shard(start_layer, end_layer)
@@ -31,9 +33,11 @@ def load_model(path_or_hf_repo: str, start_layer: Optional[int] = None, end_laye
     if dtype is None:
         dtype = torch.bfloat16 if torch.device(device).type == "cuda" else torch.float32
     model = build_stage(cfg, spec, dtype, device, backend)
+    model.expert_shard = expert_shard
     tied = cfg.tie_word_embeddings
     # HF-style per-expert keys also belong to the layer range, key_in_shard handles them by prefix
-    sd = dict(iter_safetensors(model_path, lambda k: key_in_shard(k, spec, tied, cfg.model_type)))
+    sd = dict(shard_expert_tensors(iter_safetensors(model_path, lambda k: key_in_shard(k, spec, tied, cfg.model_type)),
+                                   cfg.n_routed_experts or 0, expert_shard))
     if not sd:
         raise ValueError(f"no tensors for layers [{spec.start_layer}, {spec.end_layer}) in {model_path}")
     model.load_state(sd)
@@ -44,7 +48,7 @@ def load_model(path_or_hf_repo: str, start_layer: Optional[int] = None, end_laye
 
 def random_model(config: dict, start_layer: Optional[int] = None, end_layer: Optional[int] = None,
                  dtype=torch.bfloat16, device="cpu", backend: Optional[str] = None, seed: int = 0,
-                 quantization: Optional[dict] = None, spec=None):
+                 quantization: Optional[dict] = None, spec=None, expert_shard=None):
     """Random-init stage directly on ``device`` (no disk round trip) — used by the benchmarks on the
     offline GPU box; key layout and shapes are identical to an mlx-community checkpoint."""
     config = dict(config)
@@ -53,6 +57,8 @@ def random_model(config: dict, start_layer: Optional[int] = None, end_layer: Opt
     cfg = ModelConfig.from_dict(config)
     spec = spec or cfg.shard(start_layer, end_layer)
     model = build_stage(cfg, spec, dtype, device, backend)
-    sd = dict(random_state_dict(cfg, spec, dtype=dtype, device=device, seed=seed, quantization=quantization))
+    model.expert_shard = expert_shard
+    sd = dict(shard_expert_tensors(random_state_dict(cfg, spec, dtype=dtype, device=device, seed=seed, quantization=quantization),
+                                   cfg.n_routed_experts or 0, expert_shard))
     model.load_state(sd)
     return model

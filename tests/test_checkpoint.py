@@ -127,3 +127,29 @@ def test_tied_llama_last_stage_gets_embeddings():
     full = build_stage(cfg, cfg.shard(), torch.float32).load_state(sd)
     a, b = run_sequence(parts, [1, 2, 3], 1), run_sequence([full], [1, 2, 3], 1)
     assert torch.allclose(a[-1], b[-1], atol=1e-5)
+
+
+@pytest.mark.parametrize("stacked", [True, False])
+def test_expert_sharded_load(tmp_path, stacked):
+    """``load_model(expert_shard=(r, world))`` keeps rank r's slice of every routed-expert bank (expert parallelism) — for
+    stacked ``switch_mlp.*`` banks and for HF-style per-expert tensors."""
+    import torch
+
+    from helpers import TINY_DSV2
+    from mlx_sharding_b200.utils.checkpoint import write_synthetic_checkpoint
+    from mlx_sharding_b200.utils.loader import load_model
+
+    path = write_synthetic_checkpoint(str(tmp_path / "ckpt"), TINY_DSV2, dtype=torch.float32, stacked_experts=stacked)
+    full = load_model(path, dtype=torch.float32, device="cpu")
+    E = TINY_DSV2["n_routed_experts"]
+    for r in range(2):
+        part = load_model(path, dtype=torch.float32, device="cpu", expert_shard=(r, 2))
+        assert part.expert_shard == (r, 2)
+        lo, hi = r * E // 2, (r + 1) * E // 2
+        for i, w in part.layer_weights.items():
+            if "router" not in w:
+                continue
+            for k in ("e_gate", "e_up", "e_down"):
+                assert torch.equal(w[k].weight, full.layer_weights[i][k].weight[lo:hi])
+            assert torch.equal(w["router"], full.layer_weights[i]["router"])       # router stays whole (routes over all E)
+            assert torch.equal(w["s_down"].weight, full.layer_weights[i]["s_down"].weight)

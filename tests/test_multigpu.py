@@ -34,3 +34,27 @@ def test_expert_parallel_whole_model():
     """Data-parallel attention + expert-parallel MoE for every layer, graph-captured decode loop (bench.py --parallelism ep)."""
     out = _torchrun("ep_model_parity.py", [], port=29576)
     assert "EP_MODEL_OK" in out, out[-3000:]
+
+
+def test_generate_cli_expert_parallel(tmp_path):
+    """``torchrun generate.py --expert_parallel`` (experts sharded at load, fused all-to-all) prints the same greedy text as a
+    single-GPU run of the whole model."""
+    import torch
+
+    sys.path.insert(0, HERE)
+    from helpers import GPU_DSV2
+    from mlx_sharding_b200.utils.checkpoint import write_synthetic_checkpoint
+
+    ckpt = write_synthetic_checkpoint(str(tmp_path / "dsv2"), GPU_DSV2, dtype=torch.bfloat16, seed=11)
+    root = os.path.dirname(HERE)
+    common = ["--model", ckpt, "--prompt", "expert parallel", "--max_tokens", "12", "--no_chat_template"]
+    one = subprocess.run([sys.executable, os.path.join(root, "generate.py"), *common], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES="0"))
+    assert one.returncode == 0, one.stderr[-2000:]
+    ep = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                         "--master-port", "29577", os.path.join(root, "generate.py"), *common, "--expert_parallel"],
+                        capture_output=True, text=True, timeout=420)
+    assert ep.returncode == 0, (ep.stdout + ep.stderr)[-3000:]
+    text = lambda out: out.split("==========")[0]
+    assert "Generation:" in ep.stdout
+    assert text(one.stdout) == text(ep.stdout) and len(text(one.stdout)) > 0
