@@ -7,9 +7,14 @@
 
 * model   : DeepSeek-Coder-V2-Lite-Instruct architecture (27 layers, 64 routed experts top-6, MLA), bf16,
             random-init weights in the mlx-community layout, synthetic prompts (the box is offline).
-* pipeline: N stages (cost-balanced layer ranges), N micro-batch groups of ``--batch`` sequences in flight
-            (weak scaling: per-GPU work is fixed, global batch = N x batch).
-* step    : one decode step of every group = ``N * batch`` new tokens.  ``value`` = whole-job tokens/sec,
+* sharding: on N > 1 GPUs two shardings of the model are measured in the same run (``--parallelism auto``) and the faster
+            one is the headline, the other is reported under ``also_measured``:
+            pp — N pipeline stages (cost-balanced layer / half-layer ranges), N micro-batch groups of ``--batch`` sequences in
+                 flight, fused P2P stage hand-off (the reference's layer-range sharding, BASELINE config 3);
+            ep — every rank decodes its own ``--batch`` sequences through all layers (attention replicated) and holds E/N routed
+                 experts of every MoE layer, exchanged with the fused all-to-all over NVLink peer memory (BASELINE config 5).
+            Both are weak scaling: per-GPU work is fixed, global batch = N x batch.
+* step    : one decode step of every sequence in flight = ``N * batch`` new tokens.  ``value`` = whole-job tokens/sec,
             device-timed with CUDA events after ``--warmup`` steps, max over ranks.
 * e2e     : the same metric through the public serving API (``LLMEngine.submit/step``): every step copies
             the step's token ids + metadata host->device from pinned memory and reads the sampled tokens
