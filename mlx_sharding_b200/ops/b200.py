@@ -64,7 +64,7 @@ def _bf16(t: torch.Tensor) -> torch.Tensor:
 
 def _dense(W: LinearWeight) -> torch.Tensor:
     """bf16 ``[.., N, K]`` view of a weight.  Only used for bf16 checkpoints and for quantised layouts the in-kernel
-    dequant GEMM does not cover (2-bit, fp16 scales, odd group sizes; expert-parallel banks): those are expanded once at
+    dequant GEMM does not cover (2-bit, odd group sizes; expert-parallel banks): those are expanded once at
     first use.  int4 / int8 group-64/128 weights take :func:`_qpack` and stay packed in HBM."""
     if W.is_quantized:
         if W.weight is None:
