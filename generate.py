@@ -136,17 +136,14 @@ def main_expert_parallel(args):
 
     from mlx_sharding_b200.parallel.ep import enable_expert_parallel
     from mlx_sharding_b200.parallel.pipeline import LocalPipeline, StageExecutor
+    from mlx_sharding_b200.parallel.transport import init_distributed
     from mlx_sharding_b200.utils.checkpoint import get_model_path
     from mlx_sharding_b200.utils.loader import load_model
 
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    rank, world = init_distributed(device=args.device)      # NCCL + one GPU per rank, or gloo on CPU
+    dev = f"cuda:{torch.cuda.current_device()}" if dist.get_backend() == "nccl" else "cpu"
     tokenizer = load_tokenizer(get_model_path(args.model))
-    model = load_model(args.model, device=str(dev), expert_shard=(rank, world))
+    model = load_model(args.model, device=dev, expert_shard=(rank, world))
     max_prefill = 2048
     enable_expert_parallel(model, max_tokens=max_prefill)
     num_pages, page_size = 1024, 64

@@ -127,6 +127,13 @@ class LinearWeight:
                                 group_size=self.group_size, bits=self.bits)
         return LinearWeight(weight=self.weight[sl], bias=None if self.bias is None else self.bias[start:end])
 
+    def slice_experts(self, lo: int, hi: int) -> "LinearWeight":
+        """Experts ``[lo, hi)`` of a stacked ``[E, out, in]`` bank (expert parallelism)."""
+        if self.is_quantized:
+            return LinearWeight(wq=self.wq[lo:hi].contiguous(), scales=self.scales[lo:hi].contiguous(),
+                                biases=self.biases[lo:hi].contiguous(), group_size=self.group_size, bits=self.bits)
+        return LinearWeight(weight=self.weight[lo:hi].contiguous())
+
     def select_expert(self, e: int) -> "LinearWeight":
         if self.is_quantized:
             return LinearWeight(wq=self.wq[e], scales=self.scales[e], biases=self.biases[e],

@@ -115,23 +115,90 @@ class ExpertParallelMoE:
         return C.ep_combine(b.base + b.off_flags + 128, st[W + 3:W + 4], st[-1:].data_ptr(), b.ret_y, w, residual, out)
 
 
-def enable_expert_parallel(model, max_tokens: int = 256, group=None) -> EPBuffers:
+class ExpertParallelMoERef:
+    """Backend-agnostic expert parallelism: the same exchange expressed with ``torch.distributed.all_to_all_single`` (gloo on
+    CPU, NCCL on GPU) and the ``ops.reference`` expert math.  It is the CPU path of ``enable_expert_parallel`` (tests, plumbing
+    without a GPU) and the NCCL baseline the fused kernels of ``ops/csrc/ep.cu`` are compared against.
+
+    Same contract as :class:`ExpertParallelMoE`: ``forward(x, idx, w, residual)`` == ``ops.moe_experts`` on the un-sharded
+    weights; every rank must call it the same number of times (token counts may differ per rank)."""
+
+    def __init__(self, Wg: LinearWeight, Wu: LinearWeight, Wd: LinearWeight, num_experts: int, act: str = "silu",
+                 weights_are_local: bool = False, group=None):
+        from ..ops import reference as R
+
+        self.R, self.group, self.act = R, group, act
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        assert num_experts % self.world == 0
+        self.E, self.E_local = num_experts, num_experts // self.world
+        lo, hi = self.rank * self.E_local, (self.rank + 1) * self.E_local
+        pick = (lambda W: W) if weights_are_local else (lambda W: W.slice_experts(lo, hi))
+        self.wg, self.wu, self.wd = pick(Wg), pick(Wu), pick(Wd)
+
+    def _a2a(self, send: torch.Tensor, send_counts: List[int], recv_counts: List[int]) -> torch.Tensor:
+        recv = send.new_empty((sum(recv_counts),) + tuple(send.shape[1:]))
+        dist.all_to_all_single(recv, send.contiguous(), recv_counts, send_counts, group=self.group)
+        return recv
+
+    def forward(self, x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None, peer_tokens: Optional[int] = None, join=None) -> torch.Tensor:
+        T, k = idx.shape
+        W, R = self.world, self.R
+        flat = idx.reshape(-1).long()
+        dst = flat // self.E_local
+        order = torch.argsort(dst, stable=True)                       # pairs grouped by destination rank
+        send_counts = torch.bincount(dst, minlength=W)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        sc, rc = send_counts.tolist(), recv_counts.tolist()
+        rows = self._a2a(x[order // k], sc, rc)                       # token rows, one per (token, expert) pair
+        local_e = self._a2a((flat[order] % self.E_local).to(torch.int64), sc, rc)
+        # my experts on what I received (fp32 output rows, weight 1: the routing weight is applied by the source)
+        y = torch.zeros(rows.shape[0], x.shape[1], dtype=torch.float32, device=x.device)
+        for e in range(self.E_local):
+            sel = torch.where(local_e == e)[0]
+            if sel.numel():
+                h = R.gated_up(rows[sel], self.wg.select_expert(e), self.wu.select_expert(e), self.act)
+                y[sel] = R.linear(h, self.wd.select_expert(e), out_dtype=torch.float32)
+        back = self._a2a(y, rc, sc)                                    # rows return in the order they were sent
+        pair_y = torch.empty_like(back)
+        pair_y[order] = back
+        res = (pair_y.view(T, k, -1) * w.float().unsqueeze(-1)).sum(1)
+        if residual is not None:
+            res = res + residual.float()
+        res = res.to(x.dtype)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
+
+def enable_expert_parallel(model, max_tokens: int = 256, group=None):
     """Switch a DeepSeek-V2 stage model (every rank holding the *same* layers, data-parallel over tokens) to
     expert-parallel execution: each MoE layer keeps only its ``E / world`` local experts and routes tokens through the
-    fused all-to-all.  Models loaded with ``expert_shard=(rank, world)`` (``utils/loader.py``) already hold just their slice;
-    otherwise the full banks are sliced here and dropped from this rank afterwards (1/world of the MoE memory)."""
+    expert all-to-all — the fused NVLink kernels (:class:`ExpertParallelMoE`) on the ``b200`` backend, ``all_to_all`` collectives
+    (:class:`ExpertParallelMoERef`) on the reference backend.  Models loaded with ``expert_shard=(rank, world)``
+    (``utils/loader.py``) already hold just their slice; otherwise the full banks are sliced here and dropped from this rank
+    afterwards (1/world of the MoE memory).  Returns the :class:`EPBuffers` (``None`` on the reference backend)."""
     cfg = model.cfg
-    bufs = EPBuffers(cfg.hidden_size, max_tokens, cfg.num_experts_per_tok, group=group)
     local = getattr(model, "expert_shard", None) is not None
     if local:
-        assert tuple(model.expert_shard) == (bufs.rank, bufs.world), "model was loaded for a different expert shard"
+        assert tuple(model.expert_shard) == (dist.get_rank(group), dist.get_world_size(group)), \
+            "model was loaded for a different expert shard"
+    fused = model.backend_name == "b200"
+    bufs = EPBuffers(cfg.hidden_size, max_tokens, cfg.num_experts_per_tok, group=group) if fused else None
     model.ep_layers = {}
     for i, w in model.layer_weights.items():
         if "router" not in w:
             continue
-        model.ep_layers[i] = ExpertParallelMoE(bufs, w["e_gate"], w["e_up"], w["e_down"], cfg.n_routed_experts,
-                                               weights_are_local=local)
+        if fused:
+            model.ep_layers[i] = ExpertParallelMoE(bufs, w["e_gate"], w["e_up"], w["e_down"], cfg.n_routed_experts,
+                                                   weights_are_local=local)
+        else:
+            model.ep_layers[i] = ExpertParallelMoERef(w["e_gate"], w["e_up"], w["e_down"], cfg.n_routed_experts,
+                                                      weights_are_local=local, group=group)
         for k in ("e_gate", "e_up", "e_down"):
-            w[k] = None  # the (sliced) bank lives on in the ExpertParallelMoE
-    torch.cuda.empty_cache()
+            w[k] = None  # the (sliced) bank lives on in the expert-parallel layer object
+    if fused:
+        torch.cuda.empty_cache()
     return bufs

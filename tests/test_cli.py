@@ -60,6 +60,22 @@ def test_generate_single_grpc_and_torchrun_agree(ckpt):
     assert r.stdout.split("=" * 10)[0].strip() == text.strip()
 
 
+@pytest.mark.timeout(400)
+def test_generate_expert_parallel_cpu(tmp_path):
+    """``torchrun generate.py --expert_parallel`` on CPU (gloo all_to_all path of parallel/ep.py): experts sharded at load,
+    same greedy text as the single-process run."""
+    from helpers import TINY_DSV2
+
+    ck = write_synthetic_checkpoint(str(tmp_path / "dsv2"), TINY_DSV2, dtype=torch.float32, seed=4)
+    base = ["--model", ck, "--prompt", "experts", "--max_tokens", "10", "--device", "cpu", "--no_chat_template"]
+    text = _gen(base).split("=" * 10)[0]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29612", os.path.join(REPO, "generate.py"), *base, "--expert_parallel"],
+                       capture_output=True, text=True, env=ENV, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.split("=" * 10)[0] == text and len(text) > 0 and "Generation:" in r.stdout
+
+
 def test_console_script_targets_exist():
     import shard.main
     import shard.openai_api
