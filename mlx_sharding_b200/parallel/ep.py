@@ -94,7 +94,7 @@ class ExpertParallelMoE:
         assert T * k <= b.cap, "token batch exceeds the EP buffer capacity"
         W = b.world
         st = b.state
-        Tmax = max(T, peer_tokens or 0)
+        Tmax = max(T, peer_tokens or getattr(self, "peer_tokens_default", 0) or 0)
         # 1) dispatch my pairs to the owners of their experts (remote stores + count/flag publication); also advances the
         #    arrival target of this step's combine (st[W+3] += world)
         C.ep_dispatch(x, idx, self.E_local, b.rank, b.cap, b.t_recv_x, b.t_recv_meta, b.t_recv_count, st[W + 4:W + 5],

@@ -105,6 +105,25 @@ def parse_request_params(body: dict) -> dict:
 
 
 # ------------------------------------------------------------------------------------------------ model provider
+def _ep_device(args) -> str:
+    """Device of this rank in an expert-parallel group: its own GPU under NCCL, the CPU under gloo."""
+    import torch.distributed as dist
+
+    return f"cuda:{torch.cuda.current_device()}" if dist.get_backend() == "nccl" else "cpu"
+
+
+def serve_expert_parallel_worker(args):
+    """Rank r > 0 of ``mlx-sharding-api --expert-parallel``: load my expert shard, join the lockstep group, serve until rank 0
+    shuts the group down."""
+    from ..parallel.ep_serving import build_lockstep_group
+    from ..utils.loader import load_model
+
+    model = load_model(args.model, device=_ep_device(args), expert_shard=(int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])))
+    group = build_lockstep_group(model, args.kv_pages or 2048, args.page_size, max_seqs=args.max_batch)
+    logging.info("expert-parallel worker rank %s ready", os.environ["RANK"])
+    group.serve_forever()
+
+
 class ModelProvider:
     """Loads models on demand and keeps (model, tokenizer, engine) alive across requests
     (reference ``ModelProvider``, openai_api.py:70-127; hot-swap by the request's ``model`` field)."""
@@ -136,8 +155,12 @@ class ModelProvider:
         if num_pages is None:
             # every stage of a chain must use the same pool geometry (block ids are global): fixed default there
             num_pages = 2048 if int(os.environ.get("WORLD_SIZE", "1")) > 1 else self._default_pages(model, page_size)
-        stage = StageExecutor(model, num_pages, page_size)
         world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world > 1 and getattr(a, "expert_parallel", False):
+            from ..parallel.ep_serving import build_lockstep_group
+
+            return build_lockstep_group(model, num_pages, page_size, max_seqs=getattr(a, "max_batch", 64))
+        stage = StageExecutor(model, num_pages, page_size)
         if world > 1:
             from ..parallel.transport import TorchDistTransport
 
@@ -190,8 +213,12 @@ class ModelProvider:
             else:
                 self._validate_model_path(model_path)
                 path = model_path
-            model = load_model(path, start_layer=a.start_layer, end_layer=a.end_layer,
-                               device=getattr(a, "device", None))
+            ep = int(os.environ.get("WORLD_SIZE", "1")) > 1 and getattr(a, "expert_parallel", False)
+            if ep and self.model_key is not None:
+                raise RuntimeError("model hot-swapping is not available in --expert-parallel mode")
+            model = load_model(path, start_layer=None if ep else a.start_layer, end_layer=None if ep else a.end_layer,
+                               device=_ep_device(a) if ep else getattr(a, "device", None),
+                               expert_shard=(int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])) if ep else None)
             tokenizer = load_tokenizer(get_model_path(path), tok_cfg)
             if getattr(a, "use_default_chat_template", False) and tokenizer.chat_template is None:
                 tokenizer.chat_template = getattr(tokenizer, "default_chat_template", None)
@@ -529,6 +556,10 @@ def build_arg_parser() -> argparse.ArgumentParser:
     p.add_argument("--kv-pages", type=int, default=None, help="number of KV pages (default: sized from free memory)")
     p.add_argument("--page-size", type=int, default=64)
     p.add_argument("--max-batch", type=int, default=64, help="max concurrent sequences per micro-batch group")
+    p.add_argument("--expert-parallel", action="store_true",
+                   help="under torchrun, MoE models: instead of a layer pipeline every rank serves its own share of the requests "
+                        "through all layers and holds E/world routed experts per MoE layer (parallel/ep.py, lockstep group of "
+                        "engines: parallel/ep_serving.py); rank 0 is the HTTP front end")
     return p
 
 
@@ -538,7 +569,16 @@ def main(argv=None):
                         format="%(asctime)s - %(levelname)s - %(message)s")
     stubs = []
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1:
+    if world > 1 and args.expert_parallel:
+        # expert-parallel group (torchrun): every rank is a full data-parallel engine, rank 0 additionally serves HTTP
+        from ..parallel.transport import init_distributed
+
+        rank, _ = init_distributed(device=args.device)
+        if args.model is None:
+            raise SystemExit("--expert-parallel needs --model (all ranks load their expert shard at start-up)")
+        if rank != 0:
+            return serve_expert_parallel_worker(args)
+    elif world > 1:
         # native chain (torchrun): rank 0 serves HTTP + the first stage, every other rank is a stage worker.
         # Layer ranges default to a cost-balanced split when neither --start-layer/--end-layer nor the config give them.
         from ..parallel.transport import init_distributed
@@ -558,7 +598,7 @@ def main(argv=None):
 
             return serve_chain(args.model, args.start_layer, args.end_layer, args.device, None,
                                args.kv_pages or 2048, args.page_size)
-    needs_remote = args.end_layer is not None and world == 1
+    needs_remote = args.end_layer is not None and world == 1 and not args.expert_parallel
     if args.model is not None and not needs_remote:
         try:
             from ..config import ModelConfig

@@ -79,3 +79,46 @@ def test_chat_completions_over_4_stage_chain(tmp_path):
             except subprocess.TimeoutExpired:
                 os.killpg(proc.pid, signal.SIGKILL)
     assert answers[0] == answers[1] and len(answers[0]) == 8
+
+
+@pytest.mark.timeout(400)
+def test_chat_completions_expert_parallel_group(tmp_path):
+    """``mlx-sharding-api --expert-parallel`` under torchrun (CPU, gloo): 2 ranks, experts sharded at load, lockstep group of
+    engines; concurrent requests land on different ranks and every answer equals the single-process answer."""
+    import concurrent.futures
+
+    from helpers import TINY_DSV2
+
+    ckpt = write_synthetic_checkpoint(str(tmp_path / "dsv2"), TINY_DSV2, dtype=torch.float32, seed=2)
+    env = dict(os.environ, PYTHONPATH=REPO, OMP_NUM_THREADS="1")
+    bodies = [{"messages": [{"role": "user", "content": f"hello experts {i}"}], "max_tokens": 6 + i, "temperature": 0, "logprobs": 1}
+              for i in range(4)]
+    answers = []
+    for nproc in (1, 2):
+        http_port, master_port = _free_port(), _free_port()
+        if nproc == 1:
+            cmd = [sys.executable, "-m", "shard.openai_api"]
+        else:
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr",
+                   "127.0.0.1", "--master-port", str(master_port), "-m", "shard.openai_api", "--expert-parallel"]
+        cmd += ["--model", ckpt, "--port", str(http_port), "--device", "cpu", "--kv-pages", "64", "--page-size", "16"]
+        proc = subprocess.Popen(cmd, cwd=str(tmp_path), env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                                start_new_session=True)
+        try:
+            _wait_http(http_port, proc)
+            with concurrent.futures.ThreadPoolExecutor(4) as ex:
+                res = list(ex.map(lambda b: _post(http_port, b), bodies))
+            assert all(st == 200 for st, _ in res)
+            answers.append([j["choices"][0]["logprobs"]["tokens"] for _, j in res])
+            if nproc == 2:
+                c = http.client.HTTPConnection("127.0.0.1", http_port, timeout=10)
+                c.request("GET", "/metrics")
+                text = c.getresponse().read().decode()
+                assert "lockstep_assigned_rank0 2" in text and "lockstep_assigned_rank1 2" in text, text
+        finally:
+            os.killpg(proc.pid, signal.SIGTERM)
+            try:
+                proc.wait(timeout=20)
+            except subprocess.TimeoutExpired:
+                os.killpg(proc.pid, signal.SIGKILL)
+    assert answers[0] == answers[1] and [len(a) for a in answers[0]] == [6, 7, 8, 9]
