@@ -13,8 +13,8 @@ exactly that:
 * token events flow back to rank 0 after every iteration and are pushed into the caller's ``Request`` object, so streaming,
   stop sequences, log-probs and cancellation behave exactly as with a local engine.
 
-The control plane (assignments, need-flags, events) uses a gloo group with pickled Python objects; it is three small
-collectives per iteration.  The data plane is whatever ``parallel/ep.py`` uses for the backend (fused NVLink kernels on
+The control plane (assignments, need-flags, events) uses a gloo group with pickled Python objects: ONE small
+``all_gather_object`` per iteration.  The data plane is whatever ``parallel/ep.py`` uses for the backend (fused NVLink kernels on
 ``b200``, ``all_to_all`` on the reference backend — which is how this module is tested on CPU, ``tests/test_ep_cpu.py``).
 
 No reference counterpart: the reference serves one request at a time on one pipeline (shard/openai_api.py:552).
@@ -53,23 +53,30 @@ class LockstepEngine(LLMEngine):
         return StepInput(0, [_SCRATCH_SEQ], torch.zeros(1, dtype=torch.int64), meta, [SamplingParams(temperature=0.0)], [[]],
                          [True], False)
 
-    def step(self) -> bool:
-        """One lockstep iteration.  Returns True if *any* rank ran a forward."""
+    def prepare(self):
+        """Admit waiting requests and build my next step (``None`` if I have nothing to run)."""
         self._admit()
-        built = self._build_step(0)
-        need = [None] * dist.get_world_size(self.ctrl)
-        dist.all_gather_object(need, built is not None, group=self.ctrl)
-        if not any(need):
-            return False
+        return self._build_step(0)
+
+    def run(self, built) -> None:
+        """The group decided that a forward happens this iteration: run my step, or a dummy one to stay aligned."""
         if built is None:
             self.pipe.wait(self.pipe.submit(self._dummy_input()))   # keep the expert all-to-all aligned
             self.dummy_steps += 1
-            return True
+            return
         inp, seqs, q_lens = built
         out = self.pipe.wait(self.pipe.submit(inp))
         self.stats["steps"] += 1
         self._process(0, seqs, q_lens, inp, out)
-        return True
+
+    def step(self) -> bool:
+        """Stand-alone lockstep iteration (one extra collective); ``LockstepGroup`` folds this exchange into its own."""
+        built = self.prepare()
+        need = [None] * dist.get_world_size(self.ctrl)
+        dist.all_gather_object(need, built is not None, group=self.ctrl)
+        if any(need):
+            self.run(built)
+        return any(need)
 
 
 class _Proxy(Request):
@@ -92,6 +99,7 @@ class LockstepGroup:
         self._stop = threading.Event()
         self._iterations = 0
         self._assigned = [0] * self.world
+        self._next_msg: Optional[dict] = None                   # control message received in the previous exchange
 
     # -------------------------------------------------------------------------- LLMEngine surface (rank 0)
     @property
@@ -205,22 +213,32 @@ class LockstepGroup:
                     del self._proxies[gid]
 
     def iterate(self) -> bool:
-        """One group iteration (collective).  Returns False once rank 0 asked the group to stop."""
-        box = [self._plan() if self.rank == 0 else None]
-        dist.broadcast_object_list(box, src=0, group=self.ctrl)
-        msg = box[0]
-        if msg["stop"]:
-            return False
-        self._apply(msg)
+        """One group iteration = ONE control-plane collective (``all_gather_object``) + at most one forward per rank.
+
+        Every rank contributes ``(I have a step, token events of my last forward, [rank 0] control message)``.  The control
+        message (assignments / cancellations / stop) travels with the exchange of iteration *i* and is applied at the start
+        of iteration *i + 1* on all ranks, so everybody applies it at the same point of the sequence."""
+        msg, self._next_msg = self._next_msg, None
+        if msg is not None:
+            if msg["stop"]:
+                return False
+            self._apply(msg)
         try:
-            self.engine.step()
-        except BaseException as e:  # noqa: BLE001 — fail my requests, keep the group alive
+            built = self.engine.prepare()
+        except BaseException as e:  # noqa: BLE001 — fail my requests, stay in the collective
             self.engine._fail_all(e)
-        events = self._drain_events()
-        gathered = [None] * self.world if self.rank == 0 else None
-        dist.gather_object(events, gathered, dst=0, group=self.ctrl)
+            built = None
+        item = (built is not None, self._drain_events(), self._plan() if self.rank == 0 else None)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, item, group=self.ctrl)
+        self._next_msg = gathered[0][2]
         if self.rank == 0:
-            self._route(gathered)
+            self._route([g[1] for g in gathered])
+        if any(g[0] for g in gathered):
+            try:
+                self.engine.run(built)
+            except BaseException as e:  # noqa: BLE001
+                self.engine._fail_all(e)
         self._iterations += 1
         return True
 
