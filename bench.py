@@ -136,18 +136,28 @@ def main(argv=None):
     if mode in ("ep", "both"):
         gc.collect()
         torch.cuda.empty_cache()
-        ep = run_ep(args, world, rank, local, dev)
-        if rank == 0:
+        try:
+            ep = run_ep(args, world, rank, local, dev)
+        except Exception:  # noqa: BLE001 — keep the pipeline measurement if the second sharding fails on every rank
+            import traceback
+
+            traceback.print_exc()
+            if res is None:
+                raise
+            ep = None
+            if rank == 0:
+                res["also_measured"] = {"expert parallel (config 5)": {"error": "run failed, see stderr"}}
+        if rank == 0 and ep is not None:
             if res is not None:
                 keep = ("value", "ms_per_step", "config", "ttft_p50_ms", "ttft_microbatch_ms", "e2e", "gpu_launches", "clocks")
                 pp_summary = {k: res[k] for k in keep}
                 if "invalid" in res:
                     pp_summary["invalid"] = res["invalid"]
-                if ep["value"] >= res["value"] or "invalid" in res:
+                if "invalid" not in ep and (ep["value"] >= res["value"] or "invalid" in res):
                     ep["also_measured"] = {"layer-range pipeline (config 3)": pp_summary}
                     res = ep
                 else:
-                    res["also_measured"] = {"expert parallel (config 5)": {k: ep[k] for k in keep}}
+                    res["also_measured"] = {"expert parallel (config 5)": {k: ep[k] for k in keep + (("invalid",) if "invalid" in ep else ())}}
             else:
                 res = ep
     if rank == 0:
