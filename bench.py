@@ -148,24 +148,24 @@ def main(argv=None):
             if rank == 0:
                 res["also_measured"] = {"expert parallel (config 5)": {"error": "run failed, see stderr"}}
         if rank == 0 and ep is not None:
-            if res is not None:
-                keep = ("value", "ms_per_step", "config", "ttft_p50_ms", "ttft_microbatch_ms", "e2e", "gpu_launches", "clocks")
-                pp_summary = {k: res[k] for k in keep}
-                if "invalid" in res:
-                    pp_summary["invalid"] = res["invalid"]
-                if "invalid" not in ep and (ep["value"] >= res["value"] or "invalid" in res):
-                    ep["also_measured"] = {"layer-range pipeline (config 3)": pp_summary}
-                    res = ep
-                else:
-                    res["also_measured"] = {"expert parallel (config 5)": {k: ep[k] for k in keep + (("invalid",) if "invalid" in ep else ())}}
-            else:
-                res = ep
+            res = merge_results(res, ep)
     if rank == 0:
         print(json.dumps(res), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def merge_results(pp, ep):
+    """Headline = the faster *valid* sharding; the other one is reported under ``also_measured`` (pure function, unit-tested)."""
+    if pp is None:
+        return ep
+    keep = ("value", "ms_per_step", "config", "ttft_p50_ms", "ttft_microbatch_ms", "e2e", "gpu_launches", "clocks", "invalid")
+    brief = lambda r: {k: r[k] for k in keep if k in r}
+    if "invalid" not in ep and (ep["value"] >= pp["value"] or "invalid" in pp):
+        return dict(ep, also_measured={"layer-range pipeline (config 3)": brief(pp)})
+    return dict(pp, also_measured={"expert parallel (config 5)": brief(ep)})
 
 
 def run_pp(args, world, rank, local, dev):

@@ -90,3 +90,28 @@ def test_console_script_targets_exist():
                                        "--cache-limit-gb", "4", "--use-default-chat-template", "--trust-remote-code",
                                        "--chat-template", "t", "--log-level", "DEBUG", "--static-dir", "z"])
     assert a.llm_shard_addresses == "h:1,h:2" and a.start_layer == 0 and a.end_layer == 14 and a.cache_limit_gb == 4
+
+
+def test_bench_result_merge_and_reference_arm(capsys):
+    """bench.py host-side contract pieces that need no GPU: the pp/ep result merge and the reference arm's JSON line."""
+    import importlib.util
+    import json
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(REPO, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    pp = dict(value=60.0, ms_per_step=8.0, config={"parallelism": "pp8"}, ttft_p50_ms=8.0, ttft_microbatch_ms=60.0, e2e=None,
+              gpu_launches=1, clocks={}, metric="m")
+    ep = dict(pp, value=99.0, config={"parallelism": "ep8+dp8"})
+    m = bench.merge_results(pp, ep)
+    assert m["value"] == 99.0 and m["also_measured"]["layer-range pipeline (config 3)"]["value"] == 60.0
+    m = bench.merge_results(pp, dict(ep, invalid="EP flag wait timed out"))
+    assert m["value"] == 60.0 and m["also_measured"]["expert parallel (config 5)"]["invalid"]
+    m = bench.merge_results(dict(pp, invalid="x"), dict(ep, value=1.0))
+    assert m["value"] == 1.0
+    assert bench.merge_results(None, ep) is ep
+    assert bench.main(["--impl", "reference"]) == 0
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and "unavailable" in line
+    a = bench.parse_args([])
+    assert a.gpus == 1 and a.warmup >= 3 and a.parallelism == "auto"
