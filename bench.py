@@ -142,10 +142,10 @@ def main(argv=None):
             import traceback
 
             traceback.print_exc()
-            if res is None:
+            if mode != "both":   # nothing else was measured
                 raise
             ep = None
-            if rank == 0:
+            if rank == 0 and res is not None:
                 res["also_measured"] = {"expert parallel (config 5)": {"error": "run failed, see stderr"}}
         if rank == 0 and ep is not None:
             res = merge_results(res, ep)
