@@ -106,7 +106,7 @@ class ExpertParallelMoE:
         # 3) my experts: grouped swap-AB tcgen05 GEMMs on the received rows; the down-projection epilogue stores every output
         #    row straight into its source rank's return buffer (peer memory) and the last tile bumps all sources' flags
         max_rows = min(W * Tmax, x_perm.shape[0])  # upper bound of rows one expert can receive (every rank sends <= Tmax)
-        exp_rows = Tmax * k  # balanced routing: every rank receives about as many pairs as it sends (sizes the token tile)
+        exp_rows = T * k  # balanced routing: a rank receives about as many pairs as it sends (only picks the token tile size)
         h = C.grouped_linear(x_perm, self.wg, self.wu, offs, max_rows, self.act, False, None, None, None, exp_rows)
         C.grouped_linear(h, self.wd, None, offs, max_rows, 0, True, row_dst, b.ret_flags_dev, st[W + 1:W + 2], exp_rows)
         # 4) wait for all my pairs to come home + weighted combine (+ residual): one kernel
