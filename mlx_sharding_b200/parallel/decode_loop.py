@@ -138,13 +138,24 @@ class DecodeLoop:
         else:
             dist.recv(self.hidden_in[g], self.rank - 1)
 
+    def _send(self, t: torch.Tensor, dst: int):
+        """NCCL sends are stream-ordered and return immediately; gloo's ``send`` blocks until the peer posts the matching
+        ``recv``, which would dead-lock the ring (rank r sends group g+1 forward while the last rank sends group g's tokens
+        back) — on gloo the send is posted asynchronously and completed in ``drain`` / before the buffer is reused."""
+        if dist.get_backend() != "gloo":
+            dist.send(t, dst)
+            return
+        self._sends = [(w, keep) for w, keep in getattr(self, "_sends", []) if not w.is_completed()]
+        keep = t.clone()
+        self._sends.append((dist.isend(keep, dst), keep))
+
     def _nccl_post(self, g: int, out):
         if self.transport != "nccl":
             return
         if self.last:
-            dist.send(self.groups[g].tokens, 0)
+            self._send(self.groups[g].tokens, 0)
         else:
-            dist.send(out, self.rank + 1)
+            self._send(out, self.rank + 1)
 
     # ------------------------------------------------------------------------------------------ setup
     def prime_tokens(self):
@@ -218,3 +229,6 @@ class DecodeLoop:
         if self.transport == "nccl" and self.first and self.world > 1:
             for g in range(self.G):
                 dist.recv(self.groups[g].tokens, self.world - 1)
+        for w, _ in getattr(self, "_sends", []):
+            w.wait()
+        self._sends = []
