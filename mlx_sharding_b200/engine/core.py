@@ -22,7 +22,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from ..ops.meta import BatchMeta
-from .kv_cache import PageAllocator, SequenceTable
+from .kv_cache import PageAllocator, PrefixCache, SequenceTable
 from .sampler import SamplingParams
 
 
@@ -79,6 +79,7 @@ class Request:
         self.t_first: Optional[float] = None
         self.t_done: Optional[float] = None
         self.prefilled = 0            # prompt tokens already in the KV cache
+        self.cached_pages = 0         # leading pages of this request that are registered in the prefix cache
 
     def cancel(self):
         self.cancelled = True
@@ -113,7 +114,8 @@ def stopping_criteria(tokens: List[int], stop_id_sequences: List[List[int]], eos
 # ---------------------------------------------------------------------------------------------
 class LLMEngine:
     def __init__(self, pipeline, num_pages: int, page_size: int = 64, num_groups: Optional[int] = None,
-                 max_seqs_per_group: int = 64, max_prefill_tokens: int = 2048, max_model_len: int = 32768):
+                 max_seqs_per_group: int = 64, max_prefill_tokens: int = 2048, max_model_len: int = 32768,
+                 prefix_cache: bool = False):
         self.pipe = pipeline
         self.page_size = page_size
         self.num_groups = num_groups or max(1, getattr(pipeline, "num_stages", 1))
@@ -121,6 +123,8 @@ class LLMEngine:
         self.max_prefill_tokens = max_prefill_tokens
         self.max_model_len = max_model_len
         self.table = SequenceTable(PageAllocator(num_pages), page_size)
+        # automatic prefix caching (engine/kv_cache.py::PrefixCache): full prompt pages are shared between requests
+        self.table.prefix = PrefixCache(self.table.alloc, page_size) if prefix_cache else None
         self.waiting: "queue.Queue[Request]" = queue.Queue()
         self.groups: List[List[Request]] = [[] for _ in range(self.num_groups)]
         self.inflight: List[Optional[tuple]] = [None] * self.num_groups
@@ -128,7 +132,7 @@ class LLMEngine:
         self._thread: Optional[threading.Thread] = None
         self._stop = threading.Event()
         self._wake = threading.Event()
-        self.stats = dict(steps=0, prefill_tokens=0, decode_tokens=0, finished=0)
+        self.stats = dict(steps=0, prefill_tokens=0, decode_tokens=0, finished=0, prefix_cached_tokens=0)
 
     # -------------------------------------------------------------------------- public API
     def submit(self, prompt: Sequence[int], params: Optional[SamplingParams] = None, max_tokens: int = 100,
@@ -209,8 +213,12 @@ class LLMEngine:
                 r = self.waiting.get_nowait()
             except queue.Empty:
                 return
-            need = (len(r.prompt) + r.max_tokens + self.page_size - 1) // self.page_size
+            cache = self.table.prefix
+            shared = cache.match(r.prompt) if cache is not None else []
+            need = (len(r.prompt) + r.max_tokens + self.page_size - 1) // self.page_size - len(shared)
             if need > self.table.alloc.num_free:
+                if shared:
+                    cache.release(shared)   # give the references back; the request is retried later
                 if not any(self.groups):
                     r.error = MemoryError("request does not fit in the KV pool")
                     r.finished = True
@@ -220,7 +228,15 @@ class LLMEngine:
                 self.waiting.queue.appendleft(r)
                 return
             self.table.add(r.id)
-            self.table.reserve(r.id, len(r.prompt) + r.max_tokens)
+            if shared:
+                # the matched prefix is already in the KV pool (on every stage): start the prefill behind it
+                n = len(shared) * self.page_size
+                self.table.pages[r.id] = list(shared)
+                self.table.length[r.id] = n
+                r.prefilled = n
+                r.cached_pages = len(shared)
+                self.stats["prefix_cached_tokens"] += n
+            self.table.reserve(r.id, len(r.prompt) - r.prefilled + r.max_tokens)
             self.groups[g].append(r)
 
     def _build_step(self, g: int) -> Optional[StepInput]:
@@ -273,6 +289,8 @@ class LLMEngine:
             else:
                 self.stats["decode_tokens"] += 1
             self.table.advance(r.id, q_lens[b])
+            if inp.is_prefill and self.table.prefix is not None:
+                r.cached_pages = self.table.prefix.insert(r.prompt, self.table.pages[r.id], r.prefilled, r.cached_pages)
             if r.cancelled and not r.finished:
                 self._finish(r, "cancelled")
                 r.events.put(TokenEvent(-1, 0.0, None, True, "cancelled"))

@@ -248,7 +248,7 @@ class LockstepGroup:
 
 
 def build_lockstep_group(model, num_pages: int, page_size: int = 64, max_seqs: int = 64, max_prefill_tokens: int = 2048,
-                         ep_max_tokens: Optional[int] = None) -> LockstepGroup:
+                         ep_max_tokens: Optional[int] = None, prefix_cache: bool = False) -> LockstepGroup:
     """Collective helper: expert-parallel ``model`` (loaded with ``expert_shard``) -> a started-able ``LockstepGroup``."""
     from .ep import enable_expert_parallel
     from .pipeline import LocalPipeline, StageExecutor
@@ -259,5 +259,5 @@ def build_lockstep_group(model, num_pages: int, page_size: int = 64, max_seqs: i
     for layer in model.ep_layers.values():
         layer.peer_tokens_default = bound                       # ranks run different batch sizes: size temporaries for the bound
     engine = LockstepEngine(LocalPipeline([StageExecutor(model, num_pages, page_size)]), num_pages, page_size, ctrl_group=ctrl,
-                            max_seqs_per_group=max_seqs, max_prefill_tokens=max_prefill_tokens)
+                            max_seqs_per_group=max_seqs, max_prefill_tokens=max_prefill_tokens, prefix_cache=prefix_cache)
     return LockstepGroup(engine, ctrl)

@@ -159,14 +159,15 @@ class ModelProvider:
         if world > 1 and getattr(a, "expert_parallel", False):
             from ..parallel.ep_serving import build_lockstep_group
 
-            return build_lockstep_group(model, num_pages, page_size, max_seqs=getattr(a, "max_batch", 64))
+            return build_lockstep_group(model, num_pages, page_size, max_seqs=getattr(a, "max_batch", 64),
+                                        prefix_cache=getattr(a, "prefix_cache", False))
         stage = StageExecutor(model, num_pages, page_size)
         if world > 1:
             from ..parallel.transport import TorchDistTransport
 
             pipe = ChainPipeline(stage, TorchDistTransport(model.device))
             return LLMEngine(pipe, num_pages, page_size, num_groups=world,
-                             max_seqs_per_group=getattr(a, "max_batch", 64))
+                             max_seqs_per_group=getattr(a, "max_batch", 64), prefix_cache=getattr(a, "prefix_cache", False))
         if not model.spec.is_last:
             if not self.stubs:
                 raise RuntimeError("this process only holds layers "
@@ -175,7 +176,7 @@ class ModelProvider:
             pipe = GrpcRelayPipeline(stage, self.stubs)
             return LLMEngine(pipe, num_pages, page_size, num_groups=1, max_seqs_per_group=1)
         return LLMEngine(LocalPipeline([stage]), num_pages, page_size, num_groups=1,
-                         max_seqs_per_group=getattr(a, "max_batch", 64))
+                         max_seqs_per_group=getattr(a, "max_batch", 64), prefix_cache=getattr(a, "prefix_cache", False))
 
     def _default_pages(self, model, page_size) -> int:
         """Size the KV pool: ``--cache-limit-gb`` (the reference's Metal cache limit flag) caps it."""
@@ -556,6 +557,9 @@ def build_arg_parser() -> argparse.ArgumentParser:
     p.add_argument("--kv-pages", type=int, default=None, help="number of KV pages (default: sized from free memory)")
     p.add_argument("--page-size", type=int, default=64)
     p.add_argument("--max-batch", type=int, default=64, help="max concurrent sequences per micro-batch group")
+    p.add_argument("--prefix-cache", action="store_true",
+                   help="automatic prefix caching: full KV pages of prompt prefixes are shared between requests (chat system "
+                        "prompts are prefilled once); not available with gRPC reference shards")
     p.add_argument("--expert-parallel", action="store_true",
                    help="under torchrun, MoE models: instead of a layer pipeline every rank serves its own share of the requests "
                         "through all layers and holds E/world routed experts per MoE layer (parallel/ep.py, lockstep group of "

@@ -18,7 +18,7 @@ def server(tmp_path_factory):
     path = write_synthetic_checkpoint(str(d / "tiny"), TINY_LLAMA, dtype=torch.float32)
     cwd = os.getcwd()
     os.chdir(d)
-    args = openai_api.build_arg_parser().parse_args(["--model", path, "--port", "0", "--kv-pages", "128", "--page-size", "16"])
+    args = openai_api.build_arg_parser().parse_args(["--model", path, "--port", "0", "--kv-pages", "128", "--page-size", "16", "--prefix-cache"])
     args.static_dir = os.path.join(os.path.dirname(openai_api.__file__), "static")
     provider = openai_api.ModelProvider(args, [])
     httpd = openai_api.make_server("127.0.0.1", 0, provider, args.static_dir)
@@ -143,3 +143,17 @@ def test_concurrent_requests(server):
 def test_convert_chat_fallback():
     s = openai_api.convert_chat([{"role": "system", "content": "be nice"}, {"role": "user", "content": "hi"}])
     assert s == "ASSISTANT's RULE: be nice\nUSER: hi\nASSISTANT:"
+
+
+def test_prefix_cache_hits_show_up_in_metrics(server):
+    """The server fixture runs with --prefix-cache: repeating a long prompt re-uses its KV pages and answers identically."""
+    port, provider = server
+    body = {"prompt": "the quick brown fox jumps over the lazy dog " * 3, "max_tokens": 6, "temperature": 0}
+    _, a = _post(port, "/v1/completions", body)
+    before = provider.engine.stats["prefix_cached_tokens"]
+    _, b = _post(port, "/v1/completions", body)
+    assert a["choices"][0]["text"] == b["choices"][0]["text"]
+    assert provider.engine.stats["prefix_cached_tokens"] > before
+    c = http.client.HTTPConnection("127.0.0.1", port, timeout=10)
+    c.request("GET", "/metrics")
+    assert "mlx_sharding_engine_prefix_cached_tokens" in c.getresponse().read().decode()

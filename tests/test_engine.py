@@ -95,3 +95,55 @@ def test_oversized_request_rejected():
     r = eng.submit(list(range(1, 200)), SamplingParams(), max_tokens=2000)
     eng.drain()
     assert isinstance(r.error, MemoryError)
+
+
+def _prefix_engine(num_pages=64, page_size=4, ranges=None, **kw):
+    cfg = ModelConfig.from_dict(TINY_LLAMA)
+    sd = dict(random_state_dict(cfg, dtype=torch.float32))
+    ranges = ranges or [(0, cfg.num_hidden_layers)]
+    models = [build_stage(cfg, cfg.shard(s, e), torch.float32).load_state(sd) for s, e in ranges]
+    pipe = LocalPipeline.from_models(models, num_pages=num_pages, page_size=page_size)
+    return models, LLMEngine(pipe, num_pages=num_pages, page_size=page_size, prefix_cache=True, **kw)
+
+
+def test_prefix_cache_reuses_prompt_pages_and_keeps_outputs():
+    """Automatic prefix caching: a second prompt sharing a prefix skips the cached full pages (less prefill work) and still
+    produces exactly the tokens of an uncached run; works across a 2-stage pipeline (same page ids on every stage)."""
+    models, eng = _prefix_engine(ranges=[(0, 2), (2, 4)])
+    system = [7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17]                     # 11 tokens: 2 full pages of 4 + 3
+    a, b = system + [100, 101], system + [200]
+    g = SamplingParams(temperature=0.0)
+    assert eng.generate(a, g, max_tokens=5) == _greedy_oracle(models, a, 5)
+    assert eng.stats["prefix_cached_tokens"] == 0
+    before = eng.stats["prefill_tokens"]
+    assert eng.generate(b, g, max_tokens=5) == _greedy_oracle(models, b, 5)
+    assert eng.stats["prefix_cached_tokens"] == 8                          # two full pages re-used
+    assert eng.stats["prefill_tokens"] - before == len(b) - 8
+    # the very same prompt again: everything but the page holding the last prompt token is re-used
+    assert eng.generate(a, g, max_tokens=5) == _greedy_oracle(models, a, 5)
+    assert eng.stats["prefix_cached_tokens"] == 8 + 12
+    # concurrent requests on shared pages + a batch of unrelated ones
+    reqs = [eng.submit(p, g, max_tokens=4) for p in (a, b, [5, 5, 5, 5, 5, 5], system + [300, 301, 302])]
+    eng.drain()
+    for r, p in zip(reqs, (a, b, [5, 5, 5, 5, 5, 5], system + [300, 301, 302])):
+        assert r.output == _greedy_oracle(models, p, 4)
+    # bookkeeping: nothing is referenced any more, every page is either free or evictable; eviction returns all of them
+    cache = eng.table.prefix
+    assert all(v == 0 for v in cache.refs.values()) and len(cache.lru) == len(cache.refs) > 0
+    assert eng.table.alloc.num_free == 64 - 1
+    cache.evict(10 ** 6)
+    assert len(eng.table.alloc._free) == 64 - 1 and not cache.by_digest
+
+
+def test_prefix_cache_evicts_under_memory_pressure():
+    """A pool too small to keep old prefixes: cached pages are evicted LRU-first, requests still run and stay correct."""
+    models, eng = _prefix_engine(num_pages=12, page_size=4)                 # 11 usable pages
+    g = SamplingParams(temperature=0.0)
+    prompts = [[i * 10 + j for j in range(9)] for i in range(1, 6)]         # 5 unrelated 9-token prompts: 2 cacheable pages each
+    for p in prompts:
+        assert eng.generate(p, g, max_tokens=4) == _greedy_oracle(models, p, 4)
+    assert eng.table.prefix.evictions > 0
+    p = prompts[-1]                                                         # most recent prefix is still resident
+    before = eng.stats["prefix_cached_tokens"]
+    assert eng.generate(p, g, max_tokens=4) == _greedy_oracle(models, p, 4)
+    assert eng.stats["prefix_cached_tokens"] == before + 8
