@@ -115,13 +115,16 @@ def stopping_criteria(tokens: List[int], stop_id_sequences: List[List[int]], eos
 class LLMEngine:
     def __init__(self, pipeline, num_pages: int, page_size: int = 64, num_groups: Optional[int] = None,
                  max_seqs_per_group: int = 64, max_prefill_tokens: int = 2048, max_model_len: int = 32768,
-                 prefix_cache: bool = False):
+                 prefix_cache: bool = False, mixed_batches: bool = False):
         self.pipe = pipeline
         self.page_size = page_size
         self.num_groups = num_groups or max(1, getattr(pipeline, "num_stages", 1))
         self.max_seqs = max_seqs_per_group
         self.max_prefill_tokens = max_prefill_tokens
         self.max_model_len = max_model_len
+        # mixed_batches: a prefill step also carries the next decode token of every running sequence of the group (one ragged
+        # batch), so streams in flight keep their inter-token latency while new prompts are being prefilled
+        self.mixed_batches = mixed_batches
         self.table = SequenceTable(PageAllocator(num_pages), page_size)
         # automatic prefix caching (engine/kv_cache.py::PrefixCache): full prompt pages are shared between requests
         self.table.prefix = PrefixCache(self.table.alloc, page_size) if prefix_cache else None
@@ -257,6 +260,14 @@ class LLMEngine:
                 toks.extend(r.prompt[r.prefilled:r.prefilled + n])
                 mask.append(r.prefilled + n == len(r.prompt))
                 budget -= n
+            if self.mixed_batches:
+                for r in reqs:
+                    if r.prefilled >= len(r.prompt) and r.output:
+                        seqs.append(r)
+                        q_lens.append(1)
+                        ctx0.append(self.table.length[r.id])
+                        toks.append(r.output[-1])
+                        mask.append(True)
             is_prefill = True
         else:
             for r in reqs:
@@ -283,13 +294,13 @@ class LLMEngine:
 
     def _process(self, g: int, seqs: List[Request], q_lens: List[int], inp: StepInput, out: StepOutput):
         for b, r in enumerate(seqs):
-            if inp.is_prefill:
+            if inp.is_prefill and r.prefilled < len(r.prompt):
                 r.prefilled += q_lens[b]
                 self.stats["prefill_tokens"] += q_lens[b]
             else:
                 self.stats["decode_tokens"] += 1
             self.table.advance(r.id, q_lens[b])
-            if inp.is_prefill and self.table.prefix is not None:
+            if inp.is_prefill and self.table.prefix is not None and r.cached_pages * self.page_size < len(r.prompt):
                 r.cached_pages = self.table.prefix.insert(r.prompt, self.table.pages[r.id], r.prefilled, r.cached_pages)
             if r.cancelled and not r.finished:
                 self._finish(r, "cancelled")

@@ -167,7 +167,8 @@ class ModelProvider:
 
             pipe = ChainPipeline(stage, TorchDistTransport(model.device))
             return LLMEngine(pipe, num_pages, page_size, num_groups=world,
-                             max_seqs_per_group=getattr(a, "max_batch", 64), prefix_cache=getattr(a, "prefix_cache", False))
+                             max_seqs_per_group=getattr(a, "max_batch", 64), prefix_cache=getattr(a, "prefix_cache", False),
+                             mixed_batches=getattr(a, "mixed_batches", False))
         if not model.spec.is_last:
             if not self.stubs:
                 raise RuntimeError("this process only holds layers "
@@ -176,7 +177,8 @@ class ModelProvider:
             pipe = GrpcRelayPipeline(stage, self.stubs)
             return LLMEngine(pipe, num_pages, page_size, num_groups=1, max_seqs_per_group=1)
         return LLMEngine(LocalPipeline([stage]), num_pages, page_size, num_groups=1,
-                         max_seqs_per_group=getattr(a, "max_batch", 64), prefix_cache=getattr(a, "prefix_cache", False))
+                         max_seqs_per_group=getattr(a, "max_batch", 64), prefix_cache=getattr(a, "prefix_cache", False),
+                             mixed_batches=getattr(a, "mixed_batches", False))
 
     def _default_pages(self, model, page_size) -> int:
         """Size the KV pool: ``--cache-limit-gb`` (the reference's Metal cache limit flag) caps it."""
@@ -560,6 +562,9 @@ def build_arg_parser() -> argparse.ArgumentParser:
     p.add_argument("--prefix-cache", action="store_true",
                    help="automatic prefix caching: full KV pages of prompt prefixes are shared between requests (chat system "
                         "prompts are prefilled once); not available with gRPC reference shards")
+    p.add_argument("--mixed-batches", action="store_true",
+                   help="scheduler: prefill chunks and the decode tokens of running sequences share one ragged step, so streams in "
+                        "flight keep their inter-token latency while new prompts are prefilled")
     p.add_argument("--expert-parallel", action="store_true",
                    help="under torchrun, MoE models: instead of a layer pipeline every rank serves its own share of the requests "
                         "through all layers and holds E/world routed experts per MoE layer (parallel/ep.py, lockstep group of "

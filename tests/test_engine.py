@@ -147,3 +147,29 @@ def test_prefix_cache_evicts_under_memory_pressure():
     before = eng.stats["prefix_cached_tokens"]
     assert eng.generate(p, g, max_tokens=4) == _greedy_oracle(models, p, 4)
     assert eng.stats["prefix_cached_tokens"] == before + 8
+
+
+def test_mixed_batches_keep_running_streams_decoding_during_prefill():
+    """mixed_batches=True: a step that prefills a new prompt also decodes one token of every running sequence; results are
+    identical to the separate-phase schedule and running sequences never stall behind a long prompt."""
+    long_prompt = list(range(20, 60))
+    outs = {}
+    for mixed in (False, True):
+        models, eng = _engine(mixed_batches=mixed, max_prefill_tokens=8)        # the long prompt needs 5 prefill chunks
+        g = SamplingParams(temperature=0.0)
+        first = eng.submit([3, 9, 27, 81], g, max_tokens=12)
+        for _ in range(3):
+            eng.step()
+        produced_before = len(first.output)
+        late = eng.submit(long_prompt, g, max_tokens=4)
+        stalls = 0
+        while late.prefilled < len(late.prompt):
+            n0 = len(first.output)
+            eng.step()
+            stalls += int(len(first.output) == n0 and not first.finished)
+        eng.drain()
+        outs[mixed] = (first.output, late.output, stalls)
+        assert first.output == _greedy_oracle(models, [3, 9, 27, 81], 12) and late.output == _greedy_oracle(models, long_prompt, 4)
+        assert produced_before > 0
+    assert outs[False][:2] == outs[True][:2]
+    assert outs[True][2] <= 1 < outs[False][2]          # separate phases stall the running stream for the whole prefill
