@@ -178,7 +178,7 @@ class ModelProvider:
             return LLMEngine(pipe, num_pages, page_size, num_groups=1, max_seqs_per_group=1)
         return LLMEngine(LocalPipeline([stage]), num_pages, page_size, num_groups=1,
                          max_seqs_per_group=getattr(a, "max_batch", 64), prefix_cache=getattr(a, "prefix_cache", False),
-                             mixed_batches=getattr(a, "mixed_batches", False))
+                         mixed_batches=getattr(a, "mixed_batches", False))
 
     def _default_pages(self, model, page_size) -> int:
         """Size the KV pool: ``--cache-limit-gb`` (the reference's Metal cache limit flag) caps it."""
