@@ -29,6 +29,11 @@ _EXPERT_RE = re.compile(r"^(model\.layers\.\d+\.mlp)\.experts\.(\d+)\.(gate_proj
 class DeepseekV2Stage(StageModel):
     arch = "deepseek_v2"
     overlap_shared_experts = os.environ.get("MLXB200_OVERLAP_SHARED", "1") != "0"
+    # Opt-in KV layout: cache the 512-dim latent + the 64-dim roped key (one shared "head", 576 + 512 values per token)
+    # instead of the decompressed per-head K/V (16 x (192 + 128) = 5120 values) and absorb kv_b into the query / output
+    # side.  Mathematically identical attention (see ``_attn_absorbed``); today only the reference backend implements it —
+    # the sm_100a kernel for d_qk = 576 / d_v = 512 multi-query attention is the next step (docs/NEXT.md).
+    absorbed_mla = os.environ.get("MLXB200_ABSORBED_MLA", "0") == "1"
 
     @property
     def head_dim(self):
@@ -37,6 +42,12 @@ class DeepseekV2Stage(StageModel):
 
     def _make_rope(self):
         return deepseek_rope_spec(self.cfg)
+
+    def kv_geometry(self):
+        if self.absorbed_mla:
+            c = self.cfg
+            return self.spec.num_kv_layers, 1, c.kv_lora_rank + c.qk_rope_head_dim, c.kv_lora_rank
+        return super().kv_geometry()
 
     def sanitize(self, sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         sd = super().sanitize(sd)
@@ -107,11 +118,37 @@ class DeepseekV2Stage(StageModel):
             q = O.linear(O.rmsnorm(qa[:, :ql], w["q_a_ln"], c.rms_norm_eps), w["q_b"])
             ckv, k_pe = qa[:, ql: ql + lr], qa[:, ql + lr:]
         q = q.view(T, nh, qd) if q.is_contiguous() else q.unflatten(1, (nh, qd))
+        if self.absorbed_mla:
+            return O.linear(self._attn_absorbed(w, q, ckv, k_pe, meta, kpool, vpool), w["o"], residual=h,
+                            **self._final_kwargs(i, T, "attn"))
         kv = O.linear(O.rmsnorm(ckv, w["kv_a_ln"], c.rms_norm_eps), w["kv_b"]).view(T, nh, nope + vd)
         # rope(q_pe), rope(k_pe) and the cache append K=[k_nope|k_pe], V: one fused launch
         O.mla_rope_kv_write(q, k_pe, kv, kpool, vpool, meta, self.rope, nope, vd)
         attn = O.paged_attention(q, kpool, vpool, meta, c.attn_scale, 0.0)
         return O.linear(attn.reshape(T, nh * vd), w["o"], residual=h, **self._final_kwargs(i, T, "attn"))
+
+    def _attn_absorbed(self, w, q, ckv, k_pe, meta: BatchMeta, kpool, vpool):
+        """Weight-absorbed MLA.  With ``kv_b = [W_UK | W_UV]`` per head (``k_nope = W_UK c``, ``v = W_UV c``, ``c`` = normed latent):
+
+            q_nope . k_nope = (W_UK^T q_nope) . c        -> query side absorbs W_UK   (q_abs, 512-dim)
+            sum_t p_t v_t   = W_UV (sum_t p_t c_t)       -> output side absorbs W_UV
+
+        so attention runs as multi-query attention over the cached ``[c | rope(k_pe)]`` (576) with values ``c`` (512)."""
+        if self.backend_name != "reference":
+            raise NotImplementedError("absorbed-latent MLA: only the reference backend implements it so far")
+        O, c = self.ops, self.cfg
+        T = q.shape[0]
+        nh, nope, rd, vd, lr = c.num_attention_heads, c.qk_nope_head_dim, c.qk_rope_head_dim, c.v_head_dim, c.kv_lora_rank
+        lat = O.rmsnorm(ckv, w["kv_a_ln"], c.rms_norm_eps)                                   # [T, lr]
+        q = q.clone()
+        O.rope_(q, meta.positions, self.rope, nope)                                           # q_pe in place
+        kpe = k_pe.reshape(T, 1, rd).clone()
+        O.rope_(kpe, meta.positions, self.rope, 0)
+        wkv = w["kv_b"].dense(torch.float32).view(nh, nope + vd, lr)
+        q_abs = torch.einsum("thn,hnl->thl", q[..., :nope].float(), wkv[:, :nope]).to(q.dtype)
+        O.kv_write(torch.cat([lat.unsqueeze(1), kpe.to(lat.dtype)], -1), lat.unsqueeze(1), kpool, vpool, meta.slot_mapping)
+        o_lat = O.paged_attention(torch.cat([q_abs, q[..., nope:]], -1), kpool, vpool, meta, c.attn_scale, 0.0)   # [T, nh, lr]
+        return torch.einsum("thl,hvl->thv", o_lat.float(), wkv[:, nope:]).to(q.dtype).reshape(T, nh * vd)
 
     def mlp_block(self, i, h, meta: BatchMeta):
         O, c, w = self.ops, self.cfg, self.layer_weights[i]

@@ -218,3 +218,24 @@ def test_yarn_rope_and_mscale():
     assert torch.allclose(inv[0], base[0]) and torch.allclose(inv[-1], base[-1] / 40, rtol=1e-5)
     m = 0.1 * 0.707 * math.log(40) + 1.0
     assert abs(cfg.attn_scale - (192 ** -0.5) * m * m) < 1e-9
+
+
+def test_absorbed_latent_mla_matches_decompressed_cache():
+    """Opt-in MLA cache layout (latent 512 + roped key 64 per token, kv_b absorbed into the query / output side): same logits
+    as the reference's decompressed K/V layout, 4.7x fewer cached values per token; also through a sharded pipeline."""
+    from mlx_sharding_b200.models.deepseek_v2 import DeepseekV2Stage
+
+    cfg, sd, full = _ours(TINY_DSV2)
+    ref = run_sequence(full, TOKS, 4)
+
+    class Absorbed(DeepseekV2Stage):
+        absorbed_mla = True
+
+    parts = [Absorbed(cfg, cfg.shard(s, e), torch.float32).load_state(sd) for s, e in [(0, 2), (2, 4)]]
+    L, hk, dk, dv = parts[0].kv_geometry()
+    assert (hk, dk, dv) == (1, cfg.kv_lora_rank + cfg.qk_rope_head_dim, cfg.kv_lora_rank)
+    got = run_sequence(parts, TOKS, 4, chunk=4)
+    for a, b in zip(ref, got):
+        assert torch.allclose(a, b, atol=2e-4, rtol=1e-4), (a - b).abs().max()
+    std = full[0].kv_geometry()
+    assert std[1] * (std[2] + std[3]) > 2 * (dk + dv)
