@@ -72,7 +72,9 @@ def main(argv=None):
     parser.add_argument("--dtype", type=str, default=None, choices=["bfloat16", "float16", "float32"])
     parser.add_argument("--wire-dtype", type=str, default="float16", choices=["float16", "bfloat16", "float32"],
                         help="dtype of hidden states on the gRPC wire (reference peers expect float16)")
-    parser.add_argument("--kv-pages", type=int, default=512)
+    parser.add_argument("--kv-pages", type=int, default=None,
+                        help="KV pool pages (default 512 for the gRPC servicer; 2048 in the native chain, where every stage must "
+                             "use the same pool geometry as the front end because block ids are global)")
     parser.add_argument("--page-size", type=int, default=64)
     parser.add_argument("--log-level", type=str, default="INFO")
     parser.add_argument("--rank", type=int, default=None, help="join the native chain pipeline as this rank")
@@ -88,10 +90,10 @@ def main(argv=None):
         if args.rank is not None:
             os.environ.update(RANK=str(args.rank), WORLD_SIZE=str(args.world_size or 1),
                               MASTER_ADDR=args.master_addr, MASTER_PORT=str(args.master_port))
-        serve_chain(args.model, args.start_layer, args.end_layer, args.device, dtype, args.kv_pages, args.page_size)
+        serve_chain(args.model, args.start_layer, args.end_layer, args.device, dtype, args.kv_pages or 2048, args.page_size)
     else:
         serve(args.model, args.start_layer, args.end_layer, args.port, args.device, dtype, args.wire_dtype,
-              args.kv_pages, args.page_size)
+              args.kv_pages or 512, args.page_size)
 
 
 if __name__ == "__main__":

@@ -122,3 +122,41 @@ def test_chat_completions_expert_parallel_group(tmp_path):
             except subprocess.TimeoutExpired:
                 os.killpg(proc.pid, signal.SIGKILL)
     assert answers[0] == answers[1] and [len(a) for a in answers[0]] == [6, 7, 8, 9]
+
+
+@pytest.mark.timeout(300)
+def test_manual_chain_launch_without_torchrun(tmp_path):
+    """The native chain can also be assembled by hand, reference-style: ``mlx-sharding-server --rank 1 --world-size 2`` for the
+    second stage and ``mlx-sharding-api`` with RANK / WORLD_SIZE in its environment as the front end (default KV pools match)."""
+    ckpt = write_synthetic_checkpoint(str(tmp_path / "tiny"), TINY_LLAMA, dtype=torch.float32)
+    env = dict(os.environ, PYTHONPATH=REPO, OMP_NUM_THREADS="1")
+    http_port, master_port = _free_port(), _free_port()
+    body = {"messages": [{"role": "user", "content": "manual chain"}], "max_tokens": 6, "temperature": 0, "logprobs": 1}
+    solo = subprocess.Popen([sys.executable, "-m", "shard.openai_api", "--model", ckpt, "--port", str(http_port), "--device", "cpu"],
+                            cwd=str(tmp_path), env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, start_new_session=True)
+    try:
+        _wait_http(http_port, solo)
+        _, ref = _post(http_port, body)
+    finally:
+        os.killpg(solo.pid, signal.SIGTERM)
+        solo.wait(timeout=20)
+    http_port = _free_port()
+    worker = subprocess.Popen([sys.executable, "-m", "shard.main", "--model", ckpt, "--device", "cpu", "--rank", "1", "--world-size", "2",
+                               "--master-port", str(master_port)], cwd=str(tmp_path), env=env, stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, start_new_session=True)
+    front = subprocess.Popen([sys.executable, "-m", "shard.openai_api", "--model", ckpt, "--port", str(http_port), "--device", "cpu"],
+                             cwd=str(tmp_path), env=dict(env, RANK="0", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(master_port)),
+                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, start_new_session=True)
+    try:
+        _wait_http(http_port, front)
+        status, got = _post(http_port, body)
+        assert status == 200
+        assert got["choices"][0]["logprobs"]["tokens"] == ref["choices"][0]["logprobs"]["tokens"]
+    finally:
+        for p in (front, worker):
+            os.killpg(p.pid, signal.SIGTERM)
+        for p in (front, worker):
+            try:
+                p.wait(timeout=20)
+            except subprocess.TimeoutExpired:
+                os.killpg(p.pid, signal.SIGKILL)
