@@ -92,10 +92,9 @@ class BatchMeta:
             last.append(cu[-1] - 1)
             ctx_after.append(c0 + ql)
         mb = max(max((len(p) for p in block_tables), default=1), pad_blocks_to, 1)
-        bt = torch.zeros(B, mb, dtype=torch.int32)
-        for b in range(B):
-            if len(block_tables[b]):
-                bt[b, : len(block_tables[b])] = torch.tensor(block_tables[b], dtype=torch.int32)
+        # one tensor construction for the whole (zero-padded) table: this runs on the host once per step per group
+        pad = [0] * mb
+        bt = torch.tensor([list(p) + pad[len(p):] for p in block_tables], dtype=torch.int32).reshape(B, mb)
         i32 = lambda x: torch.tensor(x, dtype=torch.int32)
         m = BatchMeta(i32(pos), i32(slots), i32(cu), i32(ctx_after), bt, i32(last), len(pos), B,
                       max(q_lens) if B else 0, max(ctx_after) if B else 0, page_size)
