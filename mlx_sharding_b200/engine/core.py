@@ -49,7 +49,7 @@ class StepOutput:
     top_logprobs: Optional[List[List[float]]] = None
 
 
-@dataclass
+@dataclass(slots=True)
 class TokenEvent:
     token: int
     logprob: float
@@ -70,7 +70,7 @@ class Request:
         self.eos_token_id = eos_token_id
         self.stop_id_sequences = stop_id_sequences or []
         self.output: List[int] = []
-        self.events: "queue.Queue[TokenEvent]" = queue.Queue()
+        self.events: "queue.SimpleQueue[TokenEvent]" = queue.SimpleQueue()   # C implementation: one put per generated token
         self.finished = False
         self.finish_reason: Optional[str] = None
         self.error: Optional[BaseException] = None
@@ -270,12 +270,13 @@ class LLMEngine:
                         mask.append(True)
             is_prefill = True
         else:
-            for r in reqs:
-                seqs.append(r)
-                q_lens.append(1)
-                ctx0.append(self.table.length[r.id])
-                toks.append(r.output[-1])
-                mask.append(True)
+            # pure decode step (the hot host path: runs once per generated token of the whole group)
+            length = self.table.length
+            seqs = reqs
+            q_lens = [1] * len(reqs)
+            ctx0 = [length[r.id] for r in reqs]
+            toks = [r.output[-1] for r in reqs]
+            mask = [True] * len(reqs)
             is_prefill = False
         bts = [self.table.pages[r.id] for r in seqs]
         # block-table width rounded up to a multiple of 8 so captured decode graphs (graph_decode.py) are reused
@@ -293,13 +294,14 @@ class LLMEngine:
         self.stats["finished"] += 1
 
     def _process(self, g: int, seqs: List[Request], q_lens: List[int], inp: StepInput, out: StepOutput):
+        length, n_decode = self.table.length, 0
         for b, r in enumerate(seqs):
             if inp.is_prefill and r.prefilled < len(r.prompt):
                 r.prefilled += q_lens[b]
                 self.stats["prefill_tokens"] += q_lens[b]
             else:
-                self.stats["decode_tokens"] += 1
-            self.table.advance(r.id, q_lens[b])
+                n_decode += 1
+            length[r.id] += q_lens[b]                      # == self.table.advance(r.id, q_lens[b])
             if inp.is_prefill and self.table.prefix is not None and r.cached_pages * self.page_size < len(r.prompt):
                 r.cached_pages = self.table.prefix.insert(r.prompt, self.table.pages[r.id], r.prefilled, r.cached_pages)
             if r.cancelled and not r.finished:
@@ -316,11 +318,13 @@ class LLMEngine:
             if r.params.logprobs > 0 and out.top_ids is not None:
                 k = r.params.logprobs
                 top = {int(i): float(l) for i, l in zip(out.top_ids[b][:k], out.top_logprobs[b][:k])}
-            stop, _ = stopping_criteria(r.output, r.stop_id_sequences, r.eos_token_id)
+            # (inlined fast path of stopping_criteria for the common no-stop-sequence case)
+            stop = tok == r.eos_token_id if not r.stop_id_sequences else stopping_criteria(r.output, r.stop_id_sequences, r.eos_token_id)[0]
             reason = "stop" if stop else ("length" if len(r.output) >= r.max_tokens else None)
             if reason:
                 self._finish(r, reason)
             r.events.put(TokenEvent(tok, float(out.logprobs[b]), top, reason is not None, reason))
+        self.stats["decode_tokens"] += n_decode
         self.groups[g] = [r for r in self.groups[g] if not r.finished]
 
     def step(self):

@@ -14,6 +14,7 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import List, Sequence
 
+import numpy as np
 import torch
 
 
@@ -76,6 +77,12 @@ class BatchMeta:
               page_size: int, device="cpu", pad_blocks_to: int = 0) -> "BatchMeta":
         """Build from per-sequence query lengths, already-cached lengths and page lists."""
         B = len(q_lens)
+        if B and max(q_lens) == 1 and min(q_lens) == 1:
+            # decode step: one token per sequence — no per-token inner loop (host fast path, once per generated token)
+            pos = [int(c) for c in ctx_before]
+            slots = [block_tables[b][p // page_size] * page_size + p % page_size for b, p in enumerate(pos)]
+            cu, last, ctx_after = list(range(B + 1)), list(range(B)), [p + 1 for p in pos]
+            return BatchMeta._finish_build(pos, slots, cu, ctx_after, last, q_lens, block_tables, page_size, device, pad_blocks_to)
         pos: List[int] = []
         slots: List[int] = []
         cu = [0]
@@ -91,11 +98,17 @@ class BatchMeta:
             cu.append(cu[-1] + ql)
             last.append(cu[-1] - 1)
             ctx_after.append(c0 + ql)
+        return BatchMeta._finish_build(pos, slots, cu, ctx_after, last, q_lens, block_tables, page_size, device, pad_blocks_to)
+
+    @staticmethod
+    def _finish_build(pos, slots, cu, ctx_after, last, q_lens, block_tables, page_size, device, pad_blocks_to) -> "BatchMeta":
+        B = len(q_lens)
         mb = max(max((len(p) for p in block_tables), default=1), pad_blocks_to, 1)
         # one tensor construction for the whole (zero-padded) table: this runs on the host once per step per group
         pad = [0] * mb
-        bt = torch.tensor([list(p) + pad[len(p):] for p in block_tables], dtype=torch.int32).reshape(B, mb)
-        i32 = lambda x: torch.tensor(x, dtype=torch.int32)
+        # (numpy converts nested Python lists about twice as fast as torch.tensor)
+        i32 = lambda x: torch.from_numpy(np.array(x, dtype=np.int32))
+        bt = i32([list(p) + pad[len(p):] for p in block_tables]).reshape(B, mb)
         m = BatchMeta(i32(pos), i32(slots), i32(cu), i32(ctx_after), bt, i32(last), len(pos), B,
                       max(q_lens) if B else 0, max(ctx_after) if B else 0, page_size)
         return m.to(device) if str(device) != "cpu" else m
