@@ -21,7 +21,7 @@ import torch
 
 from ..engine.core import StepInput, StepOutput
 from ..engine.kv_cache import PagedKVCache
-from ..engine.sampler import Sampler
+from ..engine.sampler import Sampler, SamplingParams
 from ..ops.meta import BatchMeta
 
 log = logging.getLogger(__name__)
@@ -130,9 +130,31 @@ class LocalPipeline:
 # -------------------------------------------------------------------------------------------------
 # Cross-process chain
 # -------------------------------------------------------------------------------------------------
+_GREEDY = SamplingParams()   # shared instance for the compact control message
+
+
+def _plain_greedy(p: SamplingParams) -> bool:
+    return (p.temperature == 0 and p.top_p == 1.0 and p.repetition_penalty in (0, 1.0) and not p.logit_bias and p.logprobs == 0
+            and p.seed is None)
+
+
 def _ctrl_of(inp: StepInput) -> dict:
+    """Per-step control message that travels down the chain (pickled, gloo).  The common case — every sequence decodes greedily
+    with default parameters — is sent as a count instead of B parameter objects + B empty contexts (half the bytes and less
+    than half the (un)pickling time per hop, which sits on every stage's critical path)."""
+    if all(_plain_greedy(p) for p in inp.params):
+        return dict(kind="step", group=inp.group, meta=inp.meta.pack(), params=len(inp.params), contexts=None,
+                    is_prefill=inp.is_prefill)
     return dict(kind="step", group=inp.group, meta=inp.meta.pack(), params=inp.params, contexts=inp.contexts,
                 is_prefill=inp.is_prefill)
+
+
+def _params_of(ctrl: dict):
+    """(params, contexts) of a control message (expands the compact greedy form)."""
+    p = ctrl["params"]
+    if isinstance(p, int):
+        return [_GREEDY] * p, [[]] * p
+    return p, ctrl["contexts"]
 
 
 class ChainPipeline:
@@ -219,7 +241,8 @@ def worker_loop(stage: StageExecutor, transport):
                 tp.send_ctrl(ctrl, rank + 1)
             continue
         meta = BatchMeta.unpack(ctrl["meta"])
-        graphed = gcache.eligible(meta, ctrl["params"])
+        params, contexts = _params_of(ctrl)
+        graphed = gcache.eligible(meta, params)
         if graphed:
             e = gcache.entry(meta.num_seqs, meta.block_tables.shape[1], meta.max_ctx_len)
             x = tp.recv_tensor((meta.num_tokens, H), stage.model.dtype, rank - 1, slot=ctrl["group"], out=e.x)
@@ -237,7 +260,7 @@ def worker_loop(stage: StageExecutor, transport):
             else:
                 out = stage.forward(x, meta.to(stage.device))
             if last:
-                res = stage.sample(out, ctrl["params"], ctrl["contexts"])
+                res = stage.sample(out, params, contexts)
                 tp.send_ctrl(dict(tokens=res.tokens, logprobs=res.logprobs, top_ids=res.top_ids,
                                   top_logprobs=res.top_logprobs), 0)
             else:

@@ -78,18 +78,32 @@ class TorchDistTransport(ChainTransport):
         self._pending = []
 
     # control plane ------------------------------------------------------------------------------
+    # One gloo message per control object: a fixed-size frame [u32 length | pickle | padding].  Objects that do not fit are
+    # announced by the frame (length with the top bit set) and follow in a second, exactly-sized message.
+    CTRL_FRAME = 16384
+
     def send_ctrl(self, obj, dst: int):
-        payload = torch.frombuffer(bytearray(pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)), dtype=torch.uint8)
-        n = torch.tensor([payload.numel()], dtype=torch.int64)
-        self._isend(n, dst, self.ctrl_group)
-        self._isend(payload, dst, self.ctrl_group)
+        raw = pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
+        n = len(raw)
+        frame = torch.zeros(self.CTRL_FRAME, dtype=torch.uint8)
+        if n <= self.CTRL_FRAME - 4:
+            frame[:4] = torch.frombuffer(bytearray(n.to_bytes(4, "little")), dtype=torch.uint8)
+            frame[4:4 + n] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+            self._isend(frame, dst, self.ctrl_group)
+            return
+        frame[:4] = torch.frombuffer(bytearray((n | 0x80000000).to_bytes(4, "little")), dtype=torch.uint8)
+        self._isend(frame, dst, self.ctrl_group)
+        self._isend(torch.frombuffer(bytearray(raw), dtype=torch.uint8), dst, self.ctrl_group)
 
     def recv_ctrl(self, src: int):
-        n = torch.zeros(1, dtype=torch.int64)
-        dist.recv(n, src, group=self.ctrl_group)
-        buf = torch.empty(int(n.item()), dtype=torch.uint8)
-        dist.recv(buf, src, group=self.ctrl_group)
-        return pickle.loads(buf.numpy().tobytes())
+        frame = torch.empty(self.CTRL_FRAME, dtype=torch.uint8)
+        dist.recv(frame, src, group=self.ctrl_group)
+        n = int.from_bytes(frame[:4].numpy().tobytes(), "little")
+        if n & 0x80000000:
+            buf = torch.empty(n & 0x7FFFFFFF, dtype=torch.uint8)
+            dist.recv(buf, src, group=self.ctrl_group)
+            return pickle.loads(buf.numpy().tobytes())
+        return pickle.loads(frame[4:4 + n].numpy().tobytes())
 
     # data plane ---------------------------------------------------------------------------------
     def send_tensor(self, t: torch.Tensor, dst: int, slot: int = 0):

@@ -82,3 +82,41 @@ def test_gloo_chain_matches_single_process(world, half):
     for p, g in zip(prompts, got):
         ref = [int(o.argmax()) for o in run_sequence([full], p, n_new - 1)]
         assert g == ref
+
+
+def _ctrl_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from mlx_sharding_b200.parallel.transport import TorchDistTransport
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tp = TorchDistTransport("cpu")
+    msgs = [dict(kind="step", n=1), dict(blob=list(range(20000))), "x" * (tp.CTRL_FRAME - 4 - 20), dict(t=torch.arange(7))]
+    if rank == 0:
+        for m in msgs:
+            tp.send_ctrl(m, 1)
+        tp.flush()
+        q.put(tp.recv_ctrl(1))
+    else:
+        got = [tp.recv_ctrl(0) for _ in msgs]
+        ok = got[0] == msgs[0] and got[1] == msgs[1] and got[2] == msgs[2] and torch.equal(got[3]["t"], msgs[3]["t"])
+        tp.send_ctrl(ok, 0)
+        tp.flush()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_control_messages_small_and_large_frames():
+    """Control objects travel as one fixed-size gloo frame; objects larger than the frame use the announced second message."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ctrl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    assert q.get(timeout=90) is True
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
