@@ -451,32 +451,39 @@ def run_ep(args, world, rank, local, dev):
 
     e2e = None
     if not args.no_e2e:
-        # every rank drives its own LLMEngine over the same request shapes, so the engines step in lockstep
-        pipe = LocalPipeline([stage])
-        eng = LLMEngine(pipe, num_pages, PS, num_groups=1, max_seqs_per_group=B, max_prefill_tokens=chunk_seqs * S)
-        n_new = total_steps + 1
-        reqs = [eng.submit(prompts[b].tolist(), SamplingParams(temperature=0.0), max_tokens=n_new) for b in range(B)]
-        while any(r.prefilled < len(r.prompt) for r in reqs) or min(len(r.output) for r in reqs) < args.warmup:
-            eng.step()
-        torch.cuda.synchronize()
-        dist.barrier()
-        h2d0, d2h0 = pipe.h2d_bytes, pipe.d2h_bytes
-        n0 = sum(len(r.output) for r in reqs)
-        tt = time.perf_counter()
-        steps = 0
-        while min(len(r.output) for r in reqs) < total_steps:
-            eng.step()
-            steps += 1
-        torch.cuda.synchronize()
-        dt = max_over_ranks(time.perf_counter() - tt)
-        n1 = sum(len(r.output) for r in reqs)
-        eng.drain()
-        steps = max(steps, 1)
-        e2e = {"value": round(world * (n1 - n0) / dt, 1), "unit": "tokens/s", "steps": steps, "ms_per_step": round(dt * 1e3 / steps, 4),
-               "h2d_bytes_per_step": int(world * (pipe.h2d_bytes - h2d0) / steps),
-               "d2h_bytes_per_step": int(world * (pipe.d2h_bytes - d2h0) / steps),
-               "path": "one LLMEngine.submit/step per rank -> LocalPipeline (pinned H2D of token ids + step metadata, D2H of sampled ids); "
-                       "wall time = max over ranks, bytes summed over ranks"}
+        try:
+            # every rank drives its own LLMEngine over the same request shapes, so the engines step in lockstep
+            pipe = LocalPipeline([stage])
+            eng = LLMEngine(pipe, num_pages, PS, num_groups=1, max_seqs_per_group=B, max_prefill_tokens=chunk_seqs * S)
+            n_new = total_steps + 1
+            reqs = [eng.submit(prompts[b].tolist(), SamplingParams(temperature=0.0), max_tokens=n_new) for b in range(B)]
+            while any(r.prefilled < len(r.prompt) for r in reqs) or min(len(r.output) for r in reqs) < args.warmup:
+                eng.step()
+            torch.cuda.synchronize()
+            dist.barrier()
+            h2d0, d2h0 = pipe.h2d_bytes, pipe.d2h_bytes
+            n0 = sum(len(r.output) for r in reqs)
+            tt = time.perf_counter()
+            steps = 0
+            while min(len(r.output) for r in reqs) < total_steps:
+                eng.step()
+                steps += 1
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - tt)
+            n1 = sum(len(r.output) for r in reqs)
+            eng.drain()
+            steps = max(steps, 1)
+            e2e = {"value": round(world * (n1 - n0) / dt, 1), "unit": "tokens/s", "steps": steps, "ms_per_step": round(dt * 1e3 / steps, 4),
+                   "h2d_bytes_per_step": int(world * (pipe.h2d_bytes - h2d0) / steps),
+                   "d2h_bytes_per_step": int(world * (pipe.d2h_bytes - d2h0) / steps),
+                   "path": "one LLMEngine.submit/step per rank -> LocalPipeline (pinned H2D of token ids + step metadata, D2H of sampled ids); "
+                           "wall time = max over ranks, bytes summed over ranks"}
+        except Exception as e:  # noqa: BLE001 — (symmetric) failure of the engine path: keep the device-timed result
+            import traceback
+
+            traceback.print_exc()
+            e2e = {"error": f"{type(e).__name__}: {e}"}
+
     dist.barrier()
     if rank == 0:
         res = {
@@ -524,31 +531,46 @@ def run_e2e(args, stage, world, rank, dev, cfg, prompts, G, B, S, num_pages, PS)
     else:
         pipe = LocalPipeline([stage])
     eng = LLMEngine(pipe, num_pages, PS, num_groups=G, max_seqs_per_group=B, max_prefill_tokens=B * S)
-    n_new = args.warmup + args.steps + 1
-    reqs = [eng.submit(prompts[g, b].tolist(), SamplingParams(temperature=0.0), max_tokens=n_new)
-            for g in range(G) for b in range(B)]
-    # prefill + warm-up decode steps (untimed)
-    while any(r.prefilled < len(r.prompt) for r in reqs) or min(len(r.output) for r in reqs) < args.warmup:
-        eng.step()
-    torch.cuda.synchronize()
-    h2d0, d2h0 = pipe.h2d_bytes, pipe.d2h_bytes
-    n0 = sum(len(r.output) for r in reqs)
-    t0 = time.perf_counter()
-    steps = 0
-    while min(len(r.output) for r in reqs) < args.warmup + args.steps:
-        eng.step()
-        steps += 1
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    n1 = sum(len(r.output) for r in reqs)
-    eng.drain()
-    if world > 1:
-        pipe.shutdown()
-    steps = max(steps, 1)
-    return {"value": round((n1 - n0) / dt, 1), "unit": "tokens/s", "steps": steps,
-            "ms_per_step": round(dt * 1e3 / steps, 4),
-            "h2d_bytes_per_step": int((pipe.h2d_bytes - h2d0) / steps), "d2h_bytes_per_step": int((pipe.d2h_bytes - d2h0) / steps),
-            "path": "LLMEngine.submit/step -> " + type(pipe).__name__ + " (pinned H2D of token ids + step metadata, D2H of sampled ids)"}
+    try:
+        n_new = args.warmup + args.steps + 1
+        reqs = [eng.submit(prompts[g, b].tolist(), SamplingParams(temperature=0.0), max_tokens=n_new)
+                for g in range(G) for b in range(B)]
+
+        def failed():
+            bad = [r for r in reqs if r.error is not None]
+            if bad:
+                raise RuntimeError(f"{len(bad)} request(s) failed: {bad[0].error!r}")
+
+        # prefill + warm-up decode steps (untimed)
+        while any(r.prefilled < len(r.prompt) for r in reqs) or min(len(r.output) for r in reqs) < args.warmup:
+            eng.step()
+            failed()
+        torch.cuda.synchronize()
+        h2d0, d2h0 = pipe.h2d_bytes, pipe.d2h_bytes
+        n0 = sum(len(r.output) for r in reqs)
+        t0 = time.perf_counter()
+        steps = 0
+        while min(len(r.output) for r in reqs) < args.warmup + args.steps:
+            eng.step()
+            steps += 1
+            failed()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        n1 = sum(len(r.output) for r in reqs)
+        eng.drain()
+        steps = max(steps, 1)
+        return {"value": round((n1 - n0) / dt, 1), "unit": "tokens/s", "steps": steps,
+                "ms_per_step": round(dt * 1e3 / steps, 4),
+                "h2d_bytes_per_step": int((pipe.h2d_bytes - h2d0) / steps), "d2h_bytes_per_step": int((pipe.d2h_bytes - d2h0) / steps),
+                "path": "LLMEngine.submit/step -> " + type(pipe).__name__ + " (pinned H2D of token ids + step metadata, D2H of sampled ids)"}
+    except Exception as e:  # noqa: BLE001 — the device-timed numbers of this run are still reported
+        import traceback
+
+        traceback.print_exc()
+        return {"error": f"{type(e).__name__}: {e}"}
+    finally:
+        if world > 1:
+            pipe.shutdown()   # always release the stage workers of the other ranks
 
 
 if __name__ == "__main__":
