@@ -173,3 +173,65 @@ def test_mixed_batches_keep_running_streams_decoding_during_prefill():
         assert produced_before > 0
     assert outs[False][:2] == outs[True][:2]
     assert outs[True][2] <= 1 < outs[False][2]          # separate phases stall the running stream for the whole prefill
+
+
+def test_scheduler_stress_random_traffic_keeps_invariants():
+    """Randomised traffic against the scheduler alone (a fake pipeline returns deterministic tokens): arrivals between steps,
+    cancellations, EOS / stop sequences, tight KV pool, prefix cache + mixed batches on.  Every request must terminate with a
+    legal reason, never exceed max_tokens, and all pages must be back (free or evictable) at the end."""
+    import random
+
+    from mlx_sharding_b200.engine.core import StepOutput
+
+    class FakePipe:
+        num_stages = 1
+
+        def submit(self, inp):
+            # token = f(sequence id, position): deterministic, occasionally the EOS id 1
+            toks = [(sid * 7 + int(c)) % 13 + 1 for sid, c in zip(inp.seq_ids, inp.meta.context_lens.tolist())]
+            assert inp.meta.num_tokens == inp.tokens.numel() and max(inp.meta.slot_mapping.tolist()) < 40 * 4
+            assert len(set(inp.meta.slot_mapping.tolist())) == inp.meta.num_tokens      # no two tokens share a KV slot
+            return StepOutput(toks, [0.0] * len(toks))
+
+        def wait(self, h):
+            return h
+
+        def reset(self):
+            pass
+
+    for seed in range(6):
+        rnd = random.Random(seed)
+        eng = LLMEngine(FakePipe(), num_pages=40, page_size=4, num_groups=rnd.choice([1, 2]), max_seqs_per_group=rnd.choice([2, 5]),
+                        max_prefill_tokens=rnd.choice([3, 8, 64]), prefix_cache=rnd.random() < 0.7, mixed_batches=rnd.random() < 0.5)
+        live, done = [], []
+        system = [rnd.randrange(20, 30) for _ in range(9)]
+        for it in range(400):
+            if rnd.random() < 0.25 and len(live) < 12:
+                prompt = (system if rnd.random() < 0.5 else []) + [rnd.randrange(20, 60) for _ in range(rnd.randrange(1, 14))]
+                r = eng.submit(prompt, SamplingParams(temperature=0.0), max_tokens=rnd.randrange(1, 12),
+                               eos_token_id=1 if rnd.random() < 0.5 else None,
+                               stop_id_sequences=[[5, 6]] if rnd.random() < 0.2 else None)
+                live.append(r)
+            if live and rnd.random() < 0.05:
+                rnd.choice(live).cancel()
+            eng.step()
+            for r in list(live):
+                if r.finished:
+                    live.remove(r)
+                    done.append(r)
+        for r in live:
+            r.cancel()
+        eng.drain()
+        done += live
+        assert done and all(r.finished for r in done)
+        for r in done:
+            assert r.error is None or isinstance(r.error, MemoryError)
+            if r.error is None:
+                assert r.finish_reason in ("stop", "length", "cancelled") and len(r.output) <= r.max_tokens
+                if r.finish_reason == "length":
+                    assert len(r.output) == r.max_tokens
+                if r.finish_reason == "stop":
+                    assert r.output[-1] == r.eos_token_id or r.output[-2:] == [5, 6]
+        assert not eng.table.pages and eng.table.alloc.num_free == 40 - 1
+        if eng.table.prefix is not None:
+            assert all(v == 0 for v in eng.table.prefix.refs.values())
