@@ -613,13 +613,15 @@ def run_e2e(args, stage, world, rank, dev, cfg, prompts, G, B, S, num_pages, PS)
 
     # fresh KV space: pages of the device-timed phase are simply reused (engine has its own allocator)
     if world > 1:
-        from mlx_sharding_b200.parallel.transport import TorchDistTransport
+        from mlx_sharding_b200.parallel.pipeline import build_chain
 
-        tp = TorchDistTransport(dev, data_backend="nccl")
+        # the serving chain: shared-memory launch ring + (default) fused P2P hand-off, one CUDA-graph replay per stage per step
+        ctl, plane = build_chain(stage, num_groups=G, max_tokens=B * S, max_seqs=B,
+                                 transport="auto" if args.transport == "auto" else args.transport)
         if rank != 0:
-            worker_loop(stage, tp)
+            worker_loop(stage, ctl, plane)
             return None
-        pipe = ChainPipeline(stage, tp)
+        pipe = ChainPipeline(stage, ctl, plane)
     else:
         pipe = LocalPipeline([stage])
     eng = LLMEngine(pipe, num_pages, PS, num_groups=G, max_seqs_per_group=B, max_prefill_tokens=B * S)
@@ -657,7 +659,9 @@ def run_e2e(args, stage, world, rank, dev, cfg, prompts, G, B, S, num_pages, PS)
                 "ms_per_step": round(dt * 1e3 / steps, 4),
                 "h2d_bytes_per_step": int((h2d1 - h2d0) / steps), "d2h_bytes_per_step": int((d2h1 - d2h0) / steps),
                 "ttft_p50_ms": ttft, "ttft_requests": TTFT_REQUESTS,
-                "path": "LLMEngine.submit/step -> " + type(pipe).__name__ + " (pinned H2D of token ids + step metadata, D2H of sampled ids)"}
+                "path": "LLMEngine.submit/step -> " + type(pipe).__name__ + (f" [{pipe.plane.name} hand-off, {type(pipe.ctl).__name__}]" if world > 1 else "")
+                        + " (per step: pinned H2D of the step block = token ids + metadata + sampling block on every stage, D2H of the result message on stage 0)",
+                "graph_replays": pipe.gcache.replays if pipe.gcache is not None else 0}
     except Exception as e:  # noqa: BLE001 — the device-timed numbers of this run are still reported
         import traceback
 

@@ -39,6 +39,7 @@ class StepInput:
     contexts: List[List[int]]       # repetition-penalty context per sequence
     sample_mask: List[bool]         # False for non-final prefill chunks
     is_prefill: bool
+    rng: Optional[List[tuple]] = None   # per sequence: (seed, tokens sampled so far) — the sampler's random stream of that request
 
 
 @dataclass
@@ -78,6 +79,9 @@ class Request:
         self.t_submit = time.perf_counter()
         self.t_first: Optional[float] = None
         self.t_done: Optional[float] = None
+        # random stream of this request: its own seed if given, else derived from the request id (reproducible per request,
+        # independent of the batch it decodes in)
+        self.seed = (int(params.seed) if params.seed is not None else (0x9E3779B1 * (self.id + 1))) & 0x7FFFFFFFFFFFFFFF
         self.prefilled = 0            # prompt tokens already in the KV cache
         self.cached_pages = 0         # leading pages of this request that are registered in the prefix cache
 
@@ -148,6 +152,12 @@ class LLMEngine:
             raise ValueError(f"prompt ({len(prompt)}) + max_tokens ({max_tokens}) exceeds max_model_len "
                              f"({self.max_model_len})")
         r = Request(prompt, params, max_tokens, eos_token_id, stop_id_sequences)
+        if r.max_tokens <= 0:
+            # the reference's ``zip(generate_step(...), range(max_tokens))`` yields nothing (openai_api.py:370-381): no forward pass
+            r.finished, r.finish_reason = True, "length"
+            r.t_done = time.perf_counter()
+            r.events.put(None)
+            return r
         self.waiting.put(r)
         self._wake.set()
         return r
@@ -173,11 +183,26 @@ class LLMEngine:
         return self
 
     def shutdown(self):
+        """Stop the loop and fail every request that is still queued or running, so no caller stays blocked in
+        ``for ev in request`` (the reference has no such path: its handlers own the generation loop, openai_api.py:370-381)."""
         self._stop.set()
         self._wake.set()
         if self._thread is not None:
             self._thread.join(timeout=10)
             self._thread = None
+        err = RuntimeError("engine shut down")
+        while True:
+            try:
+                r = self.waiting.get_nowait()
+            except queue.Empty:
+                break
+            r.error, r.finished = err, True
+            r.events.put(None)
+        if any(self.groups) or any(h is not None for h in self.inflight):
+            self._fail_all(err)
+
+    def busy(self) -> bool:
+        return self.has_work()
 
     # -------------------------------------------------------------------------- scheduling
     def has_work(self) -> bool:
@@ -195,17 +220,20 @@ class LLMEngine:
                 self._fail_all(e)
 
     def _fail_all(self, e: BaseException):
+        # first let the pipeline drain every step that is still in flight (other groups' steps keep writing KV on the downstream
+        # stages until they complete) and drop their results — only then may the pages go back to the allocator
         for g in range(self.num_groups):
             self.inflight[g] = None
+        try:
+            self.pipe.reset()
+        except Exception:
+            pass
+        for g in range(self.num_groups):
             for r in self.groups[g]:
                 r.error, r.finished = e, True
                 self.table.release(r.id)
                 r.events.put(None)
             self.groups[g] = []
-        try:
-            self.pipe.reset()
-        except Exception:
-            pass
 
     def _admit(self):
         while True:
@@ -285,7 +313,7 @@ class LLMEngine:
         ctxs = [(r.prompt + r.output)[-max(1, r.params.repetition_context_size):]
                 if r.params.repetition_penalty not in (0, 1.0) else [] for r in seqs]
         return StepInput(g, [r.id for r in seqs], torch.tensor(toks, dtype=torch.int64), meta,
-                         [r.params for r in seqs], ctxs, mask, is_prefill), seqs, q_lens
+                         [r.params for r in seqs], ctxs, mask, is_prefill, [(r.seed, len(r.output)) for r in seqs]), seqs, q_lens
 
     def _finish(self, r: Request, reason: str):
         r.finished, r.finish_reason = True, reason

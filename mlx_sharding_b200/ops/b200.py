@@ -267,6 +267,17 @@ def sample(logits, temperature, top_p, generator: Optional[torch.Generator] = No
     return toks, lp, None, None
 
 
+def sample_block(logits, sv, tag_out, toks_out, lp_out, top_ids_out, top_lp_out):
+    """Sampling driven by a step block in device memory (``parallel/graph_decode.py``): every per-step input — temperatures,
+    nucleus thresholds, per-request (seed, step) RNG state, penalty contexts, bias tables, the step tag — is read by the kernels
+    from the block, so the same captured CUDA graph serves greedy and sampled requests."""
+    logits = logits.contiguous()
+    if sv.has_pen:
+        C().apply_penalties_(logits, sv.rep, sv.penalty, sv.bidx, sv.bval)
+    k = 0 if top_ids_out is None else int(top_ids_out.shape[1])
+    C().sample_into(logits, sv.temps, sv.top_p, sv.rng, k, toks_out, lp_out, top_ids_out, top_lp_out, sv.tag, tag_out)
+
+
 def mla_rope_kv_write(q, k_pe, kv, kpool, vpool, meta: BatchMeta, spec: RopeSpec, nope: int, vdim: int):
     if not spec.interleaved:
         raise NotImplementedError("fused MLA prologue expects interleaved (traditional) rope pairs")

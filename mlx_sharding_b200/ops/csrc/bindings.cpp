@@ -445,10 +445,32 @@ std::vector<Tensor> sample(const Tensor& logits, const Tensor& temperature, cons
   Tensor top_ids = torch::empty({B, top_k}, torch::dtype(torch::kInt64).device(dev));
   Tensor top_lp = torch::empty({B, top_k}, torch::dtype(torch::kFloat32).device(dev));
   LAUNCH_OK(b200::sample_launch(logits.data_ptr<float>(), B, (int)logits.size(1), temperature.data_ptr<float>(), top_p.data_ptr<float>(),
-                              (unsigned long long)seed, (unsigned long long)step, reinterpret_cast<long long*>(tokens.data_ptr<int64_t>()),
+                              (unsigned long long)seed, (unsigned long long)step, nullptr, reinterpret_cast<long long*>(tokens.data_ptr<int64_t>()),
                               lp.data_ptr<float>(), (int)top_k, reinterpret_cast<long long*>(top_ids.data_ptr<int64_t>()),
-                              top_lp.data_ptr<float>(), cur_stream()));
+                              top_lp.data_ptr<float>(), nullptr, nullptr, cur_stream()));
   return {tokens, lp, top_ids, top_lp};
+}
+
+// Graph-replay-safe sampler: every per-step input (temperature, top-p, per-row RNG state, step tag) lives in device memory and the
+// outputs go to caller-owned buffers (views into the result message that travels back to stage 0).
+void sample_into(const Tensor& logits, const Tensor& temperature, const Tensor& top_p, const Tensor& row_rng, int64_t top_k,
+                 Tensor tokens, Tensor lp, const c10::optional<Tensor>& top_ids, const c10::optional<Tensor>& top_lp,
+                 const c10::optional<Tensor>& tag_src, const c10::optional<Tensor>& tag_dst) {
+  TORCH_CHECK(logits.is_cuda() && logits.scalar_type() == torch::kFloat32 && logits.is_contiguous());
+  TORCH_CHECK(row_rng.scalar_type() == torch::kInt64 && row_rng.is_contiguous() && row_rng.numel() >= 2 * logits.size(0));
+  TORCH_CHECK(tokens.scalar_type() == torch::kInt64 && lp.scalar_type() == torch::kFloat32);
+  TORCH_CHECK(top_k == 0 || (top_ids.has_value() && top_lp.has_value()), "top_k > 0 needs top_ids / top_lp buffers");
+  TORCH_CHECK(tag_src.has_value() == tag_dst.has_value());
+  if (tag_src.has_value())
+    TORCH_CHECK(tag_src->numel() * tag_src->element_size() >= 16 && tag_dst->numel() * tag_dst->element_size() >= 16 &&
+                reinterpret_cast<uintptr_t>(tag_src->data_ptr()) % 16 == 0 && reinterpret_cast<uintptr_t>(tag_dst->data_ptr()) % 16 == 0);
+  const c10::cuda::CUDAGuard guard(logits.device());
+  LAUNCH_OK(b200::sample_launch(logits.data_ptr<float>(), (int)logits.size(0), (int)logits.size(1), temperature.data_ptr<float>(),
+                              top_p.data_ptr<float>(), 0ull, 0ull, reinterpret_cast<const unsigned long long*>(row_rng.data_ptr<int64_t>()),
+                              reinterpret_cast<long long*>(tokens.data_ptr<int64_t>()), lp.data_ptr<float>(), (int)top_k,
+                              top_k ? reinterpret_cast<long long*>(top_ids->data_ptr<int64_t>()) : nullptr,
+                              top_k ? top_lp->data_ptr<float>() : nullptr, tag_src.has_value() ? tag_src->data_ptr() : nullptr,
+                              tag_dst.has_value() ? tag_dst->data_ptr() : nullptr, cur_stream()));
 }
 
 // ---- P2P / IPC --------------------------------------------------------------------------------------------------
@@ -599,6 +621,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("out") = py::none(), py::arg("top_k"), py::arg("signal_flag_ptr") = 0, py::arg("signal_value") = 0);
   m.def("apply_penalties_", &apply_penalties_);
   m.def("sample", &sample);
+  m.def("sample_into", &sample_into, py::arg("logits"), py::arg("temperature"), py::arg("top_p"), py::arg("row_rng"), py::arg("top_k"),
+        py::arg("tokens"), py::arg("logprobs"), py::arg("top_ids") = py::none(), py::arg("top_lp") = py::none(),
+        py::arg("tag_src") = py::none(), py::arg("tag_dst") = py::none());
   m.def("ipc_alloc", &ipc_alloc);
   m.def("ipc_open", &ipc_open);
   m.def("enable_peer_access", &enable_peer_access);

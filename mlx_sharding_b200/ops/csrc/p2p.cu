@@ -3,6 +3,8 @@
 // cannot ride a GEMM epilogue, and the on-device step-metadata advance that lets a CUDA-graphed decode
 // step re-run without any host -> device traffic.  The reference's equivalent is a blocking gRPC unary
 // call per stage per token with host staging (shard/utils.py:71-90,162-164).
+#include <cstdlib>
+
 #include "kernels.h"
 #include "launch.h"
 #include "ptx.cuh"
@@ -43,6 +45,9 @@ __global__ void wait_flag_counter_kernel(const uint32_t* flag, uint32_t* local_c
   while (true) {
     const uint32_t v = ld_acquire_sys(flag);
     if ((int32_t)(v - expected) >= 0) break;
+    // a wait that already timed out on this device poisons the following ones: they return at once instead of
+    // serialising one full timeout per queued step (the host reads the error word and fails the requests)
+    if (error_flag != nullptr && *reinterpret_cast<volatile uint32_t*>(error_flag) != 0u) break;
     if (globaltimer_ns() - t0 > timeout_ns) {
       if (error_flag != nullptr) atomicExch(error_flag, 1u);
       break;
@@ -89,13 +94,23 @@ __global__ void advance_meta_kernel(int* positions, int* context_lens, int* slot
 
 }  // namespace
 
+// bounded spin of the flag waits: MLXB200_P2P_TIMEOUT_S (default 20 s)
+static unsigned long long wait_timeout_ns() {
+  static const unsigned long long ns = [] {
+    const char* e = std::getenv("MLXB200_P2P_TIMEOUT_S");
+    const double sec = (e != nullptr && std::atof(e) > 0.0) ? std::atof(e) : 20.0;
+    return static_cast<unsigned long long>(sec * 1e9);
+  }();
+  return ns;
+}
+
 cudaError_t wait_flag_launch(const uint32_t* flag, uint32_t expected, uint32_t* error_flag, cudaStream_t s) {
-  (void)launch_pdl(wait_flag_kernel, dim3(1), dim3(1), 0, s, flag, expected, error_flag, 20ull * 1000ull * 1000ull * 1000ull);
+  (void)launch_pdl(wait_flag_kernel, dim3(1), dim3(1), 0, s, flag, expected, error_flag, wait_timeout_ns());
   return cudaGetLastError();
 }
 
 cudaError_t wait_flag_counter_launch(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag, cudaStream_t s) {
-  (void)launch_pdl(wait_flag_counter_kernel, dim3(1), dim3(1), 0, s, flag, local_counter, error_flag, 20ull * 1000ull * 1000ull * 1000ull);
+  (void)launch_pdl(wait_flag_counter_kernel, dim3(1), dim3(1), 0, s, flag, local_counter, error_flag, wait_timeout_ns());
   return cudaGetLastError();
 }
 

@@ -58,9 +58,21 @@ __device__ float block_sum(float x, float* sm) {
 
 __global__ void __launch_bounds__(kSampThreads)
 sample_kernel(const float* __restrict__ logits, int V, const float* __restrict__ temperature, const float* __restrict__ top_p,
-              unsigned long long seed, unsigned long long step, long long* __restrict__ tokens, float* __restrict__ logprobs,
-              int top_k, long long* __restrict__ top_ids, float* __restrict__ top_lp) {
+              unsigned long long seed, unsigned long long step, const unsigned long long* __restrict__ row_rng,
+              long long* __restrict__ tokens, float* __restrict__ logprobs, int top_k, long long* __restrict__ top_ids,
+              float* __restrict__ top_lp, const uint4* __restrict__ tag_src, uint4* __restrict__ tag_dst) {
   pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
+  // Random stream of a row: (seed, step) launch scalars, or — for CUDA-graph replay, where scalars are frozen at capture — a
+  // per-row (seed, step) pair in device memory (`row_rng[b]` = request seed, number of tokens that request has sampled so far:
+  // a request's stream is then independent of which batch / row it decodes in).
+  uint32_t rng_row = blockIdx.x;
+  if (row_rng != nullptr) {
+    seed = row_rng[2 * blockIdx.x];
+    step = row_rng[2 * blockIdx.x + 1];
+    rng_row = 0;
+  }
+  // 16-byte tag (step id of the scheduler) copied next to the results so the receiver can match result <-> step
+  if (tag_dst != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *tag_dst = *tag_src;
   __shared__ ArgMax sm_a[kSampThreads / 32];
   __shared__ float sm_f[kSampThreads / 32];
   const int b = blockIdx.x;
@@ -107,7 +119,7 @@ sample_kernel(const float* __restrict__ logits, int V, const float* __restrict__
     for (int i = threadIdx.x; i < V; i += kSampThreads) {
       const float x = lg[i];
       if (x > thresh) {
-        const float u = uniform01(seed, step, b, i);
+        const float u = uniform01(seed, step, rng_row, i);
         const float g = -__logf(-__logf(u));
         gm = better(gm, ArgMax{(x - am.v) * inv_t + g, i});
       }
@@ -172,11 +184,13 @@ cudaError_t apply_penalties_launch(float* logits, int B, int V, const int* rep_c
 }
 
 cudaError_t sample_launch(const float* logits, int B, int V, const float* temperature, const float* top_p,
-                          unsigned long long seed, unsigned long long step, long long* tokens, float* logprobs, int top_k,
-                          long long* top_ids, float* top_lp, cudaStream_t s) {
+                          unsigned long long seed, unsigned long long step, const unsigned long long* row_rng, long long* tokens,
+                          float* logprobs, int top_k, long long* top_ids, float* top_lp, const void* tag_src, void* tag_dst,
+                          cudaStream_t s) {
   if (B == 0) return cudaSuccess;
   if (top_k > 32) return cudaErrorInvalidValue;
-  (void)launch_pdl(sample_kernel, dim3(B), dim3(kSampThreads), 0, s, logits, V, temperature, top_p, seed, step, tokens, logprobs, top_k, top_ids, top_lp);
+  (void)launch_pdl(sample_kernel, dim3(B), dim3(kSampThreads), 0, s, logits, V, temperature, top_p, seed, step, row_rng, tokens,
+                   logprobs, top_k, top_ids, top_lp, static_cast<const uint4*>(tag_src), static_cast<uint4*>(tag_dst));
   return cudaGetLastError();
 }
 

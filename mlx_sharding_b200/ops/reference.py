@@ -290,6 +290,26 @@ def sample(logits: torch.Tensor, temperature: torch.Tensor, top_p: torch.Tensor,
     return tokens, tok_lp, None, None
 
 
+def sample_block(logits: torch.Tensor, sv, tag_out, toks_out, lp_out, top_ids_out, top_lp_out):
+    """Sampling driven by a step block (``parallel/graph_decode.py``): penalties, then per-sequence temperature / top-p with a
+    per-request random stream — row ``b`` draws from a generator seeded with its ``(seed, tokens sampled so far)`` pair, so a
+    request's tokens do not depend on which batch it decodes in.  Results go into the result-message views."""
+    lf = logits.float().clone()
+    if sv.has_pen:
+        apply_penalties_(lf, sv.rep, sv.penalty, sv.bidx, sv.bval)
+    B = lf.shape[0]
+    rng = sv.rng.view(B, 2).tolist()
+    k = 0 if top_ids_out is None else top_ids_out.shape[1]
+    for b in range(B):
+        g = torch.Generator(device=lf.device)
+        g.manual_seed((rng[b][0] * 1000003 + rng[b][1] * 7919 + 12345) & 0x7FFFFFFFFFFFFFFF)
+        t, lp, ti, tl = sample(lf[b:b + 1], sv.temps[b:b + 1], sv.top_p[b:b + 1], generator=g, top_logprobs=k)
+        toks_out[b], lp_out[b] = t[0], lp[0]
+        if k:
+            top_ids_out[b], top_lp_out[b] = ti[0], tl[0]
+    tag_out.copy_(sv.tag)
+
+
 def mla_rope_kv_write(q: torch.Tensor, k_pe: torch.Tensor, kv: torch.Tensor, kpool: torch.Tensor, vpool: torch.Tensor,
                       meta: BatchMeta, spec: RopeSpec, nope: int, vdim: int):
     """DeepSeek-V2 attention prologue: rope the ``*_pe`` slices (q in place) and append

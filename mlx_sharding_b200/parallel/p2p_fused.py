@@ -38,7 +38,9 @@ class FusedP2PBoundary:
     FLAG_STRIDE = 32  # uint32 elements between flags: one flag per 128 B line
 
     def __init__(self, hidden_size: int, num_groups: int, max_tokens: int, max_seqs: int, group=None,
-                 dtype=torch.bfloat16):
+                 dtype=torch.bfloat16, result_bytes: int = 0):
+        """``result_bytes``: size of stage 0's per-group result inbox (sampled ids + log-probs [+ top-k], see
+        ``graph_decode.ResultLayout``); defaults to the bare token ids (``max_seqs`` int64)."""
         from ..ops import b200
 
         self.C = b200.load_extension()
@@ -49,7 +51,8 @@ class FusedP2PBoundary:
         self.H, self.G, self.max_tokens, self.max_seqs = hidden_size, num_groups, max_tokens, max_seqs
         itemsize = torch.empty((), dtype=dtype).element_size()
         self.hidden_bytes = num_groups * max_tokens * hidden_size * itemsize
-        self.token_bytes = num_groups * max_seqs * 8
+        self.result_stride = max((max(result_bytes, max_seqs * 8) + 255) // 256 * 256, 256)
+        self.token_bytes = num_groups * self.result_stride
         self.flag_bytes = 2 * num_groups * self.FLAG_STRIDE * 4   # [hidden flags | token flags]
         total = self.hidden_bytes + self.token_bytes + self.flag_bytes
         total = (total + 255) // 256 * 256
@@ -74,7 +77,7 @@ class FusedP2PBoundary:
         return base + g * self.max_tokens * self.H * 2
 
     def _token_ptr(self, base: int, g: int) -> int:
-        return base + self.hidden_bytes + g * self.max_seqs * 8
+        return base + self.hidden_bytes + g * self.result_stride
 
     def _flag_ptr(self, base: int, g: int, kind: int) -> int:
         return base + self.hidden_bytes + self.token_bytes + (kind * self.G + g) * self.FLAG_STRIDE * 4
@@ -112,6 +115,17 @@ class FusedP2PBoundary:
         ``[1, T, V]`` logits)."""
         assert tokens.dtype == torch.int64 and tokens.is_contiguous() and (tokens.numel() * 8) % 16 == 0
         self.C.copy_signal(tokens, self.first_token_ptr(g), self.first_token_flag(g), 0)
+
+    def result_inbox(self, g: int, nbytes: int) -> torch.Tensor:
+        return self.C.tensor_from_ptr(self._token_ptr(self.base, g), [nbytes], "uint8", self.dev)
+
+    def wait_result(self, g: int):
+        self.wait_tokens(g)
+
+    def send_result(self, res: torch.Tensor, g: int):
+        """Last stage -> stage 0: the result message of a step (tag, sampled ids, log-probs [, top-k]) in one copy + flag bump."""
+        assert res.dtype == torch.uint8 and res.is_contiguous() and res.numel() % 16 == 0 and res.numel() <= self.result_stride
+        self.C.copy_signal(res, self.first_token_ptr(g), self.first_token_flag(g), 0)
 
     def send_hidden(self, x: torch.Tensor, g: int):
         """Un-fused fallback (e.g. Gemma-2, whose last op is a norm): copy kernel + signal."""

@@ -1,42 +1,61 @@
 """Pipeline runtimes: how one scheduler step (``StepInput``) travels through the stages.
 
 * ``LocalPipeline``  – all stages in this process (1 GPU, or CPU tests).
-* ``ChainPipeline``  – **direct chain** ``stage i -> i+1`` across processes; the last stage samples on
-  device and only token ids (+ logprobs) return to stage 0.  Replaces the reference's hub-and-spoke
-  relay that bounces every hidden state through the primary and ships full ``[1,T,V]`` logits back
-  (shard/utils.py:162-166, server/server.py:36-48).
+* ``ChainPipeline``  – **direct chain** ``stage i -> i+1`` across processes; the last stage samples on device and only a small
+  result message (token ids + log-probs) returns to stage 0.  Replaces the reference's hub-and-spoke relay that bounces every
+  hidden state through the primary and ships full ``[1,T,V]`` logits back (shard/utils.py:162-166, server/server.py:36-48;
+  SURVEY X1-X3).
 * ``worker_loop``    – what a non-first stage process runs.
 
-Data plane and control plane come from a ``ChainTransport`` (``parallel/transport.py``): gloo on CPU
-(BASELINE config 1), NCCL p2p on GPUs (the baseline hand-off), or the fused P2P store path
-(``parallel/p2p_fused.py``) where the producing kernel writes straight into the peer's inbox.
+A step is described by ONE int32 **step block** (``graph_decode.pack_step``: step tag, sampling block, packed metadata, token
+ids) that stage 0 builds and every stage copies host->device from pinned memory.  How the block reaches the other stages is the
+*control plane*; how hidden states and results move is the *data plane*:
+
+=================  ==========================================================================================================
+control plane      ``ShmControl`` (default, one node): launch ring in shared memory — publishing a step is a memcpy, picking
+                   it up is a poll; no pickle, no gloo, no system call per step.  ``DistControl``: gloo broadcast fallback for
+                   ranks that do not share a host.
+data plane         ``FusedPlane`` (B200, default): resident inboxes mapped over CUDA IPC; the *last kernel of a stage* (down-proj
+                   GEMM epilogue / MoE combine) stores its rows straight into the next stage's inbox over NVLink and bumps its
+                   flag; the consumer's step starts with a flag-wait kernel.  A decode step of a group is ONE CUDA-graph replay
+                   per stage: no NCCL call, no host hop, no control message on the hand-off.  ``DistPlane``: ``send/recv`` over
+                   gloo (CPU plumbing, BASELINE config 1) or NCCL (baseline transport).
+=================  ==========================================================================================================
+
+Failure handling (reference: ``success=False`` strings, server/server.py:55-57): a stage that fails a step records the error on
+the control plane's status page and still forwards a placeholder, so every stage keeps executing the same launch sequence
+(lock-step is what keeps the flag protocol deadlock-free); stage 0 raises on the next ``wait``; ``reset()`` drains every step
+that is still in flight *before* the engine releases KV pages; results carry their step id and are checked on receipt.
 """
 from __future__ import annotations
 
 import logging
+import os
 from collections import deque
 from typing import List, Optional
 
+import numpy as np
 import torch
 
 from ..engine.core import StepInput, StepOutput
 from ..engine.kv_cache import PagedKVCache
-from ..engine.sampler import Sampler, SamplingParams
+from ..engine.sampler import Sampler
 from ..ops.meta import BatchMeta
+from .graph_decode import (HEADER_WORDS, DecodeGraphCache, ResultLayout, StepViews, device_sample, pack_step, parse_result,
+                           unpack_header)
+from .shm_ring import KIND_SHUTDOWN, KIND_STEP
 
 log = logging.getLogger(__name__)
 
 
 class StageExecutor:
-    """A stage model + its paged KV pool (+ the sampler on the last stage)."""
+    """A stage model + its paged KV pool (+ the host-parameter sampler used by the gRPC-compat relay)."""
 
     def __init__(self, model, num_pages: int, page_size: int = 64, seed: int = 0):
         self.model = model
         self.device = model.device
         self.kv = PagedKVCache.for_model(model, num_pages, page_size)
         self.sampler = Sampler(model.ops, self.device, seed) if model.spec.is_last else None
-        import os
-
         from ..utils.tracing import StageTimer
 
         self.timer = StageTimer(enabled=os.environ.get("MLXB200_STAGE_TIMING", "0") == "1")
@@ -56,26 +75,109 @@ class StageExecutor:
                           None if so.top_logprobs is None else so.top_logprobs.tolist())
 
 
-def _pinned_to(t: torch.Tensor, device) -> torch.Tensor:
-    """Host tensor -> device through pinned memory (async copy on the current stream)."""
-    if torch.device(device).type != "cuda":
-        return t
-    return t.pin_memory().to(device, non_blocking=True)
+# -------------------------------------------------------------------------------------------------
+# One stage, one step
+# -------------------------------------------------------------------------------------------------
+class StepRunner:
+    """Executes step blocks on one stage: pinned H2D of the block, then the device work — a CUDA-graph replay for decode
+    micro-batches, eager kernels for prefill chunks / mixed batches — with the data plane's hand-off hooks around the layers."""
+
+    def __init__(self, stage: StageExecutor, plane=None):
+        self.stage, self.plane = stage, plane
+        self.model = stage.model
+        self.dev = stage.device
+        self.cuda = self.dev.type == "cuda"
+        self.first, self.last = self.model.spec.is_first, self.model.spec.is_last
+        capturable = plane is None or plane.capturable
+        self.gcache = DecodeGraphCache(stage, body=self._graph_body, per_group=plane is not None)
+        if not capturable:
+            self.gcache.enabled = False
+        self.h2d_bytes = 0
+        self._phase = 0          # 0: nothing done for the current step, 1: input consumed, 2: output handed on
+        self._x_local = None     # input hidden of an in-process (LocalPipeline) non-first stage
+
+    # ---- host -> device ------------------------------------------------------------------------
+    def _h2d(self, dst: torch.Tensor, blk: np.ndarray):
+        src = torch.from_numpy(blk)
+        if self.cuda:
+            dst.copy_(src.pin_memory(), non_blocking=True)
+            self.h2d_bytes += blk.nbytes
+        else:
+            dst.copy_(src)
+
+    # ---- device work of one step ---------------------------------------------------------------
+    def _graph_body(self, e):
+        return self._device_step(e.sv, e.group, e.res, e.rl, e.x)
+
+    def _device_step(self, sv: StepViews, g: int, res, rl: ResultLayout, x_static=None):
+        model, plane, T = self.model, self.plane, sv.lay.T
+        if self.first:
+            x = sv.tokens
+        elif plane is not None:
+            x = plane.begin(g, T, out=None if plane.capturable else x_static)
+        else:
+            x = self._x_local
+        self._phase = 1
+        if plane is not None and not self.last:
+            plane.arm(model, g, T)
+        out = model.forward(x, sv.meta, self.stage.kv)
+        if self.last:
+            device_sample(model.ops, out, sv, res, rl)
+            if plane is not None:
+                plane.send_result(res, g)
+            self._phase = 2
+            return res
+        if plane is not None:
+            plane.finish(model, out, g)
+        self._phase = 2
+        return out
+
+    @torch.inference_mode()
+    def run(self, wire: np.ndarray, group: int, x_local: Optional[torch.Tensor] = None):
+        """``wire`` = ``[header | step block]`` (int32).  Returns the stage output: hidden ``[T, H]`` or, on the last stage, the
+        result message (device uint8 tensor)."""
+        lay, _ = unpack_header(wire)
+        blk = wire[HEADER_WORDS:HEADER_WORDS + lay.size]
+        mq, mctx = int(blk[lay.meta + 2]), int(blk[lay.meta + 3])
+        self._phase, self._x_local = 0, x_local
+        with self.stage.timer.measure():
+            if self.gcache.enabled and mq == 1 and lay.T == lay.B and x_local is None:
+                e = self.gcache.entry(lay, mctx, group)
+                self._h2d(e.flat, blk)
+                return self.gcache.run(e)
+            flat = torch.empty(lay.size, dtype=torch.int32, device=self.dev)
+            self._h2d(flat, blk)
+            sv = StepViews(flat, lay, self.stage.kv.page_size, mctx, mq)
+            rl = ResultLayout(lay.B, lay.k)
+            res = torch.zeros(rl.nbytes, dtype=torch.uint8, device=self.dev) if self.last else None
+            return self._device_step(sv, group, res, rl)
+
+    def poison(self, wire: np.ndarray, group: int):
+        """After a failed step: consume the input and forward a placeholder so the chain stays in lock-step."""
+        if self.plane is None:
+            return
+        lay, _ = unpack_header(wire)
+        try:
+            if self._phase < 1 and not self.first:
+                self.plane.begin(group, lay.T)
+            if self._phase < 2:
+                self.model.boundary = None
+                if self.last:
+                    self.plane.send_result(torch.zeros(ResultLayout(lay.B, lay.k).nbytes, dtype=torch.uint8, device=self.dev), group)
+                else:
+                    self.plane.send_hidden(torch.zeros(lay.T, self.model.cfg.hidden_size, dtype=self.model.dtype, device=self.dev), group)
+        except Exception:  # noqa: BLE001 — nothing more can be done; the status page already carries the first error
+            log.exception("could not forward a placeholder after a failed step")
 
 
-def stage_inputs(inp: StepInput, device):
-    """H2D transfer of one step's inputs (token ids + packed metadata); returns (tokens, meta, bytes)."""
-    m = inp.meta
-    if torch.device(device).type != "cuda":
-        return inp.tokens, m, 0
-    parts = [m.positions, m.slot_mapping, m.cu_seqlens, m.context_lens, m.last_idx, m.block_tables.reshape(-1)]
-    sizes = [p.numel() for p in parts]
-    flat = _pinned_to(torch.cat([p.to(torch.int32) for p in parts]), device)
-    v = list(torch.split(flat, sizes))
-    meta = BatchMeta(v[0], v[1], v[2], v[3], v[5].view(m.block_tables.shape), v[4], m.num_tokens, m.num_seqs,
-                     m.max_q_len, m.max_ctx_len, m.page_size)
-    toks = _pinned_to(inp.tokens, device)
-    return toks, meta, flat.numel() * 4 + toks.numel() * 8
+def _fetch(res: torch.Tensor) -> torch.Tensor:
+    """Result message device -> host (pinned when on CUDA)."""
+    if res.device.type != "cuda":
+        return res
+    host = torch.empty(res.shape, dtype=res.dtype).pin_memory()
+    host.copy_(res, non_blocking=True)
+    torch.cuda.current_stream(res.device).synchronize()
+    return host
 
 
 class LocalPipeline:
@@ -84,41 +186,30 @@ class LocalPipeline:
     def __init__(self, stages: List[StageExecutor]):
         assert stages[0].model.spec.is_first and stages[-1].model.spec.is_last
         self.stages = stages
+        self.runners = [StepRunner(s) for s in stages]
         self.num_stages = 1  # one executor thread: a single micro-batch group keeps it busy
-        self.h2d_bytes = 0
         self.d2h_bytes = 0
-        from .graph_decode import DecodeGraphCache
+        self._seq = 0
+        self.gcache = self.runners[0].gcache if len(stages) == 1 else None
 
-        self.gcache = DecodeGraphCache(stages[0]) if len(stages) == 1 else None
+    @property
+    def h2d_bytes(self) -> int:
+        return sum(r.h2d_bytes for r in self.runners)
 
     @classmethod
     def from_models(cls, models, num_pages: int, page_size: int = 64, seed: int = 0):
         return cls([StageExecutor(m, num_pages, page_size, seed) for m in models])
 
-    def _submit_graph(self, inp: StepInput) -> StepOutput:
-        """Steady-state decode: one pinned H2D copy of (metadata, token ids), one graph replay, one D2H."""
-        m = inp.meta
-        e = self.gcache.entry(m.num_seqs, m.block_tables.shape[1], m.max_ctx_len)
-        packed = m.pack().pin_memory()
-        toks_h = inp.tokens.pin_memory()
-        e.flat.copy_(packed, non_blocking=True)
-        e.x.copy_(toks_h, non_blocking=True)
-        toks, lp = self.gcache.run(e)
-        self.h2d_bytes += packed.numel() * 4 + toks_h.numel() * 8
-        self.d2h_bytes += m.num_seqs * 12
-        return StepOutput(toks.tolist(), lp.tolist())
-
-    def submit(self, inp: StepInput):
-        if self.gcache is not None and self.gcache.eligible(inp.meta, inp.params):
-            return self._submit_graph(inp)
-        x, meta0, nbytes = stage_inputs(inp, self.stages[0].device)
-        self.h2d_bytes += nbytes
-        for i, st in enumerate(self.stages):
-            meta = meta0 if i == 0 or st.device == self.stages[0].device else inp.meta.to(st.device)
-            x = st.forward(x.to(st.device), meta)
-        out = self.stages[-1].sample(x, inp.params, inp.contexts)
-        self.d2h_bytes += len(out.tokens) * 12  # int64 token id + fp32 logprob per sequence
-        return out
+    def submit(self, inp: StepInput) -> StepOutput:
+        self._seq += 1
+        wire, lay = pack_step(self._seq, inp.meta, inp.tokens, inp.params, inp.contexts, inp.rng, inp.is_prefill)
+        x = None
+        for r in self.runners:
+            x = r.run(wire, inp.group, x_local=None if x is None else x.to(r.dev))
+        rl = ResultLayout(lay.B, lay.k)
+        host = _fetch(x)
+        self.d2h_bytes += rl.nbytes
+        return StepOutput(*parse_result(host, rl, self._seq))
 
     def wait(self, handle) -> StepOutput:
         return handle
@@ -128,145 +219,340 @@ class LocalPipeline:
 
 
 # -------------------------------------------------------------------------------------------------
+# Data planes
+# -------------------------------------------------------------------------------------------------
+class _Pending:
+    """A result message on its way to stage 0."""
+
+    def __init__(self, host: torch.Tensor, event=None, work=None, dev_buf=None):
+        self.host, self.event, self.work, self.dev_buf = host, event, work, dev_buf
+
+    def done(self) -> bool:
+        if self.event is not None:
+            return self.event.query()
+        return self.work.is_completed()
+
+    def get(self) -> torch.Tensor:
+        if self.event is not None:
+            self.event.synchronize()
+        else:
+            self.work.wait()
+            if self.dev_buf is not None:
+                self.host.copy_(self.dev_buf)
+        return self.host
+
+
+class FusedPlane:
+    """T0: resident inboxes + flags over CUDA IPC (``p2p_fused.py``); every operation is a stream-ordered kernel, so a whole stage
+    step — flag wait, layers, epilogue store into the peer, flag bump — is capturable in one CUDA graph."""
+
+    capturable = True
+    name = "fused"
+
+    def __init__(self, stage: StageExecutor, num_groups: int, max_tokens: int, max_seqs: int, group=None):
+        from .p2p_fused import FusedP2PBoundary
+
+        self.p2p = FusedP2PBoundary(stage.model.cfg.hidden_size, num_groups, max_tokens, max_seqs, group=group,
+                                    dtype=stage.model.dtype, result_bytes=ResultLayout.max_bytes(max_seqs))
+        self.max_tokens = max_tokens
+        self.dev = stage.device
+        self.side = torch.cuda.Stream(device=self.dev) if self.p2p.rank == 0 else None
+        self.d2h_bytes = 0
+
+    def begin(self, g: int, T: int, out=None) -> torch.Tensor:
+        if T > self.max_tokens:
+            raise ValueError(f"step of {T} tokens exceeds the hand-off inbox ({self.max_tokens} tokens)")
+        self.p2p.wait_hidden(g)
+        return self.p2p.hidden_inbox(g, T)
+
+    def arm(self, model, g: int, T: int):
+        if T > self.max_tokens:
+            raise ValueError(f"step of {T} tokens exceeds the hand-off inbox ({self.max_tokens} tokens)")
+        model.boundary = (self.p2p.next_hidden(g, T), self.p2p.next_hidden_flag(g))
+
+    def finish(self, model, out: torch.Tensor, g: int):
+        fused = model.boundary_fused
+        model.boundary = None
+        if not fused:   # the stage's last kernel has no fused epilogue (Gemma-2 ends in a norm): copy + signal
+            self.p2p.send_hidden(out, g)
+
+    def send_hidden(self, x: torch.Tensor, g: int):
+        self.p2p.send_hidden(x, g)
+
+    def send_result(self, res: torch.Tensor, g: int):
+        self.p2p.send_result(res, g)
+
+    def recv_result(self, g: int, nbytes: int) -> _Pending:
+        """Stage 0: flag wait + D2H of the result inbox on a side stream (the main stream never blocks on a flag)."""
+        host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        with torch.cuda.stream(self.side):
+            self.p2p.C.pdl_skip_next()
+            self.p2p.wait_result(g)
+            host.copy_(self.p2p.result_inbox(g, nbytes), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.d2h_bytes += nbytes
+        return _Pending(host, event=ev)
+
+    def failed(self) -> bool:
+        return self.p2p.error()
+
+
+class DistPlane:
+    """T1 / T2: two-sided ``send/recv`` through ``TorchDistTransport`` (gloo on CPU, NCCL on GPUs)."""
+
+    name = "dist"
+
+    def __init__(self, stage: StageExecutor, transport):
+        self.tp = transport
+        self.rank, self.world = transport.rank, transport.world_size
+        self.H, self.dtype, self.dev = stage.model.cfg.hidden_size, stage.model.dtype, stage.device
+        self.capturable = False
+        self.d2h_bytes = 0
+
+    def begin(self, g: int, T: int, out=None) -> torch.Tensor:
+        return self.tp.recv_tensor((T, self.H), self.dtype, self.rank - 1, slot=g)
+
+    def arm(self, model, g: int, T: int):
+        pass
+
+    def finish(self, model, out: torch.Tensor, g: int):
+        self.tp.send_tensor(out, self.rank + 1, slot=g)
+
+    def send_hidden(self, x: torch.Tensor, g: int):
+        self.tp.send_tensor(x, self.rank + 1, slot=g)
+
+    def send_result(self, res: torch.Tensor, g: int):
+        self.tp.send_tensor(res.clone(), 0, slot=g)
+
+    def recv_result(self, g: int, nbytes: int) -> _Pending:
+        import torch.distributed as dist
+
+        host = torch.empty(nbytes, dtype=torch.uint8)
+        if self.tp.data_backend == "gloo":
+            return _Pending(host, work=dist.irecv(host, self.world - 1, group=self.tp.data_group))
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+        self.d2h_bytes += nbytes
+        return _Pending(host, work=dist.irecv(buf, self.world - 1, group=self.tp.data_group), dev_buf=buf)
+
+    def failed(self) -> bool:
+        return False
+
+
+# -------------------------------------------------------------------------------------------------
+# Control plane fallback (ranks on different hosts)
+# -------------------------------------------------------------------------------------------------
+class DistControl:
+    """``ShmControl``'s interface over a gloo broadcast + the rendezvous store (for ranks that do not share ``/dev/shm``)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.store = dist.distributed_c10d._get_default_store()
+        self._seq = 0
+        self.max_payload_words = 1 << 26
+
+    def publish(self, kind: int, group: int, payload: Optional[np.ndarray] = None, timeout_s: float = 60.0) -> int:
+        self._seq += 1
+        n = 0 if payload is None else int(payload.size)
+        self.dist.broadcast(torch.tensor([self._seq, kind, group, n], dtype=torch.int64), 0, group=self.group)
+        if n:
+            self.dist.broadcast(torch.from_numpy(np.ascontiguousarray(payload)), 0, group=self.group)
+        return self._seq
+
+    def next(self, timeout_s: Optional[float] = None):
+        hdr = torch.zeros(4, dtype=torch.int64)
+        self.dist.broadcast(hdr, 0, group=self.group)
+        seq, kind, group, n = hdr.tolist()
+        payload = torch.zeros(n, dtype=torch.int32)
+        if n:
+            self.dist.broadcast(payload, 0, group=self.group)
+        return seq, kind, group, payload.numpy()
+
+    def set_error(self, seq: int, msg: str):
+        self.store.set(f"mlxb200/err/{self.rank}", f"{seq}:{msg}")
+        self.store.add("mlxb200/nerr", 1)
+
+    def first_error(self):
+        if self.store.add("mlxb200/nerr", 0) == 0:
+            return None
+        for r in range(self.world):
+            if self.store.check([f"mlxb200/err/{r}"]):
+                seq, _, msg = self.store.get(f"mlxb200/err/{r}").decode().partition(":")
+                return r, int(seq or 0), msg
+        return None
+
+    def clear_errors(self):
+        n = self.store.add("mlxb200/nerr", 0)
+        if n:
+            self.store.add("mlxb200/nerr", -n)
+            for r in range(self.world):
+                self.store.delete_key(f"mlxb200/err/{r}")
+
+    def request_shutdown(self):
+        pass
+
+    def unlink(self):
+        pass
+
+
+def build_chain(stage: StageExecutor, num_groups: Optional[int] = None, max_tokens: int = 2048, max_seqs: int = 64,
+                transport: str = "auto", control: str = "auto"):
+    """Collective over all ranks: set up the control plane and the data plane of a chain.  Returns ``(ctl, plane)``.
+
+    transport: ``fused`` (B200 kernels + CUDA IPC inboxes), ``nccl`` / ``gloo`` (two-sided), ``auto`` = fused on CUDA with the
+    b200 backend when every rank is on this host, else nccl on CUDA, gloo on CPU.
+    control: ``shm`` / ``dist`` / ``auto`` (shm when every rank is on this host)."""
+    import socket
+
+    import torch.distributed as dist
+
+    from .shm_ring import ShmControl
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    G = num_groups or world
+    ctrl_group = dist.new_group(backend="gloo")
+    hosts = [None] * world
+    dist.all_gather_object(hosts, socket.gethostname(), group=ctrl_group)
+    one_node = len(set(hosts)) == 1
+    if control == "auto":
+        control = "shm" if one_node else "dist"
+    if control == "shm":
+        box = [None]
+        ctl = None
+        if rank == 0:
+            # a slot holds the largest step block: a prefill chunk of max_tokens tokens (+ block tables of max_seqs sequences)
+            slot = max(256 << 10, (16 * max_tokens + 1024 * max_seqs + 4096 + 4095) // 4096 * 4096)
+            ctl = ShmControl.create(world, slots=128, slot_bytes=slot)
+            box[0] = ctl.path
+        dist.broadcast_object_list(box, 0, group=ctrl_group)
+        if rank != 0:
+            ctl = ShmControl.attach(box[0], rank, world)
+        dist.barrier(group=ctrl_group)
+        if rank == 0:
+            ctl.unlink()          # every rank holds a mapping now; nothing is left behind if a process dies
+    else:
+        ctl = DistControl(ctrl_group)
+    cuda = stage.device.type == "cuda"
+    if transport == "auto":
+        transport = "fused" if (cuda and one_node and stage.model.backend_name == "b200") else ("nccl" if cuda else "gloo")
+    if transport == "fused":
+        plane = FusedPlane(stage, G, max_tokens, max_seqs, group=ctrl_group)
+    else:
+        from .transport import TorchDistTransport
+
+        plane = DistPlane(stage, TorchDistTransport(stage.device, data_backend=transport, ctrl_group=ctrl_group))
+    return ctl, plane
+
+
+# -------------------------------------------------------------------------------------------------
 # Cross-process chain
 # -------------------------------------------------------------------------------------------------
-_GREEDY = SamplingParams()   # shared instance for the compact control message
-
-
-def _plain_greedy(p: SamplingParams) -> bool:
-    return (p.temperature == 0 and p.top_p == 1.0 and p.repetition_penalty in (0, 1.0) and not p.logit_bias and p.logprobs == 0
-            and p.seed is None)
-
-
-def _ctrl_of(inp: StepInput) -> dict:
-    """Per-step control message that travels down the chain (pickled, gloo).  The common case — every sequence decodes greedily
-    with default parameters — is sent as a count instead of B parameter objects + B empty contexts (half the bytes and less
-    than half the (un)pickling time per hop, which sits on every stage's critical path)."""
-    if all(_plain_greedy(p) for p in inp.params):
-        return dict(kind="step", group=inp.group, meta=inp.meta.pack(), params=len(inp.params), contexts=None,
-                    is_prefill=inp.is_prefill)
-    return dict(kind="step", group=inp.group, meta=inp.meta.pack(), params=inp.params, contexts=inp.contexts,
-                is_prefill=inp.is_prefill)
-
-
-def _params_of(ctrl: dict):
-    """(params, contexts) of a control message (expands the compact greedy form)."""
-    p = ctrl["params"]
-    if isinstance(p, int):
-        return [_GREEDY] * p, [[]] * p
-    return p, ctrl["contexts"]
-
-
 class ChainPipeline:
     """Stage-0 side of the cross-process chain."""
 
-    def __init__(self, stage: StageExecutor, transport):
-        self.stage = stage
-        self.tp = transport
-        self.num_stages = transport.world_size
-        self.rank = transport.rank
-        assert self.rank == 0 and stage.model.spec.is_first
-        self._pending = deque()
-        self.h2d_bytes = 0
-        self.d2h_bytes = 0
-        from .graph_decode import DecodeGraphCache
+    def __init__(self, stage: StageExecutor, ctl, plane):
+        self.stage, self.ctl, self.plane = stage, ctl, plane
+        self.num_stages = ctl.world
+        assert ctl.rank == 0 and stage.model.spec.is_first and self.num_stages > 1
+        self.runner = StepRunner(stage, plane)
+        self.gcache = self.runner.gcache
+        self._seq = 0
+        self._outstanding = deque()
+        self._dead: Optional[str] = None
 
-        self.gcache = DecodeGraphCache(stage)
+    @classmethod
+    def build(cls, stage: StageExecutor, **kw) -> "ChainPipeline":
+        return cls(stage, *build_chain(stage, **kw))
+
+    @property
+    def h2d_bytes(self) -> int:
+        return self.runner.h2d_bytes
+
+    @property
+    def d2h_bytes(self) -> int:
+        return self.plane.d2h_bytes
 
     def submit(self, inp: StepInput):
-        tp = self.tp
-        if self.num_stages > 1 and self.gcache.eligible(inp.meta, None):
-            m = inp.meta
-            e = self.gcache.entry(m.num_seqs, m.block_tables.shape[1], m.max_ctx_len)
-            packed, toks_h = m.pack().pin_memory(), inp.tokens.pin_memory()
-            e.flat.copy_(packed, non_blocking=True)
-            e.x.copy_(toks_h, non_blocking=True)
-            x = self.gcache.run(e)
-            nbytes = packed.numel() * 4 + toks_h.numel() * 8
-        else:
-            toks, meta, nbytes = stage_inputs(inp, self.stage.device)
-            x = self.stage.forward(toks, meta)
-        self.h2d_bytes += nbytes
-        self.d2h_bytes += len(inp.seq_ids) * 12
-        if self.num_stages == 1:
-            return ("local", self.stage.sample(x, inp.params, inp.contexts))
-        tp.send_ctrl(_ctrl_of(inp), 1)
-        tp.send_tensor(x, 1, slot=inp.group)
-        h = tp.irecv_ctrl(self.num_stages - 1)  # result comes straight from the last stage
-        return ("remote", h)
+        if self._dead:
+            raise RuntimeError(self._dead)
+        self._seq += 1
+        seq = self._seq
+        wire, lay = pack_step(seq, inp.meta, inp.tokens, inp.params, inp.contexts, inp.rng, inp.is_prefill)
+        self.ctl.publish(KIND_STEP, inp.group, wire)
+        try:
+            self.runner.run(wire, inp.group)
+        except Exception as e:  # noqa: BLE001 — report, keep the chain in lock-step, fail the requests on wait()
+            log.exception("stage 0 failed step %d", seq)
+            self.ctl.set_error(seq, f"{type(e).__name__}: {e}")
+            self.runner.poison(wire, inp.group)
+        rl = ResultLayout(lay.B, lay.k)
+        h = (seq, rl, self.plane.recv_result(inp.group, rl.nbytes))
+        self._outstanding.append(h)
+        return h
+
+    def _raise_if_failed(self):
+        err = self.ctl.first_error()
+        if err is not None:
+            raise RuntimeError(f"stage {err[0]} failed (step {err[1]}): {err[2]}")
 
     def wait(self, handle) -> StepOutput:
-        kind, h = handle
-        if kind == "local":
-            return h
-        res = self.tp.wait_ctrl(h)
-        if isinstance(res, dict) and res.get("error"):
-            raise RuntimeError(f"stage {res.get('rank')} failed: {res['error']}")
-        return StepOutput(**res)
+        seq, rl, pending = handle
+        host = pending.get()
+        try:
+            self._outstanding.remove(handle)
+        except ValueError:
+            pass
+        self._raise_if_failed()
+        if self.plane.failed():
+            self._dead = "P2P flag wait timed out: a pipeline stage is not responding"
+            raise RuntimeError(self._dead)
+        return StepOutput(*parse_result(host, rl, seq))
 
     def reset(self):
-        pass
+        """Called by the engine after a failure, *before* it releases KV pages: wait for every step still in flight (their
+        results are discarded — downstream stages may still be writing KV for them), then clear the error state."""
+        while self._outstanding:
+            _, _, pending = self._outstanding.popleft()
+            try:
+                pending.get()
+            except Exception:  # noqa: BLE001
+                log.exception("draining an in-flight step failed")
+        self.ctl.clear_errors()
 
     def shutdown(self):
-        if self.num_stages > 1:
-            self.tp.send_ctrl(dict(kind="shutdown"), 1)
-            if hasattr(self.tp, "flush"):
-                self.tp.flush()
-
-
-def worker_loop(stage: StageExecutor, transport):
-    """Non-first stage: ``recv (ctrl, hidden) -> forward -> send`` until a shutdown message.
-    Errors are reported down the chain to stage 0 instead of wedging the pipeline (the reference
-    replies ``success=False`` strings, server/server.py:55-57)."""
-    tp = transport
-    rank, world = tp.rank, tp.world_size
-    last = rank == world - 1
-    H = stage.model.cfg.hidden_size
-    from .graph_decode import DecodeGraphCache
-
-    gcache = DecodeGraphCache(stage)
-    while True:
-        ctrl = tp.recv_ctrl(rank - 1)
-        if ctrl["kind"] == "shutdown":
-            if not last:
-                tp.send_ctrl(ctrl, rank + 1)
-            if hasattr(tp, "flush"):
-                tp.flush()
-            return
-        if ctrl.get("error"):
-            # propagate the failure to stage 0 (drain our payload first to stay in lockstep)
-            if last:
-                tp.send_ctrl(ctrl, 0)
-            else:
-                tp.send_ctrl(ctrl, rank + 1)
-            continue
-        meta = BatchMeta.unpack(ctrl["meta"])
-        params, contexts = _params_of(ctrl)
-        graphed = gcache.eligible(meta, params)
-        if graphed:
-            e = gcache.entry(meta.num_seqs, meta.block_tables.shape[1], meta.max_ctx_len)
-            x = tp.recv_tensor((meta.num_tokens, H), stage.model.dtype, rank - 1, slot=ctrl["group"], out=e.x)
-        else:
-            x = tp.recv_tensor((meta.num_tokens, H), stage.model.dtype, rank - 1, slot=ctrl["group"])
         try:
-            if graphed:
-                e.flat.copy_(ctrl["meta"].pin_memory(), non_blocking=True)
-                out = gcache.run(e)
-                if last:
-                    toks, lp = out
-                    res = StepOutput(toks.tolist(), lp.tolist())
-                    tp.send_ctrl(dict(tokens=res.tokens, logprobs=res.logprobs, top_ids=None, top_logprobs=None), 0)
-                    continue
-            else:
-                out = stage.forward(x, meta.to(stage.device))
-            if last:
-                res = stage.sample(out, params, contexts)
-                tp.send_ctrl(dict(tokens=res.tokens, logprobs=res.logprobs, top_ids=res.top_ids,
-                                  top_logprobs=res.top_logprobs), 0)
-            else:
-                tp.send_ctrl(ctrl, rank + 1)
-                tp.send_tensor(out, rank + 1, slot=ctrl["group"])
+            self.reset()
+        finally:
+            self.ctl.publish(KIND_SHUTDOWN, 0, None)
+            self.ctl.request_shutdown()
+            tp = getattr(self.plane, "tp", None)
+            if tp is not None and hasattr(tp, "flush"):
+                tp.flush()
+
+
+def worker_loop(stage: StageExecutor, ctl, plane):
+    """Non-first stage: execute the launch records of the control plane in order until shutdown."""
+    runner = StepRunner(stage, plane)
+    while True:
+        rec = ctl.next()
+        if rec is None:
+            break
+        seq, kind, group, wire = rec
+        if kind == KIND_SHUTDOWN:
+            break
+        if kind != KIND_STEP:
+            continue
+        try:
+            runner.run(wire, group)
         except Exception as e:  # noqa: BLE001
-            log.exception("stage %d failed", rank)
-            err = dict(kind="step", error=f"{type(e).__name__}: {e}", rank=rank)
-            tp.send_ctrl(err, 0 if last else rank + 1)
+            log.exception("stage %d failed", ctl.rank)
+            ctl.set_error(seq, f"{type(e).__name__}: {e}")
+            runner.poison(wire, group)
+    if stage.device.type == "cuda":
+        torch.cuda.synchronize(stage.device)
+    tp = getattr(plane, "tp", None)
+    if tp is not None and hasattr(tp, "flush"):
+        tp.flush()

@@ -47,14 +47,14 @@ class ChainTransport:
 class TorchDistTransport(ChainTransport):
     """torch.distributed p2p: control on a gloo group, payload on ``data_backend`` (gloo | nccl)."""
 
-    def __init__(self, device="cpu", data_backend: Optional[str] = None, timeout_s: float = 600.0):
+    def __init__(self, device="cpu", data_backend: Optional[str] = None, timeout_s: float = 600.0, ctrl_group=None):
         import datetime
 
         assert dist.is_initialized(), "init_process_group first (see parallel.launch.init_distributed)"
         self.rank, self.world_size = dist.get_rank(), dist.get_world_size()
         self.device = torch.device(device)
         to = datetime.timedelta(seconds=timeout_s)
-        self.ctrl_group = dist.new_group(backend="gloo", timeout=to)
+        self.ctrl_group = ctrl_group if ctrl_group is not None else dist.new_group(backend="gloo", timeout=to)
         default_backend = dist.get_backend()
         want = data_backend or ("nccl" if self.device.type == "cuda" else "gloo")
         self.data_backend = want

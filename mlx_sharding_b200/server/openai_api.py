@@ -163,12 +163,13 @@ class ModelProvider:
                                         prefix_cache=getattr(a, "prefix_cache", False))
         stage = StageExecutor(model, num_pages, page_size)
         if world > 1:
-            from ..parallel.transport import TorchDistTransport
-
-            pipe = ChainPipeline(stage, TorchDistTransport(model.device))
-            return LLMEngine(pipe, num_pages, page_size, num_groups=world,
-                             max_seqs_per_group=getattr(a, "max_batch", 64), prefix_cache=getattr(a, "prefix_cache", False),
-                             mixed_batches=getattr(a, "mixed_batches", False))
+            # native chain: launch records through the shared-memory ring, hidden states through the fused P2P hand-off (one CUDA
+            # graph replay per stage per decode step; no NCCL / gloo / pickle on that path) — parallel/pipeline.py
+            mb, mp = getattr(a, "max_batch", 64), getattr(a, "max_prefill_tokens", 2048)
+            pipe = ChainPipeline.build(stage, num_groups=world, max_tokens=mp, max_seqs=mb,
+                                       transport=getattr(a, "transport", "auto"))
+            return LLMEngine(pipe, num_pages, page_size, num_groups=world, max_seqs_per_group=mb, max_prefill_tokens=mp,
+                             prefix_cache=getattr(a, "prefix_cache", False), mixed_batches=getattr(a, "mixed_batches", False))
         if not model.spec.is_last:
             if not self.stubs:
                 raise RuntimeError("this process only holds layers "
@@ -205,6 +206,14 @@ class ModelProvider:
             from ..utils.loader import load_model
 
             if self.engine is not None:
+                # Hot-swapping (reference ModelProvider.load, openai_api.py:87-127) is only safe on an idle single-process engine:
+                # under torchrun the other ranks keep their layer range (a swap on rank 0 alone would also dead-lock in the
+                # collective set-up), and requests in flight would lose their engine.
+                if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+                    raise ValueError("this server is one stage of a multi-process pipeline: the model cannot be switched per request")
+                busy = getattr(self.engine, "busy", None)
+                if busy is not None and busy():
+                    raise ValueError("requests are in flight: the model cannot be switched now")
                 self.engine.shutdown()
             self.model = self.tokenizer = self.engine = self.model_key = None
             a = self.cli_args
@@ -347,6 +356,9 @@ class APIHandler(BaseHTTPRequestHandler):
         self.requested_model = prm["model"]
         try:
             self.model, self.tokenizer, self.engine = self.model_provider.load(self.requested_model)
+        except ValueError as e:   # a switch that cannot be honoured right now (multi-process pipeline / requests in flight)
+            self._count(errors=1)
+            return self._send_json(400, {"error": {"message": str(e), "type": "invalid_request_error"}})
         except Exception as e:  # noqa: BLE001 — reference answers 404 on any load failure (openai_api.py:219-226)
             log.warning("model load failed: %s", e)
             self._count(errors=1)
@@ -559,6 +571,10 @@ def build_arg_parser() -> argparse.ArgumentParser:
     p.add_argument("--kv-pages", type=int, default=None, help="number of KV pages (default: sized from free memory)")
     p.add_argument("--page-size", type=int, default=64)
     p.add_argument("--max-batch", type=int, default=64, help="max concurrent sequences per micro-batch group")
+    p.add_argument("--max-prefill-tokens", type=int, default=2048, help="prompt tokens per prefill step (chunked prefill)")
+    p.add_argument("--transport", type=str, default="auto", choices=["auto", "fused", "nccl", "gloo"],
+                   help="stage hand-off of the native chain (torchrun): fused = GEMM-epilogue P2P store over NVLink (default on "
+                        "B200), nccl / gloo = send/recv")
     p.add_argument("--prefix-cache", action="store_true",
                    help="automatic prefix caching: full KV pages of prompt prefixes are shared between requests (chat system "
                         "prompts are prefilled once); not available with gRPC reference shards")
@@ -606,7 +622,8 @@ def main(argv=None):
             from .shard_server import serve_chain
 
             return serve_chain(args.model, args.start_layer, args.end_layer, args.device, None,
-                               args.kv_pages or 2048, args.page_size)
+                               args.kv_pages or 2048, args.page_size, num_groups=world, max_tokens=args.max_prefill_tokens,
+                               max_seqs=args.max_batch, transport=args.transport)
     needs_remote = args.end_layer is not None and world == 1 and not args.expert_parallel
     if args.model is not None and not needs_remote:
         try:

@@ -38,12 +38,12 @@ def serve(model_path: str, start_layer=None, end_layer=None, port: int = 0, devi
 
 
 def serve_chain(model_path: str, start_layer=None, end_layer=None, device=None, dtype=None, num_pages: int = 2048,
-                page_size: int = 64):
+                page_size: int = 64, num_groups=None, max_tokens: int = 2048, max_seqs: int = 64, transport: str = "auto"):
     """Native mode: this process is rank r > 0 of the chain pipeline (see parallel/pipeline.py)."""
     from ..config import ModelConfig
     from ..parallel.partition import balanced_split
-    from ..parallel.pipeline import StageExecutor, worker_loop
-    from ..parallel.transport import TorchDistTransport, init_distributed
+    from ..parallel.pipeline import StageExecutor, build_chain, worker_loop
+    from ..parallel.transport import init_distributed
     from ..utils.checkpoint import get_model_path
     from ..utils.loader import load_model
 
@@ -56,9 +56,10 @@ def serve_chain(model_path: str, start_layer=None, end_layer=None, device=None, 
     dev = device or (f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else "cpu")
     model = load_model(model_path, start_layer, end_layer, dtype=dtype, device=dev)
     stage = StageExecutor(model, num_pages, page_size)
-    tp = TorchDistTransport(dev)
-    log.info("rank %d/%d serving layers [%d, %d)", rank, world, model.spec.start_layer, model.spec.end_layer)
-    worker_loop(stage, tp)
+    # collective with the front end (openai_api.py / generate.py): same geometry on every rank
+    ctl, plane = build_chain(stage, num_groups=num_groups, max_tokens=max_tokens, max_seqs=max_seqs, transport=transport)
+    log.info("rank %d/%d serving layers [%d, %d) (hand-off: %s)", rank, world, model.spec.start_layer, model.spec.end_layer, plane.name)
+    worker_loop(stage, ctl, plane)
 
 
 def main(argv=None):

@@ -15,15 +15,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, C, prompts, n_new, q, half=False):
+def _worker(rank, world, port, C, prompts, n_new, q, half=False, control="auto", fail_at=None):
     import torch.distributed as dist
 
     from mlx_sharding_b200.config import ModelConfig, ShardSpec
     from mlx_sharding_b200.engine.core import LLMEngine
     from mlx_sharding_b200.engine.sampler import SamplingParams
     from mlx_sharding_b200.models import build_stage
-    from mlx_sharding_b200.parallel.pipeline import ChainPipeline, StageExecutor, worker_loop
-    from mlx_sharding_b200.parallel.transport import TorchDistTransport
+    from mlx_sharding_b200.parallel.pipeline import ChainPipeline, StageExecutor, build_chain, worker_loop
     from mlx_sharding_b200.utils.checkpoint import random_state_dict
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -41,30 +40,71 @@ def _worker(rank, world, port, C, prompts, n_new, q, half=False):
     sd = dict(random_state_dict(cfg, spec, dtype=torch.float32))
     model = build_stage(cfg, spec, torch.float32).load_state(sd)
     stage = StageExecutor(model, num_pages=32, page_size=16)
-    tp = TorchDistTransport("cpu")
+    ctl, plane = build_chain(stage, num_groups=world, max_tokens=64, max_seqs=8, control=control)
     if rank == 0:
-        pipe = ChainPipeline(stage, tp)
+        pipe = ChainPipeline(stage, ctl, plane)
         eng = LLMEngine(pipe, num_pages=32, page_size=16, num_groups=world)
-        reqs = [eng.submit(p, SamplingParams(), max_tokens=n_new) for p in prompts]
-        eng.drain()
+        if fail_at is None:
+            reqs = [eng.submit(p, SamplingParams(), max_tokens=n_new) for p in prompts]
+            eng.drain()
+            out = [r.output for r in reqs]
+        else:
+            out = _drive_with_failure(eng, prompts, n_new)
         pipe.shutdown()
-        q.put([r.output for r in reqs])
+        q.put(out)
     else:
-        worker_loop(stage, tp)
+        if fail_at is not None and rank == world - 1:
+            # inject one failure into this stage's forward after ``fail_at`` steps (two groups are in flight at that point)
+            calls, real = [0], stage.model.forward
+
+            def flaky(*a, **k):
+                calls[0] += 1
+                if calls[0] == fail_at:
+                    raise RuntimeError("injected stage failure")
+                return real(*a, **k)
+
+            stage.model.forward = flaky
+        worker_loop(stage, ctl, plane)
     dist.barrier()
     dist.destroy_process_group()
 
 
+def _drive_with_failure(eng, prompts, n_new):
+    """Two groups in flight, a worker raises once: every active request fails cleanly, pages come back, no stale result is
+    attributed to a later step, and the pipeline serves new requests afterwards (step ids + drain before release)."""
+    from mlx_sharding_b200.engine.sampler import SamplingParams
+
+    free0 = eng.table.alloc.num_free
+    reqs = [eng.submit(p, SamplingParams(), max_tokens=50) for p in prompts]
+    for _ in range(200):
+        if all(r.finished for r in reqs):
+            break
+        try:
+            eng.step()
+        except BaseException as e:  # the engine thread does this in _loop
+            eng._fail_all(e)
+    assert all(r.finished and r.error is not None for r in reqs), [(r.finished, r.error) for r in reqs]
+    assert eng.table.alloc.num_free == free0
+    assert not eng.pipe._outstanding
+    again = [eng.submit(p, SamplingParams(), max_tokens=n_new) for p in prompts]
+    eng.drain()
+    assert all(r.error is None for r in again)
+    return [r.output for r in again]
+
+
 @pytest.mark.timeout(180)
-@pytest.mark.parametrize("world,half", [(2, False), (3, False), (3, True)])
-def test_gloo_chain_matches_single_process(world, half):
+@pytest.mark.parametrize("world,half,control,fail_at", [(2, False, "shm", None), (3, False, "shm", None), (3, True, "dist", None),
+                                                        (2, False, "shm", 4), (2, False, "dist", 4)])
+def test_gloo_chain_matches_single_process(world, half, control, fail_at):
+    """Chain over gloo with the shared-memory launch ring (``shm``) and with the broadcast fallback (``dist``); ``fail_at``:
+    the last stage raises once mid-generation (see ``_drive_with_failure``)."""
     C = dict(TINY_LLAMA, num_hidden_layers=2 if world == 2 else 3)
     prompts = [[5, 6, 7, 8], [100, 50, 3], [9] * 6]
     n_new = 5
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, C, prompts, n_new, q, half)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, C, prompts, n_new, q, half, control, fail_at)) for r in range(world)]
     for p in procs:
         p.start()
     got = q.get(timeout=150)

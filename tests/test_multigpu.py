@@ -25,6 +25,14 @@ def test_pipeline_parity(arch, transport, port):
     assert "PARITY_OK" in out, out[-3000:]
 
 
+@pytest.mark.parametrize("arch,transport,port", [("dsv2", "fused", 29581), ("llama", "fused", 29582), ("dsv2", "nccl", 29583)])
+def test_serving_chain_parity(arch, transport, port):
+    """The product path: LLMEngine -> ChainPipeline (shared-memory launch ring, fused P2P hand-off inside per-stage CUDA graphs),
+    greedy + seeded sampled requests, against a single-GPU engine."""
+    out = _torchrun("serving_chain_parity.py", [arch, transport], port=port)
+    assert "SERVING_OK" in out, out[-3000:]
+
+
 def test_expert_parallel_moe():
     out = _torchrun("ep_parity.py", [], port=29574)
     assert "EP_OK" in out, out[-3000:]
