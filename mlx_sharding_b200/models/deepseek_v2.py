@@ -46,8 +46,38 @@ class DeepseekV2Stage(StageModel):
     def kv_geometry(self):
         if self.absorbed_mla:
             c = self.cfg
-            return self.spec.num_kv_layers, 1, c.kv_lora_rank + c.qk_rope_head_dim, c.kv_lora_rank
+            # the sm_100a kernel reads the values as the first 512 dims of the cached key row (no second pool)
+            dv = 0 if self.backend_name == "b200" else c.kv_lora_rank
+            return self.spec.num_kv_layers, 1, c.kv_lora_rank + c.qk_rope_head_dim, dv
         return super().kv_geometry()
+
+    def _post_load(self):
+        """Absorbed-latent MLA on the CUDA backend: fold ``W_UK`` into the query projection and ``W_UV`` into the output
+        projection once at load (fp32 products, one bf16 rounding):
+
+            q_abs[h] = W_UK[h]^T (W_q_nope[h] x)            -> rows [h*576, h*576+512) of ``qkv_abs`` (q_pe rows follow, then kv_a)
+            out     = sum_h (W_o[:, h] W_UV[h]) o_lat[h]     -> ``o_abs`` [H, 16*512]
+
+        so a decode step needs no kv_b GEMM and attention runs on the cached 576-dim latent (``ops/csrc/mla_decode.cu``).  The
+        original q / kv_b / o weights stay for prefill chunks, which decompress the context they attend to."""
+        c = self.cfg
+        if not (self.absorbed_mla and self.backend_name == "b200"):
+            return
+        if c.q_lora_rank is not None or not self.ops.mla_absorbed_supported(c.num_attention_heads, c.kv_lora_rank, c.qk_rope_head_dim):
+            raise NotImplementedError("absorbed-latent MLA kernel: 16 heads, kv_lora_rank 512, rope 64, no q-LoRA (DeepSeek-V2-Lite shapes)")
+        nh, nope, rd, vd, lr, H = c.num_attention_heads, c.qk_nope_head_dim, c.qk_rope_head_dim, c.v_head_dim, c.kv_lora_rank, c.hidden_size
+        for w in self.layer_weights.values():
+            if "qkv_a" not in w:
+                continue
+            qkv = w["qkv_a"].dense(torch.float32)                               # [nh*(nope+rd) + lr + rd, H]
+            wq = qkv[: nh * (nope + rd)].view(nh, nope + rd, H)
+            wkv = w["kv_b"].dense(torch.float32).view(nh, nope + vd, lr)
+            q_abs = torch.einsum("hnl,hnk->hlk", wkv[:, :nope], wq[:, :nope])    # [nh, lr, H]
+            rows = torch.cat([torch.cat([q_abs, wq[:, nope:]], 1).reshape(nh * (lr + rd), H), qkv[nh * (nope + rd):]], 0)
+            w["qkv_abs"] = LinearWeight(weight=rows.to(self.dtype).contiguous())
+            wo = w["o"].dense(torch.float32).view(H, nh, vd)
+            o_abs = torch.einsum("ohv,hvl->ohl", wo, wkv[:, nope:]).reshape(H, nh * lr)
+            w["o_abs"] = LinearWeight(weight=o_abs.to(self.dtype).contiguous(), bias=w["o"].bias)
 
     def sanitize(self, sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         sd = super().sanitize(sd)
@@ -107,6 +137,15 @@ class DeepseekV2Stage(StageModel):
                                 c.v_head_dim, c.kv_lora_rank)
         qd = nope + rd
         normed = O.rmsnorm(h, w["in_ln"], c.rms_norm_eps)
+        if "qkv_abs" in w and meta.max_q_len == 1 and meta.num_tokens == meta.num_seqs:
+            # decode step on the absorbed weights: one GEMM -> [q_abs | q_pe] x 16 heads, c_kv, k_pe; fused prologue (latent norm,
+            # both ropes, cache append); tcgen05 multi-query attention over the cached latent; folded output projection
+            qkv = O.linear(normed, w["qkv_abs"])
+            qa = qkv[:, : nh * (lr + rd)].unflatten(1, (nh, lr + rd))
+            O.mla_absorbed_prologue(qa, qkv[:, nh * (lr + rd): nh * (lr + rd) + lr], qkv[:, nh * (lr + rd) + lr:], w["kv_a_ln"],
+                                    c.rms_norm_eps, kpool, meta, self.rope)
+            o_lat = O.mla_decode(qa, kpool, meta, c.attn_scale)
+            return O.linear(o_lat.view(T, nh * lr), w["o_abs"], residual=h, **self._final_kwargs(i, T, "attn"))
         if "qkv_a" in w:
             qkv = O.linear(normed, w["qkv_a"])
             q = qkv[:, : nh * qd]
@@ -118,6 +157,8 @@ class DeepseekV2Stage(StageModel):
             q = O.linear(O.rmsnorm(qa[:, :ql], w["q_a_ln"], c.rms_norm_eps), w["q_b"])
             ckv, k_pe = qa[:, ql: ql + lr], qa[:, ql + lr:]
         q = q.view(T, nh, qd) if q.is_contiguous() else q.unflatten(1, (nh, qd))
+        if self.absorbed_mla and self.backend_name == "b200":
+            return self._attn_absorbed_b200(i, w, h, q, ckv, k_pe, meta, kpool)
         if self.absorbed_mla:
             return O.linear(self._attn_absorbed(w, q, ckv, k_pe, meta, kpool, vpool), w["o"], residual=h,
                             **self._final_kwargs(i, T, "attn"))
@@ -134,8 +175,6 @@ class DeepseekV2Stage(StageModel):
             sum_t p_t v_t   = W_UV (sum_t p_t c_t)       -> output side absorbs W_UV
 
         so attention runs as multi-query attention over the cached ``[c | rope(k_pe)]`` (576) with values ``c`` (512)."""
-        if self.backend_name != "reference":
-            raise NotImplementedError("absorbed-latent MLA: only the reference backend implements it so far")
         O, c = self.ops, self.cfg
         T = q.shape[0]
         nh, nope, rd, vd, lr = c.num_attention_heads, c.qk_nope_head_dim, c.qk_rope_head_dim, c.v_head_dim, c.kv_lora_rank
@@ -149,6 +188,33 @@ class DeepseekV2Stage(StageModel):
         O.kv_write(torch.cat([lat.unsqueeze(1), kpe.to(lat.dtype)], -1), lat.unsqueeze(1), kpool, vpool, meta.slot_mapping)
         o_lat = O.paged_attention(torch.cat([q_abs, q[..., nope:]], -1), kpool, vpool, meta, c.attn_scale, 0.0)   # [T, nh, lr]
         return torch.einsum("thl,hvl->thv", o_lat.float(), wkv[:, nope:]).to(q.dtype).reshape(T, nh * vd)
+
+    def _attn_absorbed_b200(self, i, w, h, q, ckv, k_pe, meta: BatchMeta, kpool):
+        """Prefill chunk / mixed batch with the latent cache (CUDA backend): append this chunk's latents, then *decompress the
+        context the batch attends to* (``kv_b`` GEMM over the cached latents of its sequences) into a temporary per-head K/V pool
+        and run the tensor-core flash-prefill kernel on it.  Costs O(context) extra GEMM work per chunk, prefill only; decode steps
+        never come here (``attn_block`` routes them to the tcgen05 latent kernel)."""
+        O, c = self.ops, self.cfg
+        T = h.shape[0]
+        nh, nope, rd, vd, lr = c.num_attention_heads, c.qk_nope_head_dim, c.qk_rope_head_dim, c.v_head_dim, c.kv_lora_rank
+        page = kpool.shape[2]
+        lat = O.rmsnorm(ckv, w["kv_a_ln"], c.rms_norm_eps)                                      # [T, lr]
+        O.rope_(q, meta.positions, self.rope, nope)                                              # q_pe in place
+        kpe = k_pe.reshape(T, 1, rd).clone()
+        O.rope_(kpe, meta.positions, self.rope, 0)
+        kpool.view(-1, lr + rd).index_copy_(0, meta.slot_mapping.long(), torch.cat([lat, kpe.view(T, rd)], 1))
+        B = meta.num_seqs
+        mb = min(meta.block_tables.shape[1], (meta.max_ctx_len + page - 1) // page)
+        ctx = kpool.view(kpool.shape[0], page, lr + rd)[meta.block_tables[:, :mb].reshape(-1).long()]   # [B*mb, page, 576]
+        rows = ctx.reshape(-1, lr + rd)
+        kvd = O.linear(rows[:, :lr], w["kv_b"]).view(B * mb, page, nh, nope + vd)
+        ktmp = torch.cat([kvd[..., :nope], rows[:, lr:].view(B * mb, page, 1, rd).expand(-1, -1, nh, -1)], -1).permute(0, 2, 1, 3).contiguous()
+        vtmp = kvd[..., nope:].permute(0, 2, 1, 3).contiguous()
+        tmp_meta = BatchMeta(meta.positions, meta.slot_mapping, meta.cu_seqlens, meta.context_lens,
+                             torch.arange(B * mb, dtype=torch.int32, device=h.device).view(B, mb), meta.last_idx, meta.num_tokens,
+                             B, meta.max_q_len, meta.max_ctx_len, page)
+        attn = O.paged_attention(q, ktmp, vtmp, tmp_meta, c.attn_scale, 0.0)
+        return O.linear(attn.reshape(T, nh * vd), w["o"], residual=h, **self._final_kwargs(i, T, "attn"))
 
     def mlp_block(self, i, h, meta: BatchMeta):
         O, c, w = self.ops, self.cfg, self.layer_weights[i]

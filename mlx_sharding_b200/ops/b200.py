@@ -267,6 +267,21 @@ def sample(logits, temperature, top_p, generator: Optional[torch.Generator] = No
     return toks, lp, None, None
 
 
+def mla_absorbed_supported(num_heads: int, kv_lora_rank: int, rope_dim: int, page_size: int = 64) -> bool:
+    """Shapes the tcgen05 absorbed-latent MLA decode kernel is built for (DeepSeek-V2 / V2-Lite / Coder-V2-Lite)."""
+    return num_heads == 16 and kv_lora_rank == 512 and rope_dim == 64 and page_size == 64
+
+
+def mla_absorbed_prologue(q, ckv, k_pe, norm_w, eps: float, pool, meta: BatchMeta, spec: RopeSpec):
+    """latent = RMSNorm(c_kv) -> pool[slot][:512], rope(k_pe) -> pool[slot][512:], rope(q_pe) in place: one launch."""
+    C().mla_absorbed_prologue(q, ckv, k_pe, norm_w, float(eps), pool, meta.slot_mapping, meta.positions, spec.inv_freq, float(spec.mscale))
+
+
+def mla_decode(q, pool, meta: BatchMeta, scale: float, nsplit: int = 0):
+    """Multi-query attention over the cached latent (d_qk 576 / d_v 512) on tcgen05: ``[B, 16, 576] -> [B, 16, 512]``."""
+    return C().mla_decode(q, pool, meta.block_tables, meta.context_lens, float(scale), int(meta.max_ctx_len), int(nsplit))
+
+
 def sample_block(logits, sv, tag_out, toks_out, lp_out, top_ids_out, top_lp_out):
     """Sampling driven by a step block in device memory (``parallel/graph_decode.py``): every per-step input — temperatures,
     nucleus thresholds, per-request (seed, step) RNG state, penalty contexts, bias tables, the step tag — is read by the kernels

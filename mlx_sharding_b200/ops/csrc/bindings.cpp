@@ -378,6 +378,49 @@ Tensor flash_prefill(const Tensor& q, const Tensor& kpool, const Tensor& vpool, 
 }
 bool flash_prefill_supported(int64_t dk, int64_t dv) { return b200::flash_prefill_supported((int)dk, (int)dv); }
 
+// ---- absorbed-latent MLA ----------------------------------------------------------------------------------------
+void mla_absorbed_prologue(Tensor q, const Tensor& ckv, const Tensor& kpe, const Tensor& norm_w, double eps, Tensor pool,
+                           const Tensor& slots, const Tensor& positions, const Tensor& inv_freq, double mscale) {
+  check_bf16(q, "q"); check_bf16(ckv, "ckv"); check_bf16(kpe, "kpe"); check_bf16(norm_w, "norm_w"); check_bf16(pool, "pool");
+  TORCH_CHECK(q.dim() == 3 && q.size(1) == 16 && q.size(2) == 576 && q.stride(2) == 1 && q.stride(1) == 576, "q must be [T,16,576] with packed heads");
+  TORCH_CHECK(ckv.dim() == 2 && ckv.size(1) == 512 && ckv.stride(1) == 1 && kpe.dim() == 2 && kpe.size(1) == 64 && kpe.stride(1) == 1);
+  TORCH_CHECK(pool.is_contiguous() && pool.size(-1) == 576 && norm_w.is_contiguous() && norm_w.numel() == 512);
+  TORCH_CHECK(slots.scalar_type() == torch::kInt32 && positions.scalar_type() == torch::kInt32 && inv_freq.scalar_type() == torch::kFloat32 &&
+              inv_freq.numel() == 32);
+  const c10::cuda::CUDAGuard guard(q.device());
+  LAUNCH_OK(b200::mla_absorbed_prologue_launch(q.data_ptr(), q.stride(0), ckv.data_ptr(), ckv.stride(0), kpe.data_ptr(), kpe.stride(0),
+                                               norm_w.data_ptr(), (float)eps, pool.data_ptr(), slots.data_ptr<int>(),
+                                               positions.data_ptr<int>(), inv_freq.data_ptr<float>(), (float)mscale, (int)q.size(0),
+                                               cur_stream()));
+}
+
+Tensor mla_decode(const Tensor& q, const Tensor& pool, const Tensor& block_tables, const Tensor& context_lens, double scale,
+                  int64_t max_ctx, int64_t nsplit_req) {
+  check_bf16(q, "q"); check_bf16(pool, "pool");
+  TORCH_CHECK(q.dim() == 3 && q.size(1) == 16 && q.size(2) == 576 && q.stride(2) == 1 && q.stride(1) == 576, "q must be [B,16,576] with packed heads");
+  TORCH_CHECK(pool.is_contiguous() && pool.dim() == 4 && pool.size(1) == 1 && pool.size(2) == 64 && pool.size(3) == 576,
+              "latent pool must be [pages, 1, 64, 576]");
+  TORCH_CHECK(block_tables.scalar_type() == torch::kInt32 && block_tables.is_contiguous() && context_lens.scalar_type() == torch::kInt32);
+  const c10::cuda::CUDAGuard guard(q.device());
+  const int B = (int)q.size(0);
+  Tensor out = torch::empty({B, 16, 512}, q.options());
+  if (B == 0) return out;
+  const int tiles = (int)((max_ctx + 63) / 64);
+  int nsplit = (int)nsplit_req;
+  if (nsplit <= 0) {   // flash-decoding split: until one wave of CTAs exists, keeping >= 2 tiles per split
+    nsplit = 1;
+    while (B * nsplit < sm_count() && tiles / (nsplit * 2) >= 2 && nsplit < 64) nsplit *= 2;
+  }
+  if (nsplit > tiles) nsplit = tiles > 0 ? tiles : 1;
+  float* ws = nullptr;
+  if (nsplit > 1) ws = scratch().get_ws((int64_t)b200::mla_decode_workspace_floats(B, nsplit), q.device()).data_ptr<float>();
+  LAUNCH_OK(b200::mla_decode_launch(q.data_ptr(), q.stride(0), B, pool.data_ptr(), pool.size(0), 64, block_tables.data_ptr<int>(),
+                                    (int)block_tables.size(1), context_lens.data_ptr<int>(), (int)max_ctx, (float)scale, nsplit, ws,
+                                    out.data_ptr(), (long long)16 * 512, cur_stream()));
+  if (nsplit > 1) ++g_launches;
+  return out;
+}
+
 // ---- MoE --------------------------------------------------------------------------------------------------------
 std::vector<Tensor> moe_route(const Tensor& x, const Tensor& gate_w, int64_t top_k, int64_t n_group, int64_t topk_group, double scaling,
                               bool norm_topk) {
@@ -507,9 +550,10 @@ Tensor tensor_from_ptr(int64_t ptr, std::vector<int64_t> shape, const std::strin
 void wait_flag(int64_t flag_ptr, int64_t expected, int64_t error_ptr) {
   LAUNCH_OK(b200::wait_flag_launch(reinterpret_cast<const uint32_t*>(flag_ptr), (uint32_t)expected, reinterpret_cast<uint32_t*>(error_ptr), cur_stream()));
 }
-void wait_flag_counter(int64_t flag_ptr, int64_t counter_ptr, int64_t error_ptr) {
+void wait_flag_counter(int64_t flag_ptr, int64_t counter_ptr, int64_t error_ptr, int64_t error_host_ptr) {
   LAUNCH_OK(b200::wait_flag_counter_launch(reinterpret_cast<const uint32_t*>(flag_ptr), reinterpret_cast<uint32_t*>(counter_ptr),
-                                         reinterpret_cast<uint32_t*>(error_ptr), cur_stream()));
+                                         reinterpret_cast<uint32_t*>(error_ptr), reinterpret_cast<uint32_t*>(error_host_ptr),
+                                         cur_stream()));
 }
 void set_flag(int64_t flag_ptr, int64_t value) { LAUNCH_OK(b200::set_flag_launch(reinterpret_cast<uint32_t*>(flag_ptr), (uint32_t)value, cur_stream())); }
 void copy_signal(const Tensor& src, int64_t dst_ptr, int64_t flag_ptr, int64_t value) {
@@ -615,6 +659,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("paged_attention", &paged_attention);
   m.def("flash_prefill", &flash_prefill);
   m.def("flash_prefill_supported", &flash_prefill_supported);
+  m.def("mla_absorbed_prologue", &mla_absorbed_prologue);
+  m.def("mla_decode", &mla_decode, py::arg("q"), py::arg("pool"), py::arg("block_tables"), py::arg("context_lens"), py::arg("scale"),
+        py::arg("max_ctx"), py::arg("nsplit") = 0);
   m.def("moe_route", &moe_route);
   m.def("moe_permute", &moe_permute);
   m.def("moe_combine", &moe_combine, py::arg("y_perm"), py::arg("pair_row"), py::arg("wts"), py::arg("residual") = py::none(),
@@ -629,7 +676,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("enable_peer_access", &enable_peer_access);
   m.def("tensor_from_ptr", &tensor_from_ptr);
   m.def("wait_flag", &wait_flag);
-  m.def("wait_flag_counter", &wait_flag_counter);
+  m.def("wait_flag_counter", &wait_flag_counter, py::arg("flag_ptr"), py::arg("counter_ptr"), py::arg("error_ptr"),
+        py::arg("error_host_ptr") = 0);
   m.def("set_flag", &set_flag);
   m.def("copy_signal", &copy_signal);
   m.def("advance_meta", &advance_meta);

@@ -52,6 +52,16 @@ struct FlashPrefillArgs {
 bool flash_prefill_supported(int dk, int dv);
 cudaError_t flash_prefill_launch(const FlashPrefillArgs& a, cudaStream_t s);
 
+// ---- mla_decode.cu (absorbed-latent MLA: tcgen05 decode attention over the cached 576-dim latent, + its prologue)
+cudaError_t mla_absorbed_prologue_launch(void* q, long long q_ld_t, const void* ckv, long long ckv_ld_t, const void* kpe,
+                                         long long pe_ld_t, const void* norm_w, float eps, void* pool, const int* slots,
+                                         const int* positions, const float* inv_freq, float mscale, int T, cudaStream_t s);
+size_t mla_decode_workspace_floats(int B, int nsplit);
+// q: bf16 [B, 16, 576] (head stride 576, token stride q_ld_t); pool: bf16 [num_pages, 1, 64, 576]; out: bf16 [B, 16, 512]
+cudaError_t mla_decode_launch(const void* q, long long q_ld_t, int B, const void* pool, long long num_pages, int page,
+                              const int* block_tables, int max_blocks, const int* context_lens, int max_ctx, float scale,
+                              int nsplit, float* workspace, void* out, long long o_ld_t, cudaStream_t s);
+
 // ---- moe.cu
 // router: fp32 softmax(x W^T) -> top-k (optionally group limited) -> weights * scaling (or normalised)
 cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, int T, int H, int E, int top_k,
@@ -79,7 +89,9 @@ cudaError_t sample_launch(const float* logits, int B, int V, const float* temper
 
 // ---- p2p.cu
 cudaError_t wait_flag_launch(const uint32_t* flag, uint32_t expected, uint32_t* error_flag, cudaStream_t s);
-cudaError_t wait_flag_counter_launch(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag, cudaStream_t s);
+// error_host (optional): mapped pinned host word set on a timeout, so the host can poll for failures without a device sync
+cudaError_t wait_flag_counter_launch(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag, uint32_t* error_host,
+                                     cudaStream_t s);
 cudaError_t set_flag_launch(uint32_t* flag, uint32_t value, cudaStream_t s);
 cudaError_t copy_signal_launch(const void* src, void* dst, size_t bytes, uint32_t* flag, uint32_t value,
                                unsigned int* done_counter, cudaStream_t s);

@@ -38,7 +38,7 @@ __global__ void wait_flag_kernel(const uint32_t* flag, uint32_t expected, uint32
 // Counting variant for CUDA-graph replay: the expected value is this consumer's own arrival count, kept in
 // device memory (`local_counter`), so the same captured node is correct on every replay.
 __global__ void wait_flag_counter_kernel(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag,
-                                         unsigned long long timeout_ns) {
+                                         uint32_t* error_host, unsigned long long timeout_ns) {
   pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const uint32_t expected = atomicAdd(local_counter, 1u) + 1u;
   const unsigned long long t0 = globaltimer_ns();
@@ -50,6 +50,8 @@ __global__ void wait_flag_counter_kernel(const uint32_t* flag, uint32_t* local_c
     if (error_flag != nullptr && *reinterpret_cast<volatile uint32_t*>(error_flag) != 0u) break;
     if (globaltimer_ns() - t0 > timeout_ns) {
       if (error_flag != nullptr) atomicExch(error_flag, 1u);
+      // mirror in mapped pinned host memory: the host learns about the timeout with a plain load, without a device sync
+      if (error_host != nullptr) { *reinterpret_cast<volatile uint32_t*>(error_host) = 1u; __threadfence_system(); }
       break;
     }
     __nanosleep(32);
@@ -109,8 +111,9 @@ cudaError_t wait_flag_launch(const uint32_t* flag, uint32_t expected, uint32_t* 
   return cudaGetLastError();
 }
 
-cudaError_t wait_flag_counter_launch(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag, cudaStream_t s) {
-  (void)launch_pdl(wait_flag_counter_kernel, dim3(1), dim3(1), 0, s, flag, local_counter, error_flag, wait_timeout_ns());
+cudaError_t wait_flag_counter_launch(const uint32_t* flag, uint32_t* local_counter, uint32_t* error_flag, uint32_t* error_host,
+                                     cudaStream_t s) {
+  (void)launch_pdl(wait_flag_counter_kernel, dim3(1), dim3(1), 0, s, flag, local_counter, error_flag, error_host, wait_timeout_ns());
   return cudaGetLastError();
 }
 

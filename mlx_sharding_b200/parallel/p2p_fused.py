@@ -70,6 +70,9 @@ class FusedP2PBoundary:
         self.next_rank = nxt
         # device-resident arrival counters (consumer side) + error word
         self.counters = torch.zeros(2 * num_groups + 1, dtype=torch.int32, device="cuda")
+        # host-visible mirror of the error word (mapped pinned memory): a wait kernel that times out sets it, ``error()`` is a plain
+        # load — no device synchronisation on the serving path
+        self.err_host = torch.zeros(4, dtype=torch.int32).pin_memory()
         dist.barrier(group=group)
 
     # -- address helpers ---------------------------------------------------------------------------
@@ -104,11 +107,12 @@ class FusedP2PBoundary:
 
     # -- stream-ordered primitives -------------------------------------------------------------------
     def wait_hidden(self, g: int):
-        self.C.wait_flag_counter(self._flag_ptr(self.base, g, 0), self.counters[g].data_ptr(), self.counters[-1].data_ptr())
+        self.C.wait_flag_counter(self._flag_ptr(self.base, g, 0), self.counters[g].data_ptr(), self.counters[-1].data_ptr(),
+                                 self.err_host.data_ptr())
 
     def wait_tokens(self, g: int):
         self.C.wait_flag_counter(self._flag_ptr(self.base, g, 1), self.counters[self.G + g].data_ptr(),
-                                 self.counters[-1].data_ptr())
+                                 self.counters[-1].data_ptr(), self.err_host.data_ptr())
 
     def send_tokens(self, tokens: torch.Tensor, g: int):
         """Last stage -> stage 0: sampled token ids (8 B per sequence instead of the reference's full
@@ -131,5 +135,8 @@ class FusedP2PBoundary:
         """Un-fused fallback (e.g. Gemma-2, whose last op is a norm): copy kernel + signal."""
         self.C.copy_signal(x.contiguous(), self._hidden_ptr(self.peer_base[self.next_rank], g), self.next_hidden_flag(g), 0)
 
-    def error(self) -> bool:
-        return bool(self.counters[-1].item())
+    def error(self, sync: bool = False) -> bool:
+        """True once a flag wait on this device timed out.  Default: read the mapped host mirror (no device sync)."""
+        if sync:
+            return bool(self.counters[-1].item())
+        return bool(self.err_host[0])

@@ -536,6 +536,7 @@ class ChainPipeline:
 def worker_loop(stage: StageExecutor, ctl, plane):
     """Non-first stage: execute the launch records of the control plane in order until shutdown."""
     runner = StepRunner(stage, plane)
+    timed_out = False
     while True:
         rec = ctl.next()
         if rec is None:
@@ -551,6 +552,9 @@ def worker_loop(stage: StageExecutor, ctl, plane):
             log.exception("stage %d failed", ctl.rank)
             ctl.set_error(seq, f"{type(e).__name__}: {e}")
             runner.poison(wire, group)
+        if not timed_out and plane.failed():
+            timed_out = True
+            ctl.set_error(seq, "P2P flag wait timed out: the previous stage is not responding")
     if stage.device.type == "cuda":
         torch.cuda.synchronize(stage.device)
     tp = getattr(plane, "tp", None)
