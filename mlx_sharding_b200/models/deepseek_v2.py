@@ -29,11 +29,21 @@ _EXPERT_RE = re.compile(r"^(model\.layers\.\d+\.mlp)\.experts\.(\d+)\.(gate_proj
 class DeepseekV2Stage(StageModel):
     arch = "deepseek_v2"
     overlap_shared_experts = os.environ.get("MLXB200_OVERLAP_SHARED", "1") != "0"
-    # Opt-in KV layout: cache the 512-dim latent + the 64-dim roped key (one shared "head", 576 + 512 values per token)
-    # instead of the decompressed per-head K/V (16 x (192 + 128) = 5120 values) and absorb kv_b into the query / output
-    # side.  Mathematically identical attention (see ``_attn_absorbed``); today only the reference backend implements it —
-    # the sm_100a kernel for d_qk = 576 / d_v = 512 multi-query attention is the next step (docs/NEXT.md).
-    absorbed_mla = os.environ.get("MLXB200_ABSORBED_MLA", "0") == "1"
+    # KV layout: cache the 512-dim latent + the 64-dim roped key (one shared "head", 576 values per token) instead of the
+    # reference's decompressed per-head K/V (16 x (192 + 128) = 5120 values, shard/server/model/deepseek_v2.py:120-125) and absorb
+    # kv_b into the query / output side.  Mathematically identical attention (see ``_attn_absorbed``).
+    #   None (default): automatic — on when the sm_100a latent-attention kernel supports the shapes (16 heads, kv_lora_rank 512,
+    #                   rope 64, no q-LoRA, unquantised attention weights, 64-token pages: DeepSeek-V2-Lite / Coder-V2-Lite);
+    #   MLXB200_ABSORBED_MLA=0 / 1 forces it off / on (``1`` on the reference backend selects the einsum formulation).
+    absorbed_mla = {"0": False, "1": True}.get(os.environ.get("MLXB200_ABSORBED_MLA", ""), None)
+
+    def __init__(self, cfg, spec=None, dtype=torch.bfloat16, device="cpu", backend=None):
+        super().__init__(cfg, spec, dtype, device, backend)
+        if self.absorbed_mla is None:
+            c = cfg
+            self.absorbed_mla = bool(
+                self.backend_name == "b200" and c.q_lora_rank is None and not c.quantization and dtype == torch.bfloat16
+                and self.ops.mla_absorbed_supported(c.num_attention_heads, c.kv_lora_rank, c.qk_rope_head_dim))
 
     @property
     def head_dim(self):
@@ -65,6 +75,12 @@ class DeepseekV2Stage(StageModel):
             return
         if c.q_lora_rank is not None or not self.ops.mla_absorbed_supported(c.num_attention_heads, c.kv_lora_rank, c.qk_rope_head_dim):
             raise NotImplementedError("absorbed-latent MLA kernel: 16 heads, kv_lora_rank 512, rope 64, no q-LoRA (DeepSeek-V2-Lite shapes)")
+        if any(w[k].is_quantized for w in self.layer_weights.values() for k in ("qkv_a", "kv_b", "o") if k in w):
+            # quantised attention weights keep their packed form (and the reference's cache layout): folding would expand them
+            if os.environ.get("MLXB200_ABSORBED_MLA") == "1":
+                raise NotImplementedError("absorbed-latent MLA with quantised attention weights")
+            self.absorbed_mla = False
+            return
         nh, nope, rd, vd, lr, H = c.num_attention_heads, c.qk_nope_head_dim, c.qk_rope_head_dim, c.v_head_dim, c.kv_lora_rank, c.hidden_size
         for w in self.layer_weights.values():
             if "qkv_a" not in w:
@@ -137,7 +153,7 @@ class DeepseekV2Stage(StageModel):
                                 c.v_head_dim, c.kv_lora_rank)
         qd = nope + rd
         normed = O.rmsnorm(h, w["in_ln"], c.rms_norm_eps)
-        if "qkv_abs" in w and meta.max_q_len == 1 and meta.num_tokens == meta.num_seqs:
+        if "qkv_abs" in w and meta.max_q_len == 1 and meta.num_tokens == meta.num_seqs and kpool.shape[2] == 64:
             # decode step on the absorbed weights: one GEMM -> [q_abs | q_pe] x 16 heads, c_kv, k_pe; fused prologue (latent norm,
             # both ropes, cache append); tcgen05 multi-query attention over the cached latent; folded output projection
             qkv = O.linear(normed, w["qkv_abs"])

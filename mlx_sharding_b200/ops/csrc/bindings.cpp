@@ -395,7 +395,7 @@ void mla_absorbed_prologue(Tensor q, const Tensor& ckv, const Tensor& kpe, const
 }
 
 Tensor mla_decode(const Tensor& q, const Tensor& pool, const Tensor& block_tables, const Tensor& context_lens, double scale,
-                  int64_t max_ctx, int64_t nsplit_req) {
+                  int64_t max_ctx, int64_t nsplit_req, const c10::optional<Tensor>& trace) {
   check_bf16(q, "q"); check_bf16(pool, "pool");
   TORCH_CHECK(q.dim() == 3 && q.size(1) == 16 && q.size(2) == 576 && q.stride(2) == 1 && q.stride(1) == 576, "q must be [B,16,576] with packed heads");
   TORCH_CHECK(pool.is_contiguous() && pool.dim() == 4 && pool.size(1) == 1 && pool.size(2) == 64 && pool.size(3) == 576,
@@ -416,7 +416,8 @@ Tensor mla_decode(const Tensor& q, const Tensor& pool, const Tensor& block_table
   if (nsplit > 1) ws = scratch().get_ws((int64_t)b200::mla_decode_workspace_floats(B, nsplit), q.device()).data_ptr<float>();
   LAUNCH_OK(b200::mla_decode_launch(q.data_ptr(), q.stride(0), B, pool.data_ptr(), pool.size(0), 64, block_tables.data_ptr<int>(),
                                     (int)block_tables.size(1), context_lens.data_ptr<int>(), (int)max_ctx, (float)scale, nsplit, ws,
-                                    out.data_ptr(), (long long)16 * 512, cur_stream()));
+                                    out.data_ptr(), (long long)16 * 512,
+                                    trace.has_value() ? reinterpret_cast<long long*>(trace->data_ptr<int64_t>()) : nullptr, cur_stream()));
   if (nsplit > 1) ++g_launches;
   return out;
 }
@@ -661,7 +662,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("flash_prefill_supported", &flash_prefill_supported);
   m.def("mla_absorbed_prologue", &mla_absorbed_prologue);
   m.def("mla_decode", &mla_decode, py::arg("q"), py::arg("pool"), py::arg("block_tables"), py::arg("context_lens"), py::arg("scale"),
-        py::arg("max_ctx"), py::arg("nsplit") = 0);
+        py::arg("max_ctx"), py::arg("nsplit") = 0, py::arg("trace") = py::none());
   m.def("moe_route", &moe_route);
   m.def("moe_permute", &moe_permute);
   m.def("moe_combine", &moe_combine, py::arg("y_perm"), py::arg("pair_row"), py::arg("wts"), py::arg("residual") = py::none(),

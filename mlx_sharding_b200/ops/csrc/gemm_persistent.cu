@@ -134,7 +134,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
 
   if (warp == 0) {
     // ============================================================== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane: uniform-datapath issue, no per-instruction ELECT loop (ptx.cuh)
       // Weights never depend on a predecessor kernel: the first ring-full of weight tiles is requested *before*
       // griddepcontrol.wait (HBM latency overlaps the predecessor's tail); the activation tiles follow after it.
       // (un-grouped launches only: iteration i <-> tile blockIdx.x + (i / kb_total) * gridDim.x, k-block i % kb_total)
@@ -177,7 +177,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
     }
   } else if (warp == 1) {
     // ============================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane: uniform-datapath issue, no per-instruction ELECT loop (ptx.cuh)
       uint32_t it = 0, tc = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const TileInfo ti = decode_tile(p, t, tiles_n, tiles_m, BN);

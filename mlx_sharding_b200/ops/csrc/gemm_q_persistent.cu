@@ -138,7 +138,7 @@ gemm_q_persistent_kernel(const __grid_constant__ CUtensorMap tmap_wq, const __gr
 
   if (warp == 0) {
     // ============================================================== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane: uniform-datapath issue, no per-instruction ELECT loop (ptx.cuh)
       uint32_t it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const QTile ti = q_decode_tile(p, t, tiles_n, tiles_m, BN);
@@ -163,7 +163,7 @@ gemm_q_persistent_kernel(const __grid_constant__ CUtensorMap tmap_wq, const __gr
     }
   } else if (warp == 1) {
     // ============================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane: uniform-datapath issue, no per-instruction ELECT loop (ptx.cuh)
       uint32_t it = 0, tc = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const QTile ti = q_decode_tile(p, t, tiles_n, tiles_m, BN);

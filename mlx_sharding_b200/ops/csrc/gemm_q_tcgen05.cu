@@ -119,7 +119,7 @@ gemm_swapab_q_kernel(const __grid_constant__ CUtensorMap tmap_wq, const __grid_c
 
   if (warp == 0) {
     // ============================================================== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane: uniform-datapath issue, no per-instruction ELECT loop (ptx.cuh)
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
@@ -141,7 +141,7 @@ gemm_swapab_q_kernel(const __grid_constant__ CUtensorMap tmap_wq, const __grid_c
     }
   } else if (warp == 1) {
     // ============================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane: uniform-datapath issue, no per-instruction ELECT loop (ptx.cuh)
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;

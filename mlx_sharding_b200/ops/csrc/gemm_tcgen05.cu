@@ -107,7 +107,7 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 
   if (warp == 0) {
     // ============================================================== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane: uniform-datapath issue, no per-instruction ELECT loop (ptx.cuh)
       // Weights never depend on a predecessor kernel: the first ring-full of weight tiles is requested *before*
       // griddepcontrol.wait, so their HBM latency overlaps the predecessor's tail; the activation tiles follow after it.
       const int pre = pdl_early ? 0 : (num_kb < STAGES ? num_kb : STAGES);
@@ -137,7 +137,7 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     }
   } else if (warp == 1) {
     // ============================================================== MMA issuer (single thread)
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane: uniform-datapath issue, no per-instruction ELECT loop (ptx.cuh)
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;

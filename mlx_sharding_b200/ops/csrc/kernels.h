@@ -60,7 +60,7 @@ size_t mla_decode_workspace_floats(int B, int nsplit);
 // q: bf16 [B, 16, 576] (head stride 576, token stride q_ld_t); pool: bf16 [num_pages, 1, 64, 576]; out: bf16 [B, 16, 512]
 cudaError_t mla_decode_launch(const void* q, long long q_ld_t, int B, const void* pool, long long num_pages, int page,
                               const int* block_tables, int max_blocks, const int* context_lens, int max_ctx, float scale,
-                              int nsplit, float* workspace, void* out, long long o_ld_t, cudaStream_t s);
+                              int nsplit, float* workspace, void* out, long long o_ld_t, long long* dbg, cudaStream_t s);
 
 // ---- moe.cu
 // router: fp32 softmax(x W^T) -> top-k (optionally group limited) -> weights * scaling (or normalised)

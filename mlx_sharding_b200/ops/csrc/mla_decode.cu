@@ -43,7 +43,7 @@ constexpr int kTileBytes = kChunks * kChunkBytes;    // 72 KB
 constexpr int kQChunkBytes = kHeads * 128;           // 2 KB
 constexpr int kQBytes = kChunks * kQChunkBytes;      // 18 KB
 constexpr int kPBytes = kHeads * 128;                // [16 heads x 64 tokens] bf16 = 2 KB
-constexpr int kThreads = 192;                        // warp 0: TMA, warp 1: MMA + TMEM, warps 2..5: softmax / epilogue
+constexpr int kThreads = 352;                        // warp 0: TMA, warp 1: QK issuer + TMEM, warp 2: PV issuer, warps 3..10: softmax
 constexpr uint32_t kTmemCols = 256;                  // S[2] x 16 + O[2] x 64 = 160 -> 256
 constexpr uint32_t kSCol = 0, kOCol = 32;
 
@@ -79,7 +79,11 @@ struct MlaParams {
   float scale_log2;                        // softmax scale * log2(e)
   __nv_bfloat16* out; long long o_ld_t;    // [B, 16, 512] (row stride o_ld_t) when nsplit == 1
   float* part_o; float* part_ml;           // [B, nsplit, 16, 512], [B, nsplit, 16, 2]
+  long long* dbg;                          // optional [6][16] clock64 timestamps of CTA (0,0) (MLXB200_MLA_TRACE, bench/mla_bench.py)
 };
+
+#define MLA_TRACE(ev, tile) \
+  do { if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (tile) < 16) p.dbg[(ev) * 16 + (tile)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(kThreads, 1)
 mla_decode_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const MlaParams p) {
@@ -123,176 +127,232 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   const int n = t_end > t_begin ? t_end - t_begin : 0;
 
   if (warp == 0) {
-    // ============================================================== TMA producer
-    if (lane == 0 && n > 0) {
-      mbar_arrive_expect_tx(q_full, kQBytes);
-      for (int c = 0; c < kChunks; ++c) tma_load_3d(q_smem + c * kQChunkBytes, &tmap_q, q_full, c * 64, 0, b);
+    // ============================================================== TMA producer (whole warp waits, one elected lane issues)
+    if (n > 0) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, kQBytes);
+        for (int c = 0; c < kChunks; ++c) tma_load_3d(q_smem + c * kQChunkBytes, &tmap_q, q_full, c * 64, 0, b);
+      }
       const int* bt = p.block_tables + (size_t)b * p.max_blocks;
+      int page_next = bt[t_begin];
       for (int i = 0; i < n; ++i) {
         const int st = i & 1;
+        const int page = page_next;
+        if (i + 1 < n) page_next = bt[t_begin + i + 1];   // the dependent global load overlaps the wait below
         mbar_wait(&kv_free[st], ((i >> 1) & 1) ^ 1);
-        const int page = bt[t_begin + i];
-        uint8_t* dst = kv_smem + st * kTileBytes;
-        mbar_arrive_expect_tx(&kv_full[st], kTileBytes);
-        for (int c = 0; c < kChunks; ++c)
-          tma_load_2d(dst + c * kChunkBytes, &tmap_kv, &kv_full[st], c * 64, page * kTileTok, kEvictFirst);
+        if (elect_one()) {
+          MLA_TRACE(0, i);
+          uint8_t* dst = kv_smem + st * kTileBytes;
+          mbar_arrive_expect_tx(&kv_full[st], kTileBytes);
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c)
+            tma_load_2d(dst + c * kChunkBytes, &tmap_kv, &kv_full[st], c * 64, page * kTileTok, kEvictFirst);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ============================================================== MMA issuer (single thread)
-    if (lane == 0 && n > 0) {
+    // ============================================================== QK issuer (single thread)
+    // The MMAs of this kernel are tiny (64 x 16 x 16: 8 tensor-pipe cycles) while issuing one costs ~50 cycles (descriptor set-up
+    // + the compiler's uniform-datapath election loop), so ONE issuing thread is the bottleneck (measured: 2.1 us per tile).  QK
+    // and PV write different TMEM accumulators and are ordered through mbarriers only, so they get an issuing thread each.
+    if (n > 0) {
       mbar_wait(q_full, 0);
-      auto issue_qk = [&](int i) {
-        const int st = i & 1;
-        mbar_wait(&kv_full[st], (i >> 1) & 1);
+      for (int j = 0; j < n; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        if (j >= 2) mbar_wait(&p_ready[st], ((j - 2) >> 1) & 1);   // softmax has drained S[st] of tile j-2
         tc_fence_after();
-        const uint32_t a0 = smem_u32(kv_smem + st * kTileBytes), b0 = smem_u32(q_smem);
-        const uint32_t d = tmem_base + kSCol + st * kHeads;
+        if (elect_one()) {
+          MLA_TRACE(1, j);
+          const uint32_t a0 = smem_u32(kv_smem + st * kTileBytes), b0 = smem_u32(q_smem);
+          const uint32_t d = tmem_base + kSCol + st * kHeads;
 #pragma unroll
-        for (int c = 0; c < kChunks; ++c) {
-          const uint64_t ad = umma_desc_sw128(a0 + c * kChunkBytes), bd = umma_desc_sw128(b0 + c * kQChunkBytes);
+          for (int c = 0; c < kChunks; ++c) {
+            const uint64_t ad = umma_desc_sw128(a0 + c * kChunkBytes), bd = umma_desc_sw128(b0 + c * kQChunkBytes);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_f16(d, ad + 2 * kk, bd + 2 * kk, kIdescQK, (c | kk) ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk) umma_f16(d, ad + 2 * kk, bd + 2 * kk, kIdescQK, (c | kk) ? 1u : 0u);
+          }
+          umma_commit(&s_full[st]);
         }
-        umma_commit(&s_full[st]);
-      };
-      issue_qk(0);
+        __syncwarp();
+      }
+    }
+  } else if (warp == 2) {
+    // ============================================================== PV issuer (single thread)
+    if (n > 0) {
       for (int i = 0; i < n; ++i) {
         const int st = i & 1;
-        if (i + 1 < n) issue_qk(i + 1);
         mbar_wait(&p_ready[st], (i >> 1) & 1);
         tc_fence_after();
-        const uint32_t v0 = smem_u32(kv_smem + st * kTileBytes), p0 = smem_u32(p_smem + st * kPBytes);
-        const uint64_t pd = umma_desc_sw128(p0);
+        if (elect_one()) {
+          MLA_TRACE(2, i);
+          const uint32_t v0 = smem_u32(kv_smem + st * kTileBytes), p0 = smem_u32(p_smem + st * kPBytes);
+          const uint64_t pd = umma_desc_sw128(p0);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t d = tmem_base + kOCol + st * 64 + j * kHeads;
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t d = tmem_base + kOCol + st * 64 + j * kHeads;
 #pragma unroll
-          for (int ks = 0; ks < kTileTok / 16; ++ks) {
-            const uint64_t ad = umma_desc_mn_sw128(v0 + (2 * j) * kChunkBytes + ks * 2048, kChunkBytes, 1024);
-            umma_f16(d, ad, pd + 2 * ks, kIdescPV, ks ? 1u : 0u);
+            for (int ks = 0; ks < kTileTok / 16; ++ks) {
+              const uint64_t ad = umma_desc_mn_sw128(v0 + (2 * j) * kChunkBytes + ks * 2048, kChunkBytes, 1024);
+              umma_f16(d, ad, pd + 2 * ks, kIdescPV, ks ? 1u : 0u);
+            }
           }
+          umma_commit(&o_full[st]);
+          // QK(i) finished reading this stage before S(i) was published, so "PV(i) done" frees it
+          umma_commit(&kv_free[st]);
         }
-        umma_commit(&o_full[st]);
-        umma_commit(&kv_free[st]);
+        __syncwarp();
       }
     }
   } else {
-    // ============================================================== softmax + running output (128 threads)
+    // ============================================================== softmax + running output (8 warps, 256 threads)
+    // Two warps share each TMEM lane quarter and split the 16 heads (TMEM columns) between them: every thread carries 8 heads,
+    // and each SM sub-partition has two softmax warps to interleave (the per-tile chain is latency-bound with one).
+    constexpr int HH = kHeads / 2;              // heads per thread
     const int q4 = warp & 3;                    // TMEM lane quarter of this warp
-    const int sw = warp - 2;                    // 0..3: slot in the cross-warp reduction buffer
+    const int half = (warp - 3) >> 2;           // 0: heads 0..7, 1: heads 8..15
+    const int h0 = half * HH;
     const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
     const int row = q4 * 16 + lane;             // token row of the tile held by this thread (lanes 0..15 only, UMMA M = 64)
-    float m_run[kHeads], l_run[kHeads], alpha_prev[kHeads], o[4 * kHeads];
+    float m_run[HH], l_run[HH], alpha_prev[HH], o[4 * HH];
 #pragma unroll
-    for (int h = 0; h < kHeads; ++h) { m_run[h] = -INFINITY; l_run[h] = 0.f; alpha_prev[h] = 1.f; }
+    for (int h = 0; h < HH; ++h) { m_run[h] = -INFINITY; l_run[h] = 0.f; alpha_prev[h] = 1.f; }
 #pragma unroll
-    for (int j = 0; j < 4 * kHeads; ++j) o[j] = 0.f;
+    for (int j = 0; j < 4 * HH; ++j) o[j] = 0.f;
+    // byte offsets of this thread's P^T elements (K-major 128B-swizzled [16 heads][64 tokens] bf16)
+    uint32_t p_off[HH];
+#pragma unroll
+    for (int h = 0; h < HH; ++h) {
+      const int hg = h0 + h;
+      p_off[h] = hg * 128 + ((((row >> 3) ^ (hg & 7)) & 7) << 4) + (row & 7) * 2;
+    }
 
     auto consume_o = [&](int i) {
       const int st = i & 1;
       mbar_wait(&o_full[st], (i >> 1) & 1);
       tc_fence_after();
+      uint32_t v[4][HH];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + lane_addr + kOCol + st * 64 + j * kHeads, v);
-        tmem_ld_wait();
+      for (int j = 0; j < 4; ++j) tmem_ld8(tmem_base + lane_addr + kOCol + st * 64 + j * kHeads + h0, v[j]);
+      tmem_ld_wait();
 #pragma unroll
-        for (int h = 0; h < kHeads; ++h) o[j * kHeads + h] = o[j * kHeads + h] * alpha_prev[h] + __uint_as_float(v[h]);
-      }
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int h = 0; h < HH; ++h) o[j * HH + h] = o[j * HH + h] * alpha_prev[h] + __uint_as_float(v[j][h]);
       tc_fence_before();
     };
 
     for (int i = 0; i < n; ++i) {
       const int st = i & 1;
       mbar_wait(&s_full[st], (i >> 1) & 1);
+      if (threadIdx.x == 96) MLA_TRACE(3, i);
       tc_fence_after();
-      uint32_t v[16];
-      tmem_ld16(tmem_base + lane_addr + kSCol + st * kHeads, v);
+      uint32_t v[HH];
+      tmem_ld8(tmem_base + lane_addr + kSCol + st * kHeads + h0, v);
       tmem_ld_wait();
       tc_fence_before();
       const bool valid = lane < 16 && ((t_begin + i) * kTileTok + row) < ctx;
-      float s[kHeads], mx[kHeads];
+      float s[HH];
 #pragma unroll
-      for (int h = 0; h < kHeads; ++h) {
-        s[h] = valid ? __uint_as_float(v[h]) * p.scale_log2 : -INFINITY;
-        mx[h] = s[h];
+      for (int h = 0; h < HH; ++h) s[h] = valid ? __uint_as_float(v[h]) * p.scale_log2 : -INFINITY;
+      // tile max per head over the 16 token rows of this warp: transpose-reduce butterfly — after the step with offset `off` a
+      // lane keeps the half of its values selected by that bit of its lane id; lanes 2k, 2k+1 end with the warp max of head k
+      float r4[4], r2[2], r1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool up = lane & 8;
+        const float send = up ? s[j] : s[j + 4], keep = up ? s[j + 4] : s[j];
+        r4[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
       }
 #pragma unroll
-      for (int off = 8; off > 0; off >>= 1)
-#pragma unroll
-        for (int h = 0; h < kHeads; ++h) mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], off));
-      float* rmax = red;                    // [4][16]
-      float* rsum = red + 4 * kHeads;
-      if (lane == 0) {
-#pragma unroll
-        for (int h = 0; h < kHeads; ++h) rmax[sw * kHeads + h] = mx[h];
+      for (int j = 0; j < 2; ++j) {
+        const bool up = lane & 4;
+        const float send = up ? r4[j] : r4[j + 2], keep = up ? r4[j + 2] : r4[j];
+        r2[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 4));
       }
-      named_bar_sync(1, 128);
-      float alpha[kHeads], ps[kHeads];
-#pragma unroll
-      for (int h = 0; h < kHeads; ++h) {
-        const float tm = fmaxf(fmaxf(rmax[h], rmax[kHeads + h]), fmaxf(rmax[2 * kHeads + h], rmax[3 * kHeads + h]));
-        const float mn = fmaxf(m_run[h], tm);
-        alpha[h] = (mn == -INFINITY) ? 1.f : exp2f(m_run[h] - mn);
-        const float pv = valid ? exp2f(s[h] - mn) : 0.f;   // mn is finite whenever any row of the tile is valid
-        s[h] = pv;
-        ps[h] = pv;
-        m_run[h] = mn;
+      {
+        const bool up = lane & 2;
+        const float send = up ? r2[0] : r2[1], keep = up ? r2[1] : r2[0];
+        r1 = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 2));
       }
+      r1 = fmaxf(r1, __shfl_xor_sync(0xffffffffu, r1, 1));
+      // red: [tile parity][half][quarter][8 heads]
+      float* rmax = red + (i & 1) * 64 + half * 32;
+      if (lane < 16 && (lane & 1) == 0) rmax[q4 * HH + (lane >> 1)] = r1;
+      named_bar_sync(1, 256);
+      float alpha[HH];
 #pragma unroll
-      for (int off = 8; off > 0; off >>= 1)
+      for (int h4 = 0; h4 < HH; h4 += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(rmax + h4), b4 = *reinterpret_cast<const float4*>(rmax + HH + h4);
+        const float4 c4 = *reinterpret_cast<const float4*>(rmax + 2 * HH + h4), d4 = *reinterpret_cast<const float4*>(rmax + 3 * HH + h4);
+        const float tm[4] = {fmaxf(fmaxf(a.x, b4.x), fmaxf(c4.x, d4.x)), fmaxf(fmaxf(a.y, b4.y), fmaxf(c4.y, d4.y)),
+                             fmaxf(fmaxf(a.z, b4.z), fmaxf(c4.z, d4.z)), fmaxf(fmaxf(a.w, b4.w), fmaxf(c4.w, d4.w))};
 #pragma unroll
-        for (int h = 0; h < kHeads; ++h) ps[h] += __shfl_xor_sync(0xffffffffu, ps[h], off);
-      if (lane == 0) {
-#pragma unroll
-        for (int h = 0; h < kHeads; ++h) rsum[sw * kHeads + h] = ps[h];
+        for (int e = 0; e < 4; ++e) {
+          const int h = h4 + e;
+          const float mn = fmaxf(m_run[h], tm[e]);
+          alpha[h] = (mn == -INFINITY) ? 1.f : exp2f(m_run[h] - mn);
+          const float pv = valid ? exp2f(s[h] - mn) : 0.f;   // mn is finite whenever any row of the tile is valid
+          s[h] = pv;
+          // the row sum stays thread-private (all threads share m_run, so partial sums add linearly): reduced once at the end
+          l_run[h] = l_run[h] * alpha[h] + pv;
+          m_run[h] = mn;
+        }
       }
-      // P^T tile -> shared memory, K-major 128B-swizzled [16 heads][64 tokens] bf16 (the PV MMA's B operand)
       if (lane < 16) {
         uint8_t* pb = p_smem + st * kPBytes;
 #pragma unroll
-        for (int h = 0; h < kHeads; ++h) {
-          const uint32_t off = h * 128 + ((((row >> 3) ^ (h & 7)) & 7) << 4) + (row & 7) * 2;
-          *reinterpret_cast<__nv_bfloat16*>(pb + off) = __float2bfloat16_rn(s[h]);
-        }
+        for (int h = 0; h < HH; ++h) *reinterpret_cast<__nv_bfloat16*>(pb + p_off[h]) = __float2bfloat16_rn(s[h]);
+        fence_proxy_async_smem();
       }
-      fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (threadIdx.x == 64) mbar_arrive(&p_ready[st]);
-#pragma unroll
-      for (int h = 0; h < kHeads; ++h) {
-        const float ts = (rsum[h] + rsum[kHeads + h]) + (rsum[2 * kHeads + h] + rsum[3 * kHeads + h]);
-        l_run[h] = l_run[h] * alpha[h] + ts;
-      }
+      named_bar_sync(1, 256);
+      if (threadIdx.x == 96) { mbar_arrive(&p_ready[st]); MLA_TRACE(4, i); }
       if (i > 0) consume_o(i - 1);          // overlaps with PV(i) / QK(i+1) on the tensor pipe
+      if (threadIdx.x == 96) MLA_TRACE(5, i);
 #pragma unroll
-      for (int h = 0; h < kHeads; ++h) alpha_prev[h] = alpha[h];
-      named_bar_sync(1, 128);               // `red` is rewritten by the next tile
+      for (int h = 0; h < HH; ++h) alpha_prev[h] = alpha[h];
     }
     if (n > 0) consume_o(n - 1);
 
-    // ---- write-out: thread = dim row (32*q4 + lane) of each of the 4 M-tiles
+    // ---- row sums: thread-private partials -> CTA totals (once per kernel)
+    named_bar_sync(1, 256);
+#pragma unroll
+    for (int h = 0; h < HH; ++h) {
+      float t = l_run[h];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+      l_run[h] = t;
+    }
+    float* rsum = red + half * 32;              // [quarter][8 heads]
+    if (lane == 0) {
+#pragma unroll
+      for (int h = 0; h < HH; ++h) rsum[q4 * HH + h] = l_run[h];
+    }
+    named_bar_sync(1, 256);
+#pragma unroll
+    for (int h = 0; h < HH; ++h) l_run[h] = (rsum[h] + rsum[HH + h]) + (rsum[2 * HH + h] + rsum[3 * HH + h]);
+
+    // ---- write-out: thread = dim row (32*q4 + lane) of each of the 4 M-tiles, heads h0..h0+7
     const int dim0 = q4 * 32 + lane;
     if (p.nsplit == 1) {
 #pragma unroll
-      for (int h = 0; h < kHeads; ++h) {
+      for (int h = 0; h < HH; ++h) {
         const float inv = l_run[h] > 0.f ? 1.0f / l_run[h] : 0.f;
-        __nv_bfloat16* orow = p.out + (size_t)b * p.o_ld_t + (size_t)h * kLat;
+        __nv_bfloat16* orow = p.out + (size_t)b * p.o_ld_t + (size_t)(h0 + h) * kLat;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) orow[j * 128 + dim0] = __float2bfloat16_rn(o[j * kHeads + h] * inv);
+        for (int j = 0; j < 4; ++j) orow[j * 128 + dim0] = __float2bfloat16_rn(o[j * HH + h] * inv);
       }
     } else {
       float* po = p.part_o + ((size_t)b * p.nsplit + split) * kHeads * kLat;
 #pragma unroll
-      for (int h = 0; h < kHeads; ++h)
+      for (int h = 0; h < HH; ++h)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) po[(size_t)h * kLat + j * 128 + dim0] = o[j * kHeads + h];
-      if (threadIdx.x == 64) {
+        for (int j = 0; j < 4; ++j) po[(size_t)(h0 + h) * kLat + j * 128 + dim0] = o[j * HH + h];
+      if (q4 == 0 && lane == 0) {               // one thread per head half
         float* ml = p.part_ml + ((size_t)b * p.nsplit + split) * kHeads * 2;
 #pragma unroll
-        for (int h = 0; h < kHeads; ++h) { ml[2 * h] = m_run[h]; ml[2 * h + 1] = l_run[h]; }
+        for (int h = 0; h < HH; ++h) { ml[2 * (h0 + h)] = m_run[h]; ml[2 * (h0 + h) + 1] = l_run[h]; }
       }
     }
   }
@@ -419,7 +479,7 @@ size_t mla_decode_workspace_floats(int B, int nsplit) {
 
 cudaError_t mla_decode_launch(const void* q, long long q_ld_t, int B, const void* pool, long long num_pages, int page,
                               const int* block_tables, int max_blocks, const int* context_lens, int max_ctx, float scale,
-                              int nsplit, float* workspace, void* out, long long o_ld_t, cudaStream_t s) {
+                              int nsplit, float* workspace, void* out, long long o_ld_t, long long* dbg, cudaStream_t s) {
   if (B == 0) return cudaSuccess;
   if (page != kTileTok || (q_ld_t % 8) != 0) return cudaErrorInvalidValue;
   EncodeTiledFn fn = encode_fn();
@@ -453,6 +513,7 @@ cudaError_t mla_decode_launch(const void* q, long long q_ld_t, int B, const void
   p.tiles_per_split = (max_tiles + nsplit - 1) / nsplit;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = static_cast<__nv_bfloat16*>(out); p.o_ld_t = o_ld_t;
+  p.dbg = dbg;
   p.part_o = workspace;
   p.part_ml = workspace != nullptr ? workspace + (size_t)B * nsplit * kHeads * kLat : nullptr;
   if (nsplit > 1 && workspace == nullptr) return cudaErrorInvalidValue;

@@ -17,6 +17,15 @@ namespace b200 {
 B200_DEVICE uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 B200_DEVICE uint32_t lane_id() { return threadIdx.x & 31; }
 
+// One elected lane of a fully converged warp.  Unlike `if (lane == 0)`, nvcc knows the branch is warp-uniform-with-one-thread, so
+// tcgen05 / TMA / mbarrier instructions inside it compile to plain uniform-datapath code; under `lane == 0` every such
+// instruction is wrapped in an ELECT / BRA.U.ANY loop with R2UR operand moves (~50 issue cycles per tcgen05.mma, measured).
+B200_DEVICE bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------------------------------------- mbarrier
 B200_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -101,6 +110,15 @@ B200_DEVICE void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// 32 lanes x 8 consecutive fp32 columns
+B200_DEVICE void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
       : "r"(taddr)
       : "memory");
 }
