@@ -71,6 +71,7 @@ class DeepseekV2Stage(StageModel):
         so a decode step needs no kv_b GEMM and attention runs on the cached 576-dim latent (``ops/csrc/mla_decode.cu``).  The
         original q / kv_b / o weights stay for prefill chunks, which decompress the context they attend to."""
         c = self.cfg
+        self._fuse_shared_experts()
         if not (self.absorbed_mla and self.backend_name == "b200"):
             return
         if c.q_lora_rank is not None or not self.ops.mla_absorbed_supported(c.num_attention_heads, c.kv_lora_rank, c.qk_rope_head_dim):
@@ -205,6 +206,45 @@ class DeepseekV2Stage(StageModel):
         o_lat = O.paged_attention(torch.cat([q_abs, q[..., nope:]], -1), kpool, vpool, meta, c.attn_scale, 0.0)   # [T, nh, lr]
         return torch.einsum("thl,hvl->thv", o_lat.float(), wkv[:, nope:]).to(q.dtype).reshape(T, nh * vd)
 
+    fuse_shared = os.environ.get("MLXB200_FUSE_SHARED", "1") != "0"
+
+    def _fuse_shared_experts(self):
+        """CUDA backend, bf16 banks, whole banks on this rank: append DeepSeek's shared experts to the routed bank as ``n_shared``
+        always-on experts (ids ``E .. E+n_shared-1``, routing weight 1).  A SwiGLU MLP is separable along its intermediate dimension,
+        so ``shared(x) = sum_j down_j(silu(gate_j x) * up_j x)`` with ``j`` over ``n_shared`` slices of width ``moe_intermediate_size``
+        — exactly the shape of a routed expert.  The two small dense GEMMs of the shared branch (latency-bound: ~37 us per layer for
+        35 MB of weights) disappear into the persistent grouped GEMMs that already stream the bank at the HBM roofline; the router
+        kernel emits the extra (id, 1.0) columns itself."""
+        c = self.cfg
+        if not (self.fuse_shared and self.backend_name == "b200" and self.expert_shard is None and c.n_shared_experts):
+            return
+        ns, I, H = c.n_shared_experts, c.moe_intermediate_size, c.hidden_size
+        for w in self.layer_weights.values():
+            if "router" not in w or "s_gate" not in w or w.get("e_gate") is None:
+                continue
+            ws = [w[k] for k in ("e_gate", "e_up", "e_down", "s_gate", "s_up", "s_down")]
+            if any(x.is_quantized or x.bias is not None for x in ws) or w["s_gate"].weight.shape[0] != ns * I:
+                continue
+            w["e_gate"] = LinearWeight(weight=torch.cat([w["e_gate"].weight, w["s_gate"].weight.view(ns, I, H)], 0))
+            w["e_up"] = LinearWeight(weight=torch.cat([w["e_up"].weight, w["s_up"].weight.view(ns, I, H)], 0))
+            w["e_down"] = LinearWeight(weight=torch.cat([w["e_down"].weight, w["s_down"].weight.view(H, ns, I).permute(1, 0, 2)], 0))
+            for k in ("s_gate", "s_up", "s_down"):
+                del w[k]
+            w["n_fused_shared"] = ns
+
+    def unfuse_shared_experts(self):
+        """Undo ``_fuse_shared_experts`` (expert parallelism shards the routed bank; the shared experts stay replicated)."""
+        c = self.cfg
+        ns, I, H, E = c.n_shared_experts, c.moe_intermediate_size, c.hidden_size, c.n_routed_experts
+        for w in self.layer_weights.values():
+            if w.pop("n_fused_shared", None) is None:
+                continue
+            g, u, d = w["e_gate"].weight, w["e_up"].weight, w["e_down"].weight
+            w["s_gate"] = LinearWeight(weight=g[E:].reshape(ns * I, H).contiguous())
+            w["s_up"] = LinearWeight(weight=u[E:].reshape(ns * I, H).contiguous())
+            w["s_down"] = LinearWeight(weight=d[E:].permute(1, 0, 2).reshape(H, ns * I).contiguous())
+            w["e_gate"], w["e_up"], w["e_down"] = (LinearWeight(weight=t[:E].contiguous()) for t in (g, u, d))
+
     def _attn_absorbed_b200(self, i, w, h, q, ckv, k_pe, meta: BatchMeta, kpool):
         """Prefill chunk / mixed batch with the latent cache (CUDA backend): append this chunk's latents, then *decompress the
         context the batch attends to* (``kv_b`` GEMM over the cached latents of its sequences) into a temporary per-head K/V pool
@@ -249,9 +289,10 @@ class DeepseekV2Stage(StageModel):
                     h = hs
                 else:
                     h = O.linear(O.gated_up(normed, w["s_gate"], w["s_up"], "silu"), w["s_down"], residual=h)
+            extra = dict(extra=w["n_fused_shared"]) if "n_fused_shared" in w else {}
             idx, wts = O.moe_route(normed, w["router"], c.num_experts_per_tok, c.topk_method,
                                    c.n_group or 1, c.topk_group or 1, c.routed_scaling_factor,
-                                   c.norm_topk_prob)
+                                   c.norm_topk_prob, **extra)
             ep = getattr(self, "ep_layers", None)
             if ep is not None and i in ep:
                 # expert-parallel mode (parallel/ep.py): routed experts are sharded over the ranks of the NVSwitch

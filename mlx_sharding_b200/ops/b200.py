@@ -175,10 +175,11 @@ def paged_attention(q, kpool, vpool, meta: BatchMeta, scale: float, softcap: flo
 
 
 def moe_route(x, gate_w, top_k: int, method: str = "greedy", n_group: int = 1, topk_group: int = 1,
-              scaling: float = 1.0, norm_topk: bool = False):
+              scaling: float = 1.0, norm_topk: bool = False, extra: int = 0):
+    """``extra``: always-on experts appended to the routed bank (ids E .. E+extra-1, weight 1.0) — see ``fuse_shared_experts``."""
     if method != "group_limited_greedy":
         n_group, topk_group = 1, 1
-    idx, w = C().moe_route(x, _bf16(gate_w), int(top_k), int(n_group), int(topk_group), float(scaling), bool(norm_topk))
+    idx, w = C().moe_route(x, _bf16(gate_w), int(top_k), int(n_group), int(topk_group), float(scaling), bool(norm_topk), int(extra))
     return idx, w
 
 

@@ -86,8 +86,12 @@ int auto_splits(int rows, int n, int k, bool grouped) {
   const int tiles = (n + 127) / 128;
   const int kb = (k + 63) / 64;
   int s = 1;
-  // fill ~one wave of SMs while keeping >= 4 k-blocks per split
-  while (tiles * (s * 2) <= sm_count() && kb / (s * 2) >= 8 && s < 4) s *= 2;  // measured: profiles/splitk_sweep.md
+  // fill ~one wave of SMs while keeping >= 8 k-blocks per split (measured: profiles/splitk_sweep.md) ...
+  while (tiles * (s * 2) <= sm_count() && kb / (s * 2) >= 8 && s < 4) s *= 2;
+  // ... and for long reductions over few feature tiles (the folded MLA output projection: 16 tiles x 128 k-blocks) go to the
+  // full portable cluster of 8 splits: 64 CTAs stream at ~100 GB/s each, so the kernel is per-SM-bandwidth bound below that
+  static const bool split8 = [] { const char* e = std::getenv("MLXB200_SPLIT8"); return e != nullptr && e[0] == '1'; }();  // measured slower (0.12 ms / step): opt-in
+  if (split8 && s == 4 && tiles * 8 <= sm_count() && kb / 8 >= 16) s = 8;
   return s;
 }
 
@@ -424,15 +428,15 @@ Tensor mla_decode(const Tensor& q, const Tensor& pool, const Tensor& block_table
 
 // ---- MoE --------------------------------------------------------------------------------------------------------
 std::vector<Tensor> moe_route(const Tensor& x, const Tensor& gate_w, int64_t top_k, int64_t n_group, int64_t topk_group, double scaling,
-                              bool norm_topk) {
+                              bool norm_topk, int64_t extra) {
   check_bf16(x, "x"); check_bf16(gate_w, "gate_w"); check_rows(x, "x");
   TORCH_CHECK(gate_w.is_contiguous());
   const c10::cuda::CUDAGuard guard(x.device());
   const int T = (int)x.size(0);
-  Tensor idx = torch::empty({T, top_k}, torch::dtype(torch::kInt32).device(x.device()));
-  Tensor w = torch::empty({T, top_k}, torch::dtype(torch::kFloat32).device(x.device()));
+  Tensor idx = torch::empty({T, top_k + extra}, torch::dtype(torch::kInt32).device(x.device()));
+  Tensor w = torch::empty({T, top_k + extra}, torch::dtype(torch::kFloat32).device(x.device()));
   LAUNCH_OK(b200::moe_route_launch(x.data_ptr(), x.stride(0), gate_w.data_ptr(), T, (int)x.size(1), (int)gate_w.size(0), (int)top_k,
-                                 (int)n_group, (int)topk_group, (float)scaling, norm_topk, idx.data_ptr<int>(), w.data_ptr<float>(),
+                                 (int)n_group, (int)topk_group, (float)scaling, norm_topk, (int)extra, idx.data_ptr<int>(), w.data_ptr<float>(),
                                  cur_stream()));
   return {idx, w};
 }
@@ -663,7 +667,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mla_absorbed_prologue", &mla_absorbed_prologue);
   m.def("mla_decode", &mla_decode, py::arg("q"), py::arg("pool"), py::arg("block_tables"), py::arg("context_lens"), py::arg("scale"),
         py::arg("max_ctx"), py::arg("nsplit") = 0, py::arg("trace") = py::none());
-  m.def("moe_route", &moe_route);
+  m.def("moe_route", &moe_route, py::arg("x"), py::arg("gate_w"), py::arg("top_k"), py::arg("n_group"), py::arg("topk_group"),
+        py::arg("scaling"), py::arg("norm_topk"), py::arg("extra") = 0);
   m.def("moe_permute", &moe_permute);
   m.def("moe_combine", &moe_combine, py::arg("y_perm"), py::arg("pair_row"), py::arg("wts"), py::arg("residual") = py::none(),
         py::arg("out") = py::none(), py::arg("top_k"), py::arg("signal_flag_ptr") = 0, py::arg("signal_value") = 0);

@@ -64,8 +64,9 @@ cudaError_t mla_decode_launch(const void* q, long long q_ld_t, int B, const void
 
 // ---- moe.cu
 // router: fp32 softmax(x W^T) -> top-k (optionally group limited) -> weights * scaling (or normalised)
+// `extra`: always-on experts appended after the routed ones (ids E .. E+extra-1, weight 1); idx / wts rows are top_k + extra wide
 cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, int T, int H, int E, int top_k,
-                             int n_group, int topk_group, float scaling, bool norm_topk, int* idx, float* wts,
+                             int n_group, int topk_group, float scaling, bool norm_topk, int extra, int* idx, float* wts,
                              cudaStream_t s);
 // permutation: counts/offsets per expert, destination row of every (token, k) pair, gathered rows
 cudaError_t moe_permute_launch(const int* idx, int T, int top_k, int E, int* expert_offsets /*E+1*/, int* pair_row /*T*k*/,

@@ -38,7 +38,7 @@ __device__ __forceinline__ void warp_argmax(float& v, int& i) {
 template <int kRouteToks>
 __global__ void __launch_bounds__(kRouteToks == 1 ? 1024 : kRouteThreads)
 moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv_bfloat16* __restrict__ gw, int T, int H,
-                 int E, int top_k, int n_group, int topk_group, float scaling, int norm_topk, int* __restrict__ idx,
+                 int E, int top_k, int n_group, int topk_group, float scaling, int norm_topk, int extra, int* __restrict__ idx,
                  float* __restrict__ wts) {
   pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   extern __shared__ __align__(16) uint8_t smem[];
@@ -165,10 +165,16 @@ moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv
     wsum += wv;
     if (lane == r) { my_w = wv; my_i = bi; }
   }
+  // `extra` always-on experts (DeepSeek's shared experts appended to the routed bank as experts E .. E+extra-1, weight 1): they
+  // ride the same permutation / grouped GEMMs / combine as the routed ones instead of two separate small dense GEMMs
+  const int row = top_k + extra;
   if (lane < top_k) {
     const float w = (norm_topk && top_k > 1) ? my_w / (wsum + 1e-20f) : my_w * scaling;
-    idx[(size_t)t * top_k + lane] = my_i;
-    wts[(size_t)t * top_k + lane] = w;
+    idx[(size_t)t * row + lane] = my_i;
+    wts[(size_t)t * row + lane] = w;
+  } else if (lane < row) {
+    idx[(size_t)t * row + lane] = E + (lane - top_k);
+    wts[(size_t)t * row + lane] = 1.0f;
   }
 }
 
@@ -259,9 +265,9 @@ __global__ void moe_combine_kernel(const float* __restrict__ y_perm, const int* 
 }  // namespace
 
 cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, int T, int H, int E, int top_k, int n_group,
-                             int topk_group, float scaling, bool norm_topk, int* idx, float* wts, cudaStream_t s) {
+                             int topk_group, float scaling, bool norm_topk, int extra, int* idx, float* wts, cudaStream_t s) {
   if (T == 0) return cudaSuccess;
-  if (E > 32 * kMaxEPerLane || top_k > 32 || (H % 8) || n_group > 32 || (n_group > 1 && E % n_group)) return cudaErrorInvalidValue;
+  if (E > 32 * kMaxEPerLane || top_k + extra > 32 || extra < 0 || (H % 8) || n_group > 32 || (n_group > 1 && E % n_group)) return cudaErrorInvalidValue;
   auto xx = static_cast<const __nv_bfloat16*>(x);
   auto gw = static_cast<const __nv_bfloat16*>(gate_w);
   if (T <= 1024) {
@@ -269,7 +275,7 @@ cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, 
     if (smem > 48 * 1024) return cudaErrorInvalidValue;
     // one token per CTA, 32 warps: each warp owns <= 2 experts, so the whole router row set costs two L2 round trips
     (void)launch_pdl(moe_route_kernel<1>, dim3(T), dim3(E >= 64 ? 1024 : (E >= 32 ? 512 : kRouteThreads)), smem, s, xx, ld_x, gw, T, H, E, top_k, n_group, topk_group, scaling,
-                                                       norm_topk ? 1 : 0, idx, wts);
+                                                       norm_topk ? 1 : 0, extra, idx, wts);
   } else {
     constexpr int TOKS = 8;
     const size_t smem = (size_t)TOKS * H * 2 + (size_t)TOKS * E * 4;
@@ -280,7 +286,7 @@ cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, 
       configured = smem;
     }
     (void)launch_pdl(moe_route_kernel<TOKS>, dim3((T + TOKS - 1) / TOKS), dim3(kRouteThreads), smem, s, xx, ld_x, gw, T, H, E, top_k, n_group, topk_group,
-                                                                           scaling, norm_topk ? 1 : 0, idx, wts);
+                                                                           scaling, norm_topk ? 1 : 0, extra, idx, wts);
   }
   return cudaGetLastError();
 }

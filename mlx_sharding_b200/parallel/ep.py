@@ -185,6 +185,8 @@ def enable_expert_parallel(model, max_tokens: int = 256, group=None):
     if local:
         assert tuple(model.expert_shard) == (dist.get_rank(group), dist.get_world_size(group)), \
             "model was loaded for a different expert shard"
+    if hasattr(model, "unfuse_shared_experts"):
+        model.unfuse_shared_experts()     # shared experts were appended to the (un-sharded) routed bank: split them off again
     fused = model.backend_name == "b200"
     bufs = EPBuffers(cfg.hidden_size, max_tokens, cfg.num_experts_per_tok, group=group) if fused else None
     model.ep_layers = {}
