@@ -290,6 +290,13 @@ class DeepseekV2Stage(StageModel):
                 else:
                     h = O.linear(O.gated_up(normed, w["s_gate"], w["s_up"], "silu"), w["s_down"], residual=h)
             extra = dict(extra=w["n_fused_shared"]) if "n_fused_shared" in w else {}
+            ep = getattr(self, "ep_layers", None)
+            if hasattr(O, "moe_block") and join is None and not (ep is not None and i in ep):
+                # CUDA backend, whole bank local: router + experts as one op (scatter path for decode batches, ops/b200.py)
+                return O.moe_block(normed, w["router"], dict(top_k=c.num_experts_per_tok, method=c.topk_method, n_group=c.n_group or 1,
+                                                             topk_group=c.topk_group or 1, scaling=c.routed_scaling_factor,
+                                                             norm_topk=c.norm_topk_prob),
+                                   w["e_gate"], w["e_up"], w["e_down"], "silu", residual=h, **extra, **self._final_kwargs(i, T, "mlp"))
             idx, wts = O.moe_route(normed, w["router"], c.num_experts_per_tok, c.topk_method,
                                    c.n_group or 1, c.topk_group or 1, c.routed_scaling_factor,
                                    c.norm_topk_prob, **extra)

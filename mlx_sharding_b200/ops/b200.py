@@ -246,6 +246,46 @@ def moe_experts(x, idx, w, Wg: LinearWeight, Wu: LinearWeight, Wd: LinearWeight,
     return c.moe_combine(y, pair_row, w, residual, out, int(k), int(flag), int(val))
 
 
+_scatter_bufs = {}
+SCATTER_MAX_TOKENS = 128
+
+
+def moe_block(x, gate_w, route_kw: dict, Wg: LinearWeight, Wu: LinearWeight, Wd: LinearWeight, act: str = "silu",
+              residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, signal: Optional[Tuple[int, int]] = None,
+              extra: int = 0):
+    """Router + routed (and appended shared) experts of one MoE block.  Decode-sized batches with bf16 banks take the *scatter*
+    path: the router kernel claims a slot per (token, expert) pair in the expert's fixed-stride segment and copies the token row
+    there itself, the grouped GEMMs read per-expert row counts — route / counting sort / gather are ONE launch, the block is
+    router -> grouped gate-up -> grouped down -> combine.  Larger batches (prefill) keep the compact counting-sort permutation."""
+    c = C()
+    T = x.shape[0]
+    quant = Wg.is_quantized or Wu.is_quantized or Wd.is_quantized
+    if quant or T > SCATTER_MAX_TOKENS or os.environ.get("MLXB200_MOE_SCATTER", "1") == "0":
+        idx, wts = moe_route(x, gate_w, extra=extra, **route_kw)
+        return moe_experts(x, idx, wts, Wg, Wu, Wd, act, residual=residual, out=out, signal=signal)
+    wg, wu, wd = _dense(Wg), _dense(Wu), _dense(Wd)
+    E, H = wg.shape[0], x.shape[1]
+    stride = 64 if T <= 64 else SCATTER_MAX_TOKENS
+    key = (x.device.index, E, H, stride)
+    bufs = _scatter_bufs.get(key)
+    if bufs is None:
+        # persistent (graph-safe) per-device buffers: row counters (zero between blocks: the combine resets them) + scattered rows
+        bufs = _scatter_bufs[key] = (torch.zeros(E, dtype=torch.int32, device=x.device),
+                                     torch.empty(E * stride, H, dtype=torch.bfloat16, device=x.device))
+    counts, xs = bufs
+    rk = dict(route_kw)
+    method = rk.pop("method", "greedy")
+    if method != "group_limited_greedy":
+        rk["n_group"], rk["topk_group"] = 1, 1
+    idx, wts, pair_row = c.moe_route(x, _bf16(gate_w), int(rk["top_k"]), int(rk["n_group"]), int(rk["topk_group"]), float(rk["scaling"]),
+                                     bool(rk["norm_topk"]), int(extra), counts, stride, xs)
+    k = idx.shape[1]
+    h = c.grouped_linear(xs, wg, wu, counts, stride, ACT_IDS[act], False, None, None, None, T * k, stride)
+    y = c.grouped_linear(h, wd, None, counts, stride, 0, True, None, None, None, T * k, stride)
+    flag, val = signal if signal is not None else (0, 0)
+    return c.moe_combine(y, pair_row, wts, residual, out, int(k), int(flag), int(val), counts)
+
+
 def softcap_(logits, cap: float):
     return torch.tanh(logits / cap) * cap
 

@@ -136,12 +136,15 @@ Tensor linear(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& w2,
 
 Tensor grouped_linear(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& w2, const Tensor& expert_offsets,
                       int64_t max_rows, int64_t act, bool out_fp32, const c10::optional<Tensor>& row_dst,
-                      const c10::optional<Tensor>& signal_peers, const c10::optional<Tensor>& done_counter, int64_t expected_rows) {
+                      const c10::optional<Tensor>& signal_peers, const c10::optional<Tensor>& done_counter, int64_t expected_rows,
+                      int64_t expert_stride) {
   check_bf16(x, "x"); check_bf16(w, "w"); check_rows(x, "x");
   TORCH_CHECK(w.dim() == 3 && w.is_contiguous(), "w must be contiguous [E, N, K]");
   const c10::cuda::CUDAGuard guard(x.device());
   const int64_t R = x.size(0), K = x.size(1), E = w.size(0), N = w.size(1);
-  TORCH_CHECK(w.size(2) == K && expert_offsets.numel() == E + 1 && expert_offsets.scalar_type() == torch::kInt32);
+  // expert_stride > 0 (scatter layout): expert e owns rows [e * stride, e * stride + expert_offsets[e]) and the array holds COUNTS
+  TORCH_CHECK(w.size(2) == K && expert_offsets.scalar_type() == torch::kInt32 &&
+              (expert_stride > 0 ? (expert_offsets.numel() >= E && R >= E * expert_stride) : expert_offsets.numel() == E + 1));
   // EP return path (parallel/ep.py): every output row goes to the address in row_dst[row] (the source rank's return buffer, peer
   // memory) and all `signal_peers` flags are bumped once every tile is stored — the un-fused return kernel disappears
   const bool ep_ret = row_dst.has_value();
@@ -152,7 +155,7 @@ Tensor grouped_linear(const Tensor& x, const Tensor& w, const c10::optional<Tens
   a.w = w.data_ptr(); a.ld_w = K;
   if (w2.has_value()) { check_bf16(*w2, "w2"); TORCH_CHECK(w2->is_contiguous() && w2->sizes() == w.sizes()); a.w2 = w2->data_ptr(); }
   a.m = (int)R; a.n = (int)N; a.k = (int)K; a.max_rows = (int)std::min<int64_t>(max_rows, R);
-  a.num_experts = (int)E; a.expert_offsets = expert_offsets.data_ptr<int>();
+  a.num_experts = (int)E; a.expert_offsets = expert_offsets.data_ptr<int>(); a.expert_stride = (int)expert_stride;
   if (ep_ret) {
     TORCH_CHECK(signal_peers.has_value() && done_counter.has_value() && row_dst->scalar_type() == torch::kInt64 &&
                 signal_peers->scalar_type() == torch::kInt64 && row_dst->numel() >= R && row_dst->is_contiguous(), "bad EP return arguments");
@@ -428,16 +431,27 @@ Tensor mla_decode(const Tensor& q, const Tensor& pool, const Tensor& block_table
 
 // ---- MoE --------------------------------------------------------------------------------------------------------
 std::vector<Tensor> moe_route(const Tensor& x, const Tensor& gate_w, int64_t top_k, int64_t n_group, int64_t topk_group, double scaling,
-                              bool norm_topk, int64_t extra) {
+                              bool norm_topk, int64_t extra, const c10::optional<Tensor>& sc_counts, int64_t sc_stride,
+                              const c10::optional<Tensor>& sc_x) {
   check_bf16(x, "x"); check_bf16(gate_w, "gate_w"); check_rows(x, "x");
   TORCH_CHECK(gate_w.is_contiguous());
   const c10::cuda::CUDAGuard guard(x.device());
   const int T = (int)x.size(0);
   Tensor idx = torch::empty({T, top_k + extra}, torch::dtype(torch::kInt32).device(x.device()));
   Tensor w = torch::empty({T, top_k + extra}, torch::dtype(torch::kFloat32).device(x.device()));
+  const bool scatter = sc_counts.has_value();
+  Tensor pair_row;
+  if (scatter) {
+    TORCH_CHECK(sc_x.has_value() && sc_counts->scalar_type() == torch::kInt32 && sc_x->scalar_type() == torch::kBFloat16 && sc_x->is_contiguous() &&
+                sc_x->size(1) == x.size(1) && sc_stride >= T && sc_x->size(0) >= sc_counts->numel() * sc_stride &&
+                sc_counts->numel() >= gate_w.size(0) + extra, "bad scatter buffers");
+    pair_row = torch::empty({T, top_k + extra}, torch::dtype(torch::kInt32).device(x.device()));
+  }
   LAUNCH_OK(b200::moe_route_launch(x.data_ptr(), x.stride(0), gate_w.data_ptr(), T, (int)x.size(1), (int)gate_w.size(0), (int)top_k,
                                  (int)n_group, (int)topk_group, (float)scaling, norm_topk, (int)extra, idx.data_ptr<int>(), w.data_ptr<float>(),
-                                 cur_stream()));
+                                 scatter ? sc_counts->data_ptr<int>() : nullptr, (int)sc_stride, scatter ? pair_row.data_ptr<int>() : nullptr,
+                                 scatter ? sc_x->data_ptr() : nullptr, cur_stream()));
+  if (scatter) return {idx, w, pair_row};
   return {idx, w};
 }
 
@@ -456,8 +470,10 @@ std::vector<Tensor> moe_permute(const Tensor& idx, const Tensor& x, int64_t E) {
 }
 
 Tensor moe_combine(const Tensor& y_perm, const Tensor& pair_row, const Tensor& wts, const c10::optional<Tensor>& residual,
-                   const c10::optional<Tensor>& out_, int64_t top_k, int64_t signal_flag_ptr, int64_t signal_value) {
+                   const c10::optional<Tensor>& out_, int64_t top_k, int64_t signal_flag_ptr, int64_t signal_value,
+                   const c10::optional<Tensor>& zero_counts) {
   TORCH_CHECK(y_perm.is_cuda() && y_perm.scalar_type() == torch::kFloat32 && y_perm.is_contiguous());
+  TORCH_CHECK(!zero_counts.has_value() || zero_counts->scalar_type() == torch::kInt32);
   TORCH_CHECK(wts.scalar_type() == torch::kFloat32 && wts.is_contiguous() && pair_row.scalar_type() == torch::kInt32);
   const c10::cuda::CUDAGuard guard(y_perm.device());
   const int H = (int)y_perm.size(1), T = (int)(pair_row.numel() / top_k);
@@ -469,7 +485,8 @@ Tensor moe_combine(const Tensor& y_perm, const Tensor& pair_row, const Tensor& w
   if (signal_flag_ptr != 0) done = reinterpret_cast<unsigned int*>(scratch().get_counters(y_perm.device()).data_ptr<int>()) + 65534;
   LAUNCH_OK(b200::moe_combine_launch(y_perm.data_ptr(), pair_row.data_ptr<int>(), wts.data_ptr<float>(), res, ldr, out.data_ptr(),
                                    out.stride(0), T, (int)top_k, H, reinterpret_cast<uint32_t*>(signal_flag_ptr), (uint32_t)signal_value,
-                                   done, cur_stream()));
+                                   done, zero_counts.has_value() ? zero_counts->data_ptr<int>() : nullptr,
+                                   zero_counts.has_value() ? (int)zero_counts->numel() : 0, cur_stream()));
   return out;
 }
 
@@ -650,7 +667,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("out") = py::none(), py::arg("splits") = 0, py::arg("signal_flag_ptr") = 0, py::arg("signal_value") = 0);
   m.def("grouped_linear", &grouped_linear, py::arg("x"), py::arg("w"), py::arg("w2") = py::none(), py::arg("expert_offsets"),
         py::arg("max_rows"), py::arg("act") = 0, py::arg("out_fp32") = false, py::arg("row_dst") = py::none(),
-        py::arg("signal_peers") = py::none(), py::arg("done_counter") = py::none(), py::arg("expected_rows") = 0);
+        py::arg("signal_peers") = py::none(), py::arg("done_counter") = py::none(), py::arg("expected_rows") = 0,
+        py::arg("expert_stride") = 0);
   m.def("linear_q", &linear_q);
   m.def("grouped_linear_q", &grouped_linear_q);
   m.def("gemm_q_supported", &gemm_q_supported);
@@ -668,10 +686,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mla_decode", &mla_decode, py::arg("q"), py::arg("pool"), py::arg("block_tables"), py::arg("context_lens"), py::arg("scale"),
         py::arg("max_ctx"), py::arg("nsplit") = 0, py::arg("trace") = py::none());
   m.def("moe_route", &moe_route, py::arg("x"), py::arg("gate_w"), py::arg("top_k"), py::arg("n_group"), py::arg("topk_group"),
-        py::arg("scaling"), py::arg("norm_topk"), py::arg("extra") = 0);
+        py::arg("scaling"), py::arg("norm_topk"), py::arg("extra") = 0, py::arg("sc_counts") = py::none(), py::arg("sc_stride") = 0,
+        py::arg("sc_x") = py::none());
   m.def("moe_permute", &moe_permute);
   m.def("moe_combine", &moe_combine, py::arg("y_perm"), py::arg("pair_row"), py::arg("wts"), py::arg("residual") = py::none(),
-        py::arg("out") = py::none(), py::arg("top_k"), py::arg("signal_flag_ptr") = 0, py::arg("signal_value") = 0);
+        py::arg("out") = py::none(), py::arg("top_k"), py::arg("signal_flag_ptr") = 0, py::arg("signal_value") = 0,
+        py::arg("zero_counts") = py::none());
   m.def("apply_penalties_", &apply_penalties_);
   m.def("sample", &sample);
   m.def("sample_into", &sample_into, py::arg("logits"), py::arg("temperature"), py::arg("top_p"), py::arg("row_rng"), py::arg("top_k"),

@@ -48,9 +48,14 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmParams& p, int t, int 
   ti.row_base = 0;
   ti.rows_valid = p.m;
   if (p.expert_offsets != nullptr) {
-    const int lo = __ldg(p.expert_offsets + expert), hi = __ldg(p.expert_offsets + expert + 1);
-    ti.row_base = lo;
-    ti.rows_valid = hi - lo;
+    if (p.expert_stride > 0) {   // scatter layout: fixed stride per expert, the array holds row counts (written by atomics: no __ldg)
+      ti.row_base = expert * p.expert_stride;
+      ti.rows_valid = __ldcg(p.expert_offsets + expert);
+    } else {
+      const int lo = __ldg(p.expert_offsets + expert), hi = __ldg(p.expert_offsets + expert + 1);
+      ti.row_base = lo;
+      ti.rows_valid = hi - lo;
+    }
   }
   ti.rows_valid -= ti.mt * BN;
   ti.row_base += ti.mt * BN;
@@ -390,6 +395,7 @@ cudaError_t gemm_persistent_launch(const GemmArgs& a, cudaStream_t stream) {
   p.row_dst = nullptr; p.signal_peers = nullptr; p.num_signal_peers = 0;
   p.m = a.m; p.n = a.n; p.k = a.k; p.splits = 1; p.cluster_splitk = 0;
   p.expert_offsets = a.expert_offsets;
+  p.expert_stride = a.expert_stride;
   p.out = a.out; p.ld_out = a.ld_out;
   p.residual = static_cast<const __nv_bfloat16*>(a.residual); p.ld_res = a.ld_res;
   p.bias = static_cast<const __nv_bfloat16*>(a.bias); p.act = a.act; p.softcap = a.softcap;

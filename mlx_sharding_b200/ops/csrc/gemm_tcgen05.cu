@@ -68,9 +68,14 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   const int mt = blockIdx.z / p.splits;
   int row_base = 0, rows_valid = p.m;
   if (p.expert_offsets != nullptr) {
-    const int lo = p.expert_offsets[expert], hi = p.expert_offsets[expert + 1];
-    row_base = lo;
-    rows_valid = hi - lo;
+    if (p.expert_stride > 0) {
+      row_base = expert * p.expert_stride;
+      rows_valid = __ldcg(p.expert_offsets + expert);
+    } else {
+      const int lo = p.expert_offsets[expert], hi = p.expert_offsets[expert + 1];
+      row_base = lo;
+      rows_valid = hi - lo;
+    }
   }
   rows_valid -= mt * BN;
   row_base += mt * BN;
@@ -330,6 +335,7 @@ cudaError_t gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   // DSMEM (cluster) split-K when the fp32 partial tile fits the idle stage ring and the cluster is portable
   p.cluster_splitk = (a.cluster_splitk && splits > 1 && splits <= 8 && bn * (dual ? 2 : 1) <= 128) ? 1 : 0;
   p.expert_offsets = a.expert_offsets;
+  p.expert_stride = a.expert_stride;
   p.out = a.out; p.ld_out = a.ld_out;
   p.residual = static_cast<const __nv_bfloat16*>(a.residual); p.ld_res = a.ld_res;
   p.bias = static_cast<const __nv_bfloat16*>(a.bias); p.act = a.act; p.softcap = a.softcap;

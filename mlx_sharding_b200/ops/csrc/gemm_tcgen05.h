@@ -13,6 +13,7 @@ enum : int { kActNone = 0, kActSilu = 1, kActGeluTanh = 2 };
 struct GemmParams {
   int m, n, k, splits;
   const int* expert_offsets;
+  int expert_stride;  // > 0: experts live at fixed row stride, expert_offsets[e] is the row COUNT of expert e (scatter layout)
   void* out;
   long long ld_out;
   const __nv_bfloat16* residual;
@@ -45,6 +46,7 @@ struct GemmArgs {
   int max_rows = 0;               // upper bound of rows per (expert) problem: sizes the grid
   int num_experts = 0;            // grouped: number of experts
   const int* expert_offsets = nullptr;  // grouped: int32 [num_experts + 1] row offsets into x / out (device)
+  int expert_stride = 0;                // > 0: expert e owns rows [e * stride, e * stride + expert_offsets[e]) (counts, not offsets)
   void* out = nullptr;            // bf16 (or fp32 if out_fp32) [rows, n], row stride ld_out; may be a peer pointer
   long long ld_out = 0;
   bool out_fp32 = false;

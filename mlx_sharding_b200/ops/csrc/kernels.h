@@ -67,7 +67,9 @@ cudaError_t mla_decode_launch(const void* q, long long q_ld_t, int B, const void
 // `extra`: always-on experts appended after the routed ones (ids E .. E+extra-1, weight 1); idx / wts rows are top_k + extra wide
 cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, int T, int H, int E, int top_k,
                              int n_group, int topk_group, float scaling, bool norm_topk, int extra, int* idx, float* wts,
-                             cudaStream_t s);
+                             int* sc_counts, int sc_stride, int* sc_pair_row, void* sc_x, cudaStream_t s);
+// (sc_*: scatter mode for decode batches — every (token, k) pair claims slot `atomicAdd(sc_counts[e])` of expert e's fixed-stride
+//  segment, its row index goes to sc_pair_row and the token row is copied to sc_x[row]: no separate permutation kernels)
 // permutation: counts/offsets per expert, destination row of every (token, k) pair, gathered rows
 cudaError_t moe_permute_launch(const int* idx, int T, int top_k, int E, int* expert_offsets /*E+1*/, int* pair_row /*T*k*/,
                                int* counters /*E scratch*/, const void* x, long long ld_x, void* x_perm, int H,
@@ -75,7 +77,8 @@ cudaError_t moe_permute_launch(const int* idx, int T, int top_k, int E, int* exp
 // y[t] = sum_k w[t,k] * y_perm[pair_row[t,k]] (+ residual[t]); out may be a peer pointer; optional release flag
 cudaError_t moe_combine_launch(const void* y_perm, const int* pair_row, const float* wts, const void* residual,
                                long long ld_res, void* out, long long ld_out, int T, int top_k, int H,
-                               uint32_t* signal_flag, uint32_t signal_value, unsigned int* done_counter, cudaStream_t s);
+                               uint32_t* signal_flag, uint32_t signal_value, unsigned int* done_counter, int* zero_counts,
+                               int n_zero, cudaStream_t s);
 
 // ---- sampler.cu
 cudaError_t apply_penalties_launch(float* logits, int B, int V, const int* rep_ctx, int C, const float* penalty,

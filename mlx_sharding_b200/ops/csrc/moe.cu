@@ -39,7 +39,8 @@ template <int kRouteToks>
 __global__ void __launch_bounds__(kRouteToks == 1 ? 1024 : kRouteThreads)
 moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv_bfloat16* __restrict__ gw, int T, int H,
                  int E, int top_k, int n_group, int topk_group, float scaling, int norm_topk, int extra, int* __restrict__ idx,
-                 float* __restrict__ wts) {
+                 float* __restrict__ wts, int* __restrict__ sc_counts, int sc_stride, int* __restrict__ sc_pair_row,
+                 __nv_bfloat16* __restrict__ sc_x) {
   pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   extern __shared__ __align__(16) uint8_t smem[];
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem);                 // [kRouteToks][H]
@@ -95,7 +96,8 @@ moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv
   // ---- one warp per token: softmax, (group mask), top-k
   const int tk = warp;
   const int t = t0 + tk;
-  if (tk >= kRouteToks || t >= T) return;
+  __shared__ int s_rows[32];
+  if (tk < kRouteToks && t < T) {
   float sc[kMaxEPerLane], sel[kMaxEPerLane];
   float mx = -INFINITY;
 #pragma unroll
@@ -176,6 +178,26 @@ moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv
     idx[(size_t)t * row + lane] = E + (lane - top_k);
     wts[(size_t)t * row + lane] = 1.0f;
   }
+  // Scatter mode (decode batches, one token per CTA): claim a slot of the expert's fixed-stride segment with one atomic and record
+  // the row — the counting sort (`moe_offsets_kernel`) and the gather (`moe_gather_kernel`) are folded into the router.  Slot order
+  // within an expert is arbitrary; results do not depend on it (rows are independent GEMM columns, the combine gathers by pair).
+  if (sc_counts != nullptr && lane < row) {
+    const int e = lane < top_k ? my_i : E + (lane - top_k);
+    const int r = e * sc_stride + atomicAdd(&sc_counts[e], 1);
+    sc_pair_row[(size_t)t * row + lane] = r;
+    s_rows[lane] = r;
+  }
+  }
+  if (kRouteToks == 1 && sc_counts != nullptr) {
+    __syncthreads();
+    if (t0 < T) {
+      const int row = top_k + extra;
+      for (int i = threadIdx.x; i < row * nvec; i += blockDim.x) {
+        const int k = i / nvec, v = i % nvec;
+        reinterpret_cast<uint4*>(sc_x + (size_t)s_rows[k] * H)[v] = reinterpret_cast<const uint4*>(xs)[v];
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ permutation
@@ -217,8 +239,12 @@ __global__ void moe_gather_kernel(const __nv_bfloat16* __restrict__ x, long long
 __global__ void moe_combine_kernel(const float* __restrict__ y_perm, const int* __restrict__ pair_row,
                                    const float* __restrict__ wts, const __nv_bfloat16* __restrict__ residual,
                                    long long ld_res, __nv_bfloat16* __restrict__ out, long long ld_out, int T, int top_k,
-                                   int H, uint32_t* signal_flag, uint32_t signal_value, unsigned int* done_counter) {
+                                   int H, uint32_t* signal_flag, uint32_t signal_value, unsigned int* done_counter,
+                                   int* __restrict__ zero_counts, int n_zero) {
   pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
+  // scatter layout: the expert row counters were consumed by the grouped GEMMs before this kernel; reset them for the next layer
+  if (zero_counts != nullptr && blockIdx.x == 0)
+    for (int e = threadIdx.x; e < n_zero; e += blockDim.x) zero_counts[e] = 0;
   const int nvec = H / 8;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < (long long)T * nvec) {
@@ -265,8 +291,10 @@ __global__ void moe_combine_kernel(const float* __restrict__ y_perm, const int* 
 }  // namespace
 
 cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, int T, int H, int E, int top_k, int n_group,
-                             int topk_group, float scaling, bool norm_topk, int extra, int* idx, float* wts, cudaStream_t s) {
+                             int topk_group, float scaling, bool norm_topk, int extra, int* idx, float* wts, int* sc_counts,
+                             int sc_stride, int* sc_pair_row, void* sc_x, cudaStream_t s) {
   if (T == 0) return cudaSuccess;
+  if (sc_counts != nullptr && (T > 1024 || sc_stride < T)) return cudaErrorInvalidValue;   // scatter: one-token-per-CTA variant only
   if (E > 32 * kMaxEPerLane || top_k + extra > 32 || extra < 0 || (H % 8) || n_group > 32 || (n_group > 1 && E % n_group)) return cudaErrorInvalidValue;
   auto xx = static_cast<const __nv_bfloat16*>(x);
   auto gw = static_cast<const __nv_bfloat16*>(gate_w);
@@ -275,7 +303,7 @@ cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, 
     if (smem > 48 * 1024) return cudaErrorInvalidValue;
     // one token per CTA, 32 warps: each warp owns <= 2 experts, so the whole router row set costs two L2 round trips
     (void)launch_pdl(moe_route_kernel<1>, dim3(T), dim3(E >= 64 ? 1024 : (E >= 32 ? 512 : kRouteThreads)), smem, s, xx, ld_x, gw, T, H, E, top_k, n_group, topk_group, scaling,
-                                                       norm_topk ? 1 : 0, extra, idx, wts);
+                                                       norm_topk ? 1 : 0, extra, idx, wts, sc_counts, sc_stride, sc_pair_row, static_cast<__nv_bfloat16*>(sc_x));
   } else {
     constexpr int TOKS = 8;
     const size_t smem = (size_t)TOKS * H * 2 + (size_t)TOKS * E * 4;
@@ -286,7 +314,7 @@ cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, 
       configured = smem;
     }
     (void)launch_pdl(moe_route_kernel<TOKS>, dim3((T + TOKS - 1) / TOKS), dim3(kRouteThreads), smem, s, xx, ld_x, gw, T, H, E, top_k, n_group, topk_group,
-                                                                           scaling, norm_topk ? 1 : 0, extra, idx, wts);
+                                                                           scaling, norm_topk ? 1 : 0, extra, idx, wts, sc_counts, sc_stride, sc_pair_row, static_cast<__nv_bfloat16*>(sc_x));
   }
   return cudaGetLastError();
 }
@@ -307,13 +335,14 @@ cudaError_t moe_permute_launch(const int* idx, int T, int top_k, int E, int* exp
 
 cudaError_t moe_combine_launch(const void* y_perm, const int* pair_row, const float* wts, const void* residual,
                                long long ld_res, void* out, long long ld_out, int T, int top_k, int H,
-                               uint32_t* signal_flag, uint32_t signal_value, unsigned int* done_counter, cudaStream_t s) {
+                               uint32_t* signal_flag, uint32_t signal_value, unsigned int* done_counter, int* zero_counts,
+                               int n_zero, cudaStream_t s) {
   if (T == 0) return cudaSuccess;
   if (H % 8) return cudaErrorInvalidValue;
   const long long total = (long long)T * (H / 8);
   (void)launch_pdl(moe_combine_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, 
       static_cast<const float*>(y_perm), pair_row, wts, static_cast<const __nv_bfloat16*>(residual), ld_res,
-      static_cast<__nv_bfloat16*>(out), ld_out, T, top_k, H, signal_flag, signal_value, done_counter);
+      static_cast<__nv_bfloat16*>(out), ld_out, T, top_k, H, signal_flag, signal_value, done_counter, zero_counts, n_zero);
   return cudaGetLastError();
 }
 

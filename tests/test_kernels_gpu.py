@@ -173,6 +173,31 @@ def test_moe_experts(B, T):
     close(got, ref, 5e-2, 2e-2)
 
 
+@pytest.mark.parametrize("T,extra", [(1, 0), (64, 2), (100, 2), (64, 0)])
+def test_moe_block_scatter_matches_permutation_path(B, T, extra):
+    """Scatter path (router claims slots + copies rows, grouped GEMMs on per-expert counts, combine resets the counters) ==
+    counting-sort permutation path, incl. the appended always-on (shared) experts; run twice: the counters must come back to 0."""
+    H, I, E, k = 2048, 1408, 64, 6
+    Et = E + extra
+    x = rnd(T, H)
+    gw = rnd(E, H, scale=0.05)
+    Wg = LinearWeight(weight=rnd(Et, I, H, scale=0.03, seed=1))
+    Wu = LinearWeight(weight=rnd(Et, I, H, scale=0.03, seed=2))
+    Wd = LinearWeight(weight=rnd(Et, H, I, scale=0.03, seed=3))
+    res = rnd(T, H)
+    rk = dict(top_k=k, method="greedy", n_group=1, topk_group=1, scaling=1.0, norm_topk=False)
+    idx, w = B.moe_route(x, gw, extra=extra, **rk)
+    assert idx.shape == (T, k + extra)
+    if extra:
+        assert (idx[:, k:] == torch.arange(E, Et, device=DEV, dtype=torch.int32)).all() and (w[:, k:] == 1).all()
+    ref = B.moe_experts(x, idx, w, Wg, Wu, Wd, "silu", residual=res)
+    for _ in range(2):
+        got = B.moe_block(x, gw, rk, Wg, Wu, Wd, "silu", residual=res, extra=extra)
+        close(got, ref, 2e-2, 1e-2)
+    torch.cuda.synchronize()
+    assert all(int(c.sum()) == 0 for c, _ in B._scatter_bufs.values())
+
+
 def test_sampler_greedy_logprobs_topk(B):
     Bn, V = 5, 102400
     logits = rnd(Bn, V, scale=3.0, dtype=torch.float32)
