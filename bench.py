@@ -50,6 +50,9 @@ def parse_args(argv=None):
     p.add_argument("--groups", type=int, default=0, help="micro-batch groups in flight (default: one per stage)")
     p.add_argument("--quant", type=int, default=0, choices=[0, 4, 8],
                    help="MLX affine quantised weights (group 64), dequantised inside the GEMM kernels (BASELINE config 2)")
+    p.add_argument("--fp8-experts", action="store_true",
+                   help="convert the routed / shared expert banks to block-scaled MXFP8 at load (tcgen05 kind::mxf8f6f4); this is the "
+                        "default for --quant 4/8 checkpoints (MLXB200_FP8_EXPERTS=0 keeps the exact in-kernel MLX-affine dequant)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-baseline", action="store_true",
                    help="skip the short same-box baseline run (baseline/torch_pipeline.py) that fills vs_baseline")
@@ -109,6 +112,8 @@ def main(argv=None):
     args = parse_args(argv)
     if args.impl == "reference":
         return reference_arm(args)
+    if args.fp8_experts:
+        os.environ["MLXB200_FP8_EXPERTS"] = "1"
 
     import gc
 
@@ -188,6 +193,14 @@ def main(argv=None):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def weights_desc(args) -> str:
+    fp8 = os.environ.get("MLXB200_FP8_EXPERTS", "")
+    if args.quant:
+        exp = "expert banks converted to block-scaled MXFP8 at load (tcgen05 kind::mxf8f6f4)" if fp8 != "0" else "expert banks dequantised in-kernel"
+        return f"mlx-affine-int{args.quant}-g64 checkpoint: attention / dense weights dequantised in-kernel, {exp}"
+    return "bf16" + (", expert banks converted to block-scaled MXFP8 at load" if fp8 == "1" else "")
 
 
 METRIC = "decode tokens/sec, DeepSeek-Coder-V2-Lite @N B200, + p50 TTFT"
@@ -399,7 +412,7 @@ def run_pp(args, world, rank, local, dev):
                        "global_batch": G * B, "seq_len": S, "parallelism": f"pp{world}",
                        "micro_batches_in_flight": G, "tokens_per_step": G * B, "transport": loop.transport,
                        "cuda_graphs": loop.use_graphs, "kv_page_size": PS,
-                       "weights": f"mlx-affine-int{args.quant}-g64 (in-kernel dequant)" if args.quant else "bf16",
+                       "weights": weights_desc(args),
                        "l2": "weights streamed per step (31 GB/stage-set) far exceed the 126 MB L2; no explicit flush",
                        "layers": [spec.start_layer, spec.end_layer] if world == 1 else
                        ("cost-balanced, whole layers" if args.whole_layers else "cost-balanced, half-layer (attention | MLP) boundaries")},

@@ -181,7 +181,7 @@ class StageModel:
         def visit(o):
             nonlocal total
             if isinstance(o, LinearWeight):
-                for t in (o.weight, o.wq, o.scales, o.biases, o.bias):
+                for t in (o.weight, o.wq, o.scales, o.biases, o.bias) + tuple(getattr(o, "_fp8", None) or ()):
                     if t is not None and t.data_ptr() not in seen:
                         seen.add(t.data_ptr())
                         total += t.numel() * t.element_size()

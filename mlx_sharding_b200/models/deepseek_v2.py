@@ -41,8 +41,10 @@ class DeepseekV2Stage(StageModel):
         super().__init__(cfg, spec, dtype, device, backend)
         if self.absorbed_mla is None:
             c = cfg
+            # (quantised attention weights: promoted to bf16 at load when the FP8 conversion policy is on, else absorbed goes off —
+            #  see ``_post_load``)
             self.absorbed_mla = bool(
-                self.backend_name == "b200" and c.q_lora_rank is None and not c.quantization and dtype == torch.bfloat16
+                self.backend_name == "b200" and c.q_lora_rank is None and dtype == torch.bfloat16
                 and self.ops.mla_absorbed_supported(c.num_attention_heads, c.kv_lora_rank, c.qk_rope_head_dim))
 
     @property
@@ -71,6 +73,7 @@ class DeepseekV2Stage(StageModel):
         so a decode step needs no kv_b GEMM and attention runs on the cached 576-dim latent (``ops/csrc/mla_decode.cu``).  The
         original q / kv_b / o weights stay for prefill chunks, which decompress the context they attend to."""
         c = self.cfg
+        self._convert_quantized_for_b200()
         self._fuse_shared_experts()
         if not (self.absorbed_mla and self.backend_name == "b200"):
             return
@@ -208,6 +211,50 @@ class DeepseekV2Stage(StageModel):
 
     fuse_shared = os.environ.get("MLXB200_FUSE_SHARED", "1") != "0"
 
+    def _convert_quantized_for_b200(self):
+        """Load-time policy for MLX 4/8-bit checkpoints on the CUDA backend (BASELINE config 2; off with MLXB200_FP8_EXPERTS=0, which
+        keeps every weight packed and dequantised in-kernel with exact MLX-affine semantics):
+
+        * routed + shared expert banks (93 % of the parameters) -> block-scaled MXFP8 (``utils/quant.py::to_mxfp8``), executed by
+          ``tcgen05.mma kind::mxf8f6f4.block_scale`` (``ops/csrc/gemm_fp8.cu``); the shared experts are appended to the bank first;
+        * attention projections (7 %) -> bf16, so the absorbed-latent MLA path (folded weights, tcgen05 latent attention) applies;
+        * embeddings, LM head, dense layer-0 MLP stay packed (in-kernel dequant GEMMs / gather).
+
+        With MLXB200_FP8_EXPERTS=1 the expert banks of a bf16 checkpoint are converted the same way."""
+        env = os.environ.get("MLXB200_FP8_EXPERTS", "")
+        if self.backend_name != "b200" or env == "0" or self.expert_shard is not None:
+            return
+        from ..utils.quant import to_mxfp8
+
+        c = self.cfg
+        ns, I, H = c.n_shared_experts or 0, c.moe_intermediate_size, c.hidden_size
+        for w in self.layer_weights.values():
+            quantized = any(isinstance(v, LinearWeight) and v.is_quantized for v in w.values())
+            if not (quantized or env == "1"):
+                continue
+            for k in ("qkv_a", "q_a_kv_a", "q_b", "kv_b", "o"):
+                if k in w and w[k].is_quantized:
+                    w[k] = LinearWeight(weight=w[k].dense(self.dtype).contiguous(), bias=w[k].bias)
+            if "router" not in w or w.get("e_gate") is None or H % 128 or I % 128:
+                continue
+            fuse = bool(ns and self.fuse_shared and "s_gate" in w and w["s_gate"].out_features == ns * I)
+
+            def bank(ek, sk, down=False):
+                parts = [w[ek].dense(torch.bfloat16)]
+                if fuse:
+                    sd = w[sk].dense(torch.bfloat16)
+                    parts.append(sd.view(H, ns, I).permute(1, 0, 2) if down else sd.view(ns, I, H))
+                qs, sfs = zip(*(to_mxfp8(ch) for p_ in parts for ch in p_.split(8)))
+                out = LinearWeight()
+                out._fp8 = (torch.cat(qs).contiguous(), torch.cat(sfs).contiguous())
+                return out
+
+            w["e_gate"], w["e_up"], w["e_down"] = bank("e_gate", "s_gate"), bank("e_up", "s_up"), bank("e_down", "s_down", True)
+            if fuse:
+                for k in ("s_gate", "s_up", "s_down"):
+                    del w[k]
+                w["n_fused_shared"] = ns
+
     def _fuse_shared_experts(self):
         """CUDA backend, bf16 banks, whole banks on this rank: append DeepSeek's shared experts to the routed bank as ``n_shared``
         always-on experts (ids ``E .. E+n_shared-1``, routing weight 1).  A SwiGLU MLP is separable along its intermediate dimension,
@@ -223,7 +270,7 @@ class DeepseekV2Stage(StageModel):
             if "router" not in w or "s_gate" not in w or w.get("e_gate") is None:
                 continue
             ws = [w[k] for k in ("e_gate", "e_up", "e_down", "s_gate", "s_up", "s_down")]
-            if any(x.is_quantized or x.bias is not None for x in ws) or w["s_gate"].weight.shape[0] != ns * I:
+            if any(x.is_quantized or x.bias is not None or x.weight is None for x in ws) or w["s_gate"].weight.shape[0] != ns * I:
                 continue
             w["e_gate"] = LinearWeight(weight=torch.cat([w["e_gate"].weight, w["s_gate"].weight.view(ns, I, H)], 0))
             w["e_up"] = LinearWeight(weight=torch.cat([w["e_up"].weight, w["s_up"].weight.view(ns, I, H)], 0))

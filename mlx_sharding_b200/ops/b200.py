@@ -224,6 +224,20 @@ def moe_experts(x, idx, w, Wg: LinearWeight, Wu: LinearWeight, Wd: LinearWeight,
     weighted combine (+ residual [+ P2P store & flag])."""
     c = C()
     T, k = idx.shape
+    if fp8_experts_enabled(Wg) and x.shape[1] % 128 == 0:
+        (gq, gs), (uq, us), (dq, ds) = _fp8pack(Wg), _fp8pack(Wu), _fp8pack(Wd)
+        E = gq.shape[0]
+        offs, pair_row, xp = c.moe_permute(idx, x, E)
+        xq, xsf = c.quant_mxfp8(xp)
+        h = c.linear_fp8(xq, xsf, gq, gs, uq, us, offs, T, None, ACT_IDS[act], False, 0, 0)
+        hq, hsf = c.quant_mxfp8(h)
+        y = c.linear_fp8(hq, hsf, dq, ds, None, None, offs, T, None, 0, True, 0, 0)
+        if extra is not None:
+            residual = extra if residual is None else residual + extra
+        flag, val = signal if signal is not None else (0, 0)
+        if join is not None:
+            join.wait()
+        return c.moe_combine(y, pair_row, w, residual, out, int(k), int(flag), int(val))
     qg, qu, qd = _qpack(Wg), _qpack(Wu), _qpack(Wd)
     if qg is not None and qu is not None and qd is not None:
         E = Wg.wq.shape[0]
@@ -246,6 +260,38 @@ def moe_experts(x, idx, w, Wg: LinearWeight, Wu: LinearWeight, Wd: LinearWeight,
     return c.moe_combine(y, pair_row, w, residual, out, int(k), int(flag), int(val))
 
 
+def quant_mxfp8(x: torch.Tensor):
+    """bf16 activations ``[R, K]`` -> (e4m3 bytes, ue8m0 scales per 32 K-values): the B operand of the block-scaled FP8 GEMMs."""
+    return C().quant_mxfp8(x)
+
+
+def _fp8pack(W: LinearWeight):
+    """MXFP8 form of a weight (``utils/quant.py::to_mxfp8``), built once on first use from the dense / dequantised values; the
+    source tensors (bf16 bank or packed MLX codes) are released — afterwards the weight lives in HBM as 1.03 bytes per parameter."""
+    f = getattr(W, "_fp8", None)
+    if f is None:
+        from ..utils.quant import to_mxfp8
+
+        src = W.dense(torch.bfloat16) if W.is_quantized else W.weight
+        qs, sfs = [], []
+        for chunk in (src.split(8) if src.dim() == 3 else [src]):     # bound the fp32 temporaries of the conversion
+            q, sf = to_mxfp8(chunk)
+            qs.append(q); sfs.append(sf)
+        f = W._fp8 = (torch.cat(qs).contiguous(), torch.cat(sfs).contiguous())
+        W.fp8_shape = tuple(src.shape)
+        W.weight = W.wq = W.scales = W.biases = None
+    return f
+
+
+def fp8_experts_enabled(W: LinearWeight) -> bool:
+    """Block-scaled FP8 expert banks.  The stage model converts at load (MLX 4/8-bit checkpoints by default, bf16 checkpoints with
+    MLXB200_FP8_EXPERTS=1; ``models/deepseek_v2.py::_convert_quantized_for_b200``); packed MLX weights handed to the ops directly
+    always take the exact in-kernel dequant GEMMs."""
+    if getattr(W, "_fp8", None) is not None:
+        return True                      # converted at load (models/deepseek_v2.py::_convert_quantized_for_b200)
+    return os.environ.get("MLXB200_FP8_EXPERTS", "") == "1" and not W.is_quantized   # explicit opt-in for bf16 banks used directly
+
+
 _scatter_bufs = {}
 SCATTER_MAX_TOKENS = 128
 
@@ -259,12 +305,17 @@ def moe_block(x, gate_w, route_kw: dict, Wg: LinearWeight, Wu: LinearWeight, Wd:
     router -> grouped gate-up -> grouped down -> combine.  Larger batches (prefill) keep the compact counting-sort permutation."""
     c = C()
     T = x.shape[0]
-    quant = Wg.is_quantized or Wu.is_quantized or Wd.is_quantized
+    fp8 = fp8_experts_enabled(Wg) and x.shape[1] % 128 == 0
+    quant = (Wg.is_quantized or Wu.is_quantized or Wd.is_quantized) and not fp8
     if quant or T > SCATTER_MAX_TOKENS or os.environ.get("MLXB200_MOE_SCATTER", "1") == "0":
         idx, wts = moe_route(x, gate_w, extra=extra, **route_kw)
         return moe_experts(x, idx, wts, Wg, Wu, Wd, act, residual=residual, out=out, signal=signal)
-    wg, wu, wd = _dense(Wg), _dense(Wu), _dense(Wd)
-    E, H = wg.shape[0], x.shape[1]
+    if fp8:
+        (gq, gs), (uq, us), (dq, ds) = _fp8pack(Wg), _fp8pack(Wu), _fp8pack(Wd)
+        E, H = gq.shape[0], x.shape[1]
+    else:
+        wg, wu, wd = _dense(Wg), _dense(Wu), _dense(Wd)
+        E, H = wg.shape[0], x.shape[1]
     stride = 64 if T <= 64 else SCATTER_MAX_TOKENS
     key = (x.device.index, E, H, stride)
     bufs = _scatter_bufs.get(key)
@@ -280,8 +331,16 @@ def moe_block(x, gate_w, route_kw: dict, Wg: LinearWeight, Wu: LinearWeight, Wd:
     idx, wts, pair_row = c.moe_route(x, _bf16(gate_w), int(rk["top_k"]), int(rk["n_group"]), int(rk["topk_group"]), float(rk["scaling"]),
                                      bool(rk["norm_topk"]), int(extra), counts, stride, xs)
     k = idx.shape[1]
-    h = c.grouped_linear(xs, wg, wu, counts, stride, ACT_IDS[act], False, None, None, None, T * k, stride)
-    y = c.grouped_linear(h, wd, None, counts, stride, 0, True, None, None, None, T * k, stride)
+    if fp8:
+        # block-scaled FP8 experts: activations are quantised per 32-wide K block right before each GEMM (garbage rows beyond an
+        # expert's count are quantised too and never read); tcgen05 kind::mxf8f6f4.block_scale applies both operands' scales
+        xq, xsf = c.quant_mxfp8(xs)
+        h = c.linear_fp8(xq, xsf, gq, gs, uq, us, counts, stride, None, ACT_IDS[act], False, T * k, stride)
+        hq, hsf = c.quant_mxfp8(h)
+        y = c.linear_fp8(hq, hsf, dq, ds, None, None, counts, stride, None, 0, True, T * k, stride)
+    else:
+        h = c.grouped_linear(xs, wg, wu, counts, stride, ACT_IDS[act], False, None, None, None, T * k, stride)
+        y = c.grouped_linear(h, wd, None, counts, stride, 0, True, None, None, None, T * k, stride)
     flag, val = signal if signal is not None else (0, 0)
     return c.moe_combine(y, pair_row, wts, residual, out, int(k), int(flag), int(val), counts)
 

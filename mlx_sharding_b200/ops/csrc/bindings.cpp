@@ -326,6 +326,49 @@ void mla_rope_kv_write(Tensor q, const Tensor& kpe, const Tensor& kv, Tensor kpo
                                      (int)kpool.size(2), (int)q.size(0), cur_stream()));
 }
 
+// ---- MXFP8 (block-scaled fp8) -----------------------------------------------------------------------------------
+std::vector<Tensor> quant_mxfp8(const Tensor& x) {
+  check_bf16(x, "x"); check_rows(x, "x");
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int64_t R = x.size(0), K = x.size(1);
+  TORCH_CHECK(K % 128 == 0, "MXFP8 GEMM operands need K % 128 == 0");
+  Tensor q = torch::empty({R, K}, x.options().dtype(torch::kUInt8));
+  Tensor sf = torch::empty({R, K / 32}, x.options().dtype(torch::kUInt8));
+  LAUNCH_OK(b200::quant_mxfp8_launch(x.data_ptr(), x.stride(0), q.data_ptr(), sf.data_ptr(), R, (int)K, cur_stream()));
+  return {q, sf};
+}
+
+// Y = (xq * xsf) (wq * wsf)^T on the tensor cores (kind::mxf8f6f4.block_scale).  Dense: wq [N, K]; grouped: wq [E, N, K] with
+// expert_offsets (offsets, or per-expert counts when expert_stride > 0) exactly like grouped_linear.
+Tensor linear_fp8(const Tensor& xq, const Tensor& xsf, const Tensor& wq, const Tensor& wsf, const c10::optional<Tensor>& w2q,
+                  const c10::optional<Tensor>& w2sf, const c10::optional<Tensor>& expert_offsets, int64_t max_rows,
+                  const c10::optional<Tensor>& residual, int64_t act, bool out_fp32, int64_t expected_rows, int64_t expert_stride) {
+  auto u8 = [](const Tensor& t, const char* n) { TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kUInt8 && t.is_contiguous(), n, " must be contiguous uint8"); };
+  u8(xq, "xq"); u8(xsf, "xsf"); u8(wq, "wq"); u8(wsf, "wsf");
+  const c10::cuda::CUDAGuard guard(xq.device());
+  const bool grouped = expert_offsets.has_value();
+  const int64_t R = xq.size(0), K = xq.size(1), N = wq.size(-2), E = grouped ? wq.size(0) : 0;
+  TORCH_CHECK(wq.size(-1) == K && K % 128 == 0 && N % 128 == 0 && xsf.numel() == R * (K / 32) && wsf.numel() == wq.numel() / 32,
+              "MXFP8 GEMM: K % 128 == 0, N % 128 == 0, one scale per 32 K-values");
+  Tensor out = torch::empty({R, N}, xq.options().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16));
+  if (R == 0) return out;
+  b200::GemmArgs a;
+  a.x = xq.data_ptr(); a.x_rows = R; a.ld_x = K; a.x_sf = xsf.data_ptr();
+  a.w = wq.data_ptr(); a.ld_w = K; a.w_sf = wsf.data_ptr();
+  if (w2q.has_value()) { u8(*w2q, "w2q"); u8(*w2sf, "w2sf"); TORCH_CHECK(w2q->sizes() == wq.sizes()); a.w2 = w2q->data_ptr(); a.w2_sf = w2sf->data_ptr(); }
+  a.m = (int)R; a.n = (int)N; a.k = (int)K;
+  a.max_rows = (int)std::min<int64_t>(grouped ? max_rows : R, R);
+  if (grouped) {
+    TORCH_CHECK(expert_offsets->scalar_type() == torch::kInt32 && (expert_stride > 0 ? expert_offsets->numel() >= E : expert_offsets->numel() == E + 1));
+    a.num_experts = (int)E; a.expert_offsets = expert_offsets->data_ptr<int>(); a.expert_stride = (int)expert_stride;
+    a.bn = grouped_bn(a.max_rows, expected_rows > 0 ? expected_rows : R, E);
+  }
+  if (residual.has_value()) { check_bf16(*residual, "residual"); check_rows(*residual, "residual"); a.residual = residual->data_ptr(); a.ld_res = residual->stride(0); }
+  a.out = out.data_ptr(); a.ld_out = N; a.out_fp32 = out_fp32; a.act = (int)act;
+  LAUNCH_OK(b200::gemm_fp8_launch(a, cur_stream()));
+  return out;
+}
+
 // ---- attention --------------------------------------------------------------------------------------------------
 Tensor paged_attention(const Tensor& q, const Tensor& kpool, const Tensor& vpool, const Tensor& block_tables, const Tensor& positions,
                        const Tensor& token_seq, double scale, double softcap, int64_t max_ctx) {
@@ -685,6 +728,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mla_absorbed_prologue", &mla_absorbed_prologue);
   m.def("mla_decode", &mla_decode, py::arg("q"), py::arg("pool"), py::arg("block_tables"), py::arg("context_lens"), py::arg("scale"),
         py::arg("max_ctx"), py::arg("nsplit") = 0, py::arg("trace") = py::none());
+  m.def("quant_mxfp8", &quant_mxfp8);
+  m.def("linear_fp8", &linear_fp8, py::arg("xq"), py::arg("xsf"), py::arg("wq"), py::arg("wsf"), py::arg("w2q") = py::none(),
+        py::arg("w2sf") = py::none(), py::arg("expert_offsets") = py::none(), py::arg("max_rows") = 0, py::arg("residual") = py::none(),
+        py::arg("act") = 0, py::arg("out_fp32") = false, py::arg("expected_rows") = 0, py::arg("expert_stride") = 0);
   m.def("moe_route", &moe_route, py::arg("x"), py::arg("gate_w"), py::arg("top_k"), py::arg("n_group"), py::arg("topk_group"),
         py::arg("scaling"), py::arg("norm_topk"), py::arg("extra") = 0, py::arg("sc_counts") = py::none(), py::arg("sc_stride") = 0,
         py::arg("sc_x") = py::none());

@@ -4,6 +4,8 @@
 // The reference gets all of these from MLX Metal kernels (mx.fast.rms_norm / mx.fast.rope / Embedding /
 // KVCache.update_and_fetch via mlx_lm blocks); these are from-scratch sm_100a kernels: 128-bit
 // vectorised accesses, one warp-shuffle reduction tree, no shared-memory round trips beyond one exchange.
+#include <cuda_fp8.h>
+
 #include "kernels.h"
 #include "launch.h"
 #include "ptx.cuh"
@@ -30,6 +32,53 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 }  // namespace
+
+// ------------------------------------------------------------------------------------------------ MXFP8 activation quantisation
+// x bf16 [R, K] -> e4m3 bytes [R, K] + one ue8m0 scale per 32 consecutive K values [R, K / 32] (OCP MX): scale = 2^ceil(log2(amax /
+// 448)), the smallest power of two that brings the block into e4m3 range, elements rounded to nearest-even.  One thread per 8
+// elements, 4 threads per block of 32.  (The weights get the same format once at load: utils/quant.py::to_mxfp8.)
+__global__ void quant_mxfp8_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, uint8_t* __restrict__ q, uint8_t* __restrict__ sf,
+                                   int K, long long total_vec) {
+  pdl_sync();
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int nvec = K / 8;
+  const bool in = i < total_vec;
+  const long long r = in ? i / nvec : 0;
+  const int v = in ? (int)(i % nvec) : 0;
+  float f[8];
+  float amax = 0.f;
+  if (in) {
+    const uint4 raw = reinterpret_cast<const uint4*>(x + r * ld_x)[v];
+    unpack8(raw, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(f[j]));
+  }
+  amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+  amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+  if (!in) return;
+  const uint32_t bits = __float_as_uint(amax * (1.0f / 448.0f));
+  uint32_t e = ((bits >> 23) & 0xffu) + ((bits & 0x7fffffu) ? 1u : 0u);   // biased exponent of the next power of two >= amax / 448
+  if (e > 254u) e = 254u;
+  const float inv = __uint_as_float((254u - e) << 23);                     // 2^-(e - 127)
+  uint32_t w[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const __nv_fp8x2_storage_t lo = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * j] * inv, f[4 * j + 1] * inv), __NV_SATFINITE, __NV_E4M3);
+    const __nv_fp8x2_storage_t hi = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * j + 2] * inv, f[4 * j + 3] * inv), __NV_SATFINITE, __NV_E4M3);
+    w[j] = (uint32_t)lo | ((uint32_t)hi << 16);
+  }
+  reinterpret_cast<uint2*>(q + r * K)[v] = make_uint2(w[0], w[1]);
+  if ((v & 3) == 0) sf[r * (K / 32) + (v >> 2)] = (uint8_t)e;
+}
+
+cudaError_t quant_mxfp8_launch(const void* x, long long ld_x, void* q, void* sf, long long rows, int K, cudaStream_t s) {
+  if (rows == 0) return cudaSuccess;
+  if ((K % 128) != 0 || (ld_x % 8) != 0) return cudaErrorInvalidValue;
+  const long long total = rows * (K / 8);
+  (void)launch_pdl(quant_mxfp8_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(x), ld_x,
+                   static_cast<uint8_t*>(q), static_cast<uint8_t*>(sf), K, total);
+  return cudaGetLastError();
+}
 
 // ------------------------------------------------------------------------------------------------ RMSNorm
 // One CTA per row; each thread keeps up to MAXV 16-byte vectors of the row in registers (H <= 256*8*MAXV).

@@ -1,14 +1,21 @@
-// Persistent variant of the swap-AB tcgen05 GEMM (dense + grouped, no split-K): one CTA per SM walks a static
-// round-robin tile list; the TMA ring never drains between tiles and the TMEM accumulator is double buffered,
-// so tile i's epilogue (TMEM -> registers -> shared -> global) overlaps tile i+1's loads and MMAs.
+// Block-scaled FP8 (MXFP8) variant of the persistent swap-AB GEMM: tcgen05.mma kind::mxf8f6f4.block_scale.
 //
-// Why: the one-tile-per-CTA kernel (gemm_tcgen05.cu) pays ~5 us of prologue + epilogue per CTA.  For the MoE
-// down-projection of a decode step (1024 tiles of 360 KB) that is ~40% on top of the weight stream — measured
-// 4.65 TB/s vs 6.1 TB/s for the gate/up launch whose tiles are 1 MB (profiles/ncu_gemm_decode.md).  Here the fixed cost is paid
-// once per SM and everything else is a continuous weight stream.
+// SURVEY §2.6 K17 / BASELINE north star: "block-scaled fp8 where the checkpoint is 4-bit/8-bit".  MLX-affine int4/int8 weights are
+// dequantised in shared memory by gemm_q_*.cu (exact MLX semantics, but the dequant ALU work caps the speed-up); here they are
+// converted ONCE at load to OCP MXFP8 — e4m3 elements with one power-of-two (ue8m0) scale per 32 consecutive K values
+// (utils/quant.py::to_mxfp8) — and the tensor core applies both operands' block scales itself:
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue.
-// Barriers: full/empty per ring stage, tmem_full/tmem_empty per accumulator buffer.
+//   * weights [N, K] e4m3 + scales [N, K/32] ue8m0, activations [T, K] e4m3 + scales [T, K/32] (quantised by
+//     elementwise.cu::quant_mxfp8_kernel); 1 byte per element, so a 128 B swizzle row is one 128-element k-block and a stage has
+//     the same bytes as in the bf16 kernel with half the TMA / MMA instruction count per weight byte;
+//   * UMMA K = 32 per instruction = exactly one scale block: the four MMAs of a k-block select byte 0..3 (a_sf_id / b_sf_id) of the
+//     32-bit scale words staged in TMEM;
+//   * scale staging: 4 extra warps (one per TMEM lane quarter) read the scale words of the stage's rows from global memory
+//     and tcgen05.st them into the slot's TMEM columns in the layout the MMA expects (row r -> lane r % 32 of every quarter,
+//     column r / 32), ahead of the TMA ring; accumulators stay fp32 in TMEM and the epilogue is the bf16 kernel's.
+//
+// Everything else — persistent tile walk, double-buffered accumulators, grouped (MoE) mode incl. the fixed-stride scatter layout,
+// DUAL gate/up with act(g)*u epilogue, residual / fp32 outputs — is shared by construction with gemm_persistent.cu.
 #include <algorithm>
 
 #include "gemm_common.cuh"
@@ -21,10 +28,16 @@ using namespace gemm;
 
 namespace {
 
+constexpr int kSfWarps = 4;                 // scale-staging warps per group (one per TMEM lane quarter)
+constexpr int kSfGroups = 3;                // groups take ring iterations round-robin: three global-load round trips in flight
+constexpr int kFp8Threads = kNumThreads + 32 * kSfWarps * kSfGroups;
+constexpr int kSfColsPerStage = 16;         // TMEM columns per ring slot: SFA (4, DUAL 8) + SFB (BN / 32 <= 8)
+constexpr int kFp8BlockK = 128;             // e4m3 elements per k-block = one 128 B swizzle row
+
 __host__ __device__ constexpr int p_acc_cols(int BN, bool dual) { return BN * (dual ? 2 : 1); }
-__host__ __device__ constexpr int p_num_acc(int BN, bool dual) { return 2 * p_acc_cols(BN, dual) <= 512 ? 2 : 1; }
+__host__ __device__ constexpr int p_num_acc(int BN, bool dual) { return 2 * p_acc_cols(BN, dual) + 8 * kSfColsPerStage <= 512 ? 2 : 1; }
 __host__ __device__ constexpr uint32_t p_tmem_cols(int BN, bool dual) {
-  int c = p_acc_cols(BN, dual) * p_num_acc(BN, dual);
+  int c = p_acc_cols(BN, dual) * p_num_acc(BN, dual) + 8 * kSfColsPerStage;
   return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512;
 }
 __host__ __device__ constexpr int p_stg_rows(int BN) { return BN < 64 ? BN : 64; }
@@ -69,7 +82,7 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmParams& p, int t, int 
 // One thread per CTA, once, after the CTA's last tile (a system fence per *tile* would stall the epilogue on an NVLink round
 // trip each time when `out` is peer memory): reports how many tiles of the grid this CTA covered; the arrival that completes
 // the grid raises the consumer flag(s) with system scope.  Every CTA fences its own stores before arriving.
-__device__ __forceinline__ void publish_tiles_done(const GemmParams& p, unsigned int n) {
+__device__ __forceinline__ void fp8_publish_tiles_done(const GemmParams& p, unsigned int n) {
   const unsigned int done = atomicAdd(p.done_counter, n) + n;
   if (done != p.signal_tiles) return;
   *p.done_counter = 0u;
@@ -84,8 +97,8 @@ __device__ __forceinline__ void publish_tiles_done(const GemmParams& p, unsigned
 }
 
 template <int BN, bool DUAL, typename OutT>
-__global__ void __launch_bounds__(kNumThreads, 1)
-gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_w2,
+__global__ void __launch_bounds__(kFp8Threads, 1)
+gemm_fp8_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_w2,
                        const __grid_constant__ CUtensorMap tmap_x, const GemmParams p, const int tiles_n, const int tiles_m,
                        const int num_tiles) {
   constexpr int STAGES = p_num_stages(BN, DUAL, sizeof(OutT));
@@ -93,7 +106,8 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   constexpr int ACC_COLS = p_acc_cols(BN, DUAL);
   constexpr int NUM_ACC = p_num_acc(BN, DUAL);
   constexpr uint32_t TMEM_COLS = p_tmem_cols(BN, DUAL);
-  constexpr uint32_t IDESC = umma_idesc_bf16(kTileM, BN);
+  constexpr uint32_t IDESC = umma_idesc_mxf8(kTileM, BN);
+  constexpr uint32_t SF_BASE_COL = NUM_ACC * ACC_COLS;   // scale slots sit behind the accumulators
   constexpr int STG_ROWS = p_stg_rows(BN);
   static_assert(STAGES >= 2, "ring too small");
 
@@ -106,7 +120,8 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* sf_full_bar = tempty_bar + 2;     // [STAGES]: scales of the slot are in TMEM
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(sf_full_bar + STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -120,6 +135,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&sf_full_bar[s], kSfWarps);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -135,7 +151,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   // PDL: let the successor's CTAs become resident now (their pre-wait prologue / weight prefetch overlaps this kernel)
   pdl_launch_dependents();
 
-  const int kb_total = (p.k + kBlockK - 1) / kBlockK;
+  const int kb_total = (p.k + kFp8BlockK - 1) / kFp8BlockK;
 
   if (warp == 0) {
     // ============================================================== TMA producer
@@ -150,7 +166,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
           if (t >= num_tiles) break;
           const TileInfo ti = decode_tile(p, t, tiles_n, tiles_m, BN);
           uint8_t* st = smem + pre * STAGE_BYTES;
-          const int kc = (int)(pre % kb_total) * kBlockK;
+          const int kc = (int)(pre % kb_total) * kFp8BlockK;
           mbar_arrive_expect_tx(&full_bar[pre], STAGE_BYTES);
           tma_load_2d(st, &tmap_w, &full_bar[pre], kc, ti.w_row, kEvictFirst);
           if (DUAL) tma_load_2d(st + kATileBytes, &tmap_w2, &full_bar[pre], kc, ti.w_row, kEvictFirst);
@@ -159,7 +175,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
         for (uint32_t i = 0; i < pre; ++i) {
           const int t = blockIdx.x + (int)(i / kb_total) * gridDim.x;
           const TileInfo ti = decode_tile(p, t, tiles_n, tiles_m, BN);
-          tma_load_2d(smem + i * STAGE_BYTES + kATileBytes * (DUAL ? 2 : 1), &tmap_x, &full_bar[i], (int)(i % kb_total) * kBlockK,
+          tma_load_2d(smem + i * STAGE_BYTES + kATileBytes * (DUAL ? 2 : 1), &tmap_x, &full_bar[i], (int)(i % kb_total) * kFp8BlockK,
                       ti.row_base, kEvictLast);
         }
       }
@@ -172,7 +188,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = smem + s * STAGE_BYTES;
-          const int kc = kb * kBlockK;
+          const int kc = kb * kFp8BlockK;
           mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
           tma_load_2d(st, &tmap_w, &full_bar[s], kc, ti.w_row, kEvictFirst);
           if (DUAL) tma_load_2d(st + kATileBytes, &tmap_w2, &full_bar[s], kc, ti.w_row, kEvictFirst);
@@ -194,24 +210,65 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
         for (int kb = 0; kb < kb_total; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
+          mbar_wait(&sf_full_bar[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t b_addr = a_addr + kATileBytes * (DUAL ? 2 : 1);
           const uint64_t adesc = umma_desc_sw128(a_addr);
           const uint64_t bdesc = umma_desc_sw128(b_addr);
+          const uint32_t sf = tmem_base + SF_BASE_COL + s * kSfColsPerStage;   // [SFA 4 | SFA2 4 | SFB 8]
 #pragma unroll
-          for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
+          for (int kk = 0; kk < 4; ++kk) {   // 4 x (K = 32) per 128-element k-block; scale byte kk of the slot's words
             const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
-            umma_f16(acc_addr, adesc + 2 * kk, bdesc + 2 * kk, IDESC, acc);
+            umma_mxf8(acc_addr, adesc + 2 * kk, bdesc + 2 * kk, umma_idesc_sf(IDESC, kk, kk), sf, sf + 8, acc);
             if (DUAL) {
               const uint64_t a2desc = umma_desc_sw128(a_addr + kATileBytes);
-              umma_f16(acc_addr + BN, a2desc + 2 * kk, bdesc + 2 * kk, IDESC, acc);
+              umma_mxf8(acc_addr + BN, a2desc + 2 * kk, bdesc + 2 * kk, umma_idesc_sf(IDESC, kk, kk), sf + 4, sf + 8, acc);
             }
           }
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&tfull_bar[ab]);
         ++tc;
+      }
+    }
+  } else if (warp >= 6) {
+    // ============================================================== scale staging (4 warps, one per TMEM lane quarter)
+    // Per ring slot: the 32-bit scale words (4 x ue8m0, one per 32-wide K block of this 128-wide k-block) of the stage's 128 weight
+    // rows and BN token rows go to TMEM columns [SFA 4 | SFA2 4 | SFB 8] of the slot: row r -> lane r % 32 (same data in every lane
+    // quarter), column r / 32.  The loads are issued one ring-depth ahead of the MMAs.
+    if (!pdl_early) pdl_wait();   // activation scales are written by the predecessor (quantisation kernel)
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t grp = static_cast<uint32_t>(warp - 6) >> 2;   // one group alone is bound by its load latency (~0.8 us / slot)
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const TileInfo ti = decode_tile(p, t, tiles_n, tiles_m, BN);
+      if (ti.rows_valid <= 0) continue;
+      for (int kb = 0; kb < kb_total; ++kb, ++it) {
+        if (it % kSfGroups != grp) continue;
+        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+        uint32_t wa[4], wa2[4], wb[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const size_t r = static_cast<size_t>(ti.w_row + c * 32 + lane);
+          wa[c] = __ldg(p.w_sf + r * p.sf_ld_w + kb);
+          wa2[c] = DUAL ? __ldg(p.w2_sf + r * p.sf_ld_w + kb) : 0u;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int r = c * 32 + lane;
+          wb[c] = (c * 32 < BN && r < ti.rows_valid) ? __ldcg(p.x_sf + static_cast<size_t>(ti.row_base + r) * p.sf_ld_x + kb) : 0x7f7f7f7fu;
+        }
+        mbar_wait(&empty_bar[s], ph ^ 1);     // the MMAs that read this slot's scales have completed
+        tc_fence_after();
+        const uint32_t sf = tmem_base + lane_base + SF_BASE_COL + s * kSfColsPerStage;
+        tmem_st4(sf, wa);
+        if (DUAL) tmem_st4(sf + 4, wa2);
+        tmem_st8(sf + 8, wb);
+        tmem_st_wait();
+        tc_fence_before();
+        if (elect_one()) mbar_arrive(&sf_full_bar[s]);
+        __syncwarp();
       }
     }
   } else {
@@ -314,7 +371,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
       // fused stage boundary / EP return: `out` rows went to peer memory; fence once, then report this CTA's tiles
       __threadfence_system();
       named_bar_sync(1, kEpiThreads);
-      if (et == 0) publish_tiles_done(p, p.signal_peers != nullptr ? my_tiles : tc);
+      if (et == 0) fp8_publish_tiles_done(p, p.signal_peers != nullptr ? my_tiles : tc);
     }
     tc_fence_before();
   }
@@ -329,7 +386,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
 // ================================================================================================ host side
 namespace {
 
-int sm_count_cached() {
+int sm_count_cached_fp8() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -341,61 +398,66 @@ int sm_count_cached() {
 }
 
 template <int BN, bool DUAL, typename OutT>
-cudaError_t p_launch_one(const CUtensorMap& tw, const CUtensorMap& tw2, const CUtensorMap& tx, const GemmParams& p, int tiles_n,
+cudaError_t f_launch_one(const CUtensorMap& tw, const CUtensorMap& tw2, const CUtensorMap& tx, const GemmParams& p, int tiles_n,
                          int tiles_m, int num_tiles, cudaStream_t stream) {
   constexpr int STAGES = p_num_stages(BN, DUAL, sizeof(OutT));
-  constexpr int smem = STAGES * stage_bytes(BN, DUAL) + p_staging_bytes(BN, sizeof(OutT)) + (2 * STAGES + 4) * 8 + 16 + 1024;
+  constexpr int smem = STAGES * stage_bytes(BN, DUAL) + p_staging_bytes(BN, sizeof(OutT)) + (3 * STAGES + 4) * 8 + 16 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
-  auto kern = gemm_persistent_kernel<BN, DUAL, OutT>;
+  auto kern = gemm_fp8_persistent_kernel<BN, DUAL, OutT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int grid = std::min(num_tiles, sm_count_cached());
-  (void)launch_pdl(kern, dim3(grid), dim3(kNumThreads), smem, stream, tw, tw2, tx, p, tiles_n, tiles_m, num_tiles);
+  const int grid = std::min(num_tiles, sm_count_cached_fp8());
+  (void)launch_pdl(kern, dim3(grid), dim3(kFp8Threads), smem, stream, tw, tw2, tx, p, tiles_n, tiles_m, num_tiles);
   return cudaGetLastError();
 }
 
 template <bool DUAL, typename OutT>
-cudaError_t p_dispatch_bn(int bn, const CUtensorMap& tw, const CUtensorMap& tw2, const CUtensorMap& tx, const GemmParams& p,
+cudaError_t f_dispatch_bn(int bn, const CUtensorMap& tw, const CUtensorMap& tw2, const CUtensorMap& tx, const GemmParams& p,
                           int tiles_n, int tiles_m, int num_tiles, cudaStream_t s) {
   switch (bn) {
-    case 16: return p_launch_one<16, DUAL, OutT>(tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, s);
-    case 32: return p_launch_one<32, DUAL, OutT>(tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, s);
-    case 64: return p_launch_one<64, DUAL, OutT>(tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, s);
-    case 128: return p_launch_one<128, DUAL, OutT>(tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, s);
-    case 256: return p_launch_one<256, DUAL, OutT>(tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, s);
+    case 16: return f_launch_one<16, DUAL, OutT>(tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, s);
+    case 32: return f_launch_one<32, DUAL, OutT>(tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, s);
+    case 64: return f_launch_one<64, DUAL, OutT>(tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, s);
+    case 128: return f_launch_one<128, DUAL, OutT>(tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, s);
+    case 256: return f_launch_one<256, DUAL, OutT>(tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, s);
     default: return cudaErrorInvalidValue;
   }
 }
 
 }  // namespace
 
-cudaError_t gemm_persistent_launch(const GemmArgs& a, cudaStream_t stream) {
+cudaError_t gemm_fp8_launch(const GemmArgs& a, cudaStream_t stream) {
   const bool dual = a.w2 != nullptr;
   const bool grouped = a.expert_offsets != nullptr;
-  const int bn = a.bn > 0 ? a.bn : gemm_pick_bn(a.max_rows);
+  int bn = a.bn > 0 ? a.bn : gemm_pick_bn(a.max_rows);
+  // TMEM budget: accumulators (BN columns, x2 for DUAL) + 128 columns of scale slots must fit the 512 columns of an SM
+  if (dual && bn > 128) bn = 128;
   if (grouped && (a.n % kTileM) != 0) return cudaErrorInvalidValue;
-  if ((a.k % 8) != 0 || (a.n % 8) != 0) return cudaErrorInvalidValue;
+  if ((a.k % kFp8BlockK) != 0 || (a.n % kTileM) != 0 || bn > 256) return cudaErrorInvalidValue;   // whole k-blocks / weight tiles only
+  if (a.w_sf == nullptr || a.x_sf == nullptr || (dual && a.w2_sf == nullptr)) return cudaErrorInvalidValue;
   if (dual && a.out_fp32) return cudaErrorInvalidValue;
 
   CUtensorMap tw, tw2, tx;
   const uint64_t w_rows = static_cast<uint64_t>(a.n) * (grouped ? a.num_experts : 1);
-  if (!gemm_make_tmap(&tw, a.w, w_rows, a.k, a.ld_w, kTileM)) return cudaErrorUnknown;
+  if (!gemm_make_tmap_u8(&tw, a.w, w_rows, a.k, a.ld_w, kTileM)) return cudaErrorUnknown;
   if (dual) {
-    if (!gemm_make_tmap(&tw2, a.w2, w_rows, a.k, a.ld_w, kTileM)) return cudaErrorUnknown;
+    if (!gemm_make_tmap_u8(&tw2, a.w2, w_rows, a.k, a.ld_w, kTileM)) return cudaErrorUnknown;
   } else {
     tw2 = tw;
   }
-  if (!gemm_make_tmap(&tx, a.x, a.x_rows, a.k, a.ld_x, bn)) return cudaErrorUnknown;
+  if (!gemm_make_tmap_u8(&tx, a.x, a.x_rows, a.k, a.ld_x, bn)) return cudaErrorUnknown;
 
   GemmParams p;
-  p.row_dst = nullptr; p.signal_peers = nullptr; p.num_signal_peers = 0; p.w_sf = p.w2_sf = p.x_sf = nullptr; p.sf_ld_w = p.sf_ld_x = 0;
+  p.row_dst = nullptr; p.signal_peers = nullptr; p.num_signal_peers = 0;
   p.m = a.m; p.n = a.n; p.k = a.k; p.splits = 1; p.cluster_splitk = 0;
   p.expert_offsets = a.expert_offsets;
   p.expert_stride = a.expert_stride;
+  p.w_sf = static_cast<const uint32_t*>(a.w_sf); p.w2_sf = static_cast<const uint32_t*>(a.w2_sf);
+  p.x_sf = static_cast<const uint32_t*>(a.x_sf); p.sf_ld_w = a.k / kFp8BlockK; p.sf_ld_x = a.k / kFp8BlockK;
   p.out = a.out; p.ld_out = a.ld_out;
   p.residual = static_cast<const __nv_bfloat16*>(a.residual); p.ld_res = a.ld_res;
   p.bias = static_cast<const __nv_bfloat16*>(a.bias); p.act = a.act; p.softcap = a.softcap;
@@ -410,9 +472,9 @@ cudaError_t gemm_persistent_launch(const GemmArgs& a, cudaStream_t stream) {
     p.row_dst = a.row_dst; p.signal_peers = a.signal_peers; p.num_signal_peers = a.num_signal_peers;
     p.signal_tiles = static_cast<unsigned int>(num_tiles);
   }
-  if (a.out_fp32) return p_dispatch_bn<false, float>(bn, tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, stream);
-  if (dual) return p_dispatch_bn<true, __nv_bfloat16>(bn, tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, stream);
-  return p_dispatch_bn<false, __nv_bfloat16>(bn, tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, stream);
+  if (a.out_fp32) return f_dispatch_bn<false, float>(bn, tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, stream);
+  if (dual) return f_dispatch_bn<true, __nv_bfloat16>(bn, tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, stream);
+  return f_dispatch_bn<false, __nv_bfloat16>(bn, tw, tw2, tx, p, tiles_n, tiles_m, num_tiles, stream);
 }
 
 }  // namespace b200

@@ -291,6 +291,26 @@ bool gemm_make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t col
   return make_tmap(m, ptr, rows, cols, ld, box_rows);
 }
 
+bool gemm_make_tmap_u8(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  // same cache, keyed with the top bit of the box to keep bf16 and byte maps of one pointer apart
+  const TmapKey key{ptr, rows, cols, ld, box_rows | 0x80000000u};
+  std::lock_guard<std::mutex> lock(g_tmap_mutex);
+  auto it = g_tmap_cache.find(key);
+  if (it != g_tmap_cache.end()) { *m = it->second; return true; }
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld};
+  cuuint32_t box[2] = {128, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  if (fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  if (g_tmap_cache.size() > 16384) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *m);
+  return true;
+}
+
 int gemm_pick_bn(int max_rows) {
   if (max_rows <= 16) return 16;
   if (max_rows <= 32) return 32;
@@ -330,7 +350,7 @@ cudaError_t gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   if (!make_tmap(&tx, a.x, a.x_rows, a.k, a.ld_x, bn)) return cudaErrorUnknown;
 
   GemmParams p;
-  p.row_dst = nullptr; p.signal_peers = nullptr; p.num_signal_peers = 0;
+  p.row_dst = nullptr; p.signal_peers = nullptr; p.num_signal_peers = 0; p.w_sf = p.w2_sf = p.x_sf = nullptr; p.sf_ld_w = p.sf_ld_x = 0;
   p.m = a.m; p.n = a.n; p.k = a.k; p.splits = splits;
   // DSMEM (cluster) split-K when the fp32 partial tile fits the idle stage ring and the cluster is portable
   p.cluster_splitk = (a.cluster_splitk && splits > 1 && splits <= 8 && bn * (dual ? 2 : 1) <= 128) ? 1 : 0;

@@ -13,6 +13,9 @@ enum : int { kActNone = 0, kActSilu = 1, kActGeluTanh = 2 };
 struct GemmParams {
   int m, n, k, splits;
   const int* expert_offsets;
+  // block-scaled FP8 (gemm_fp8.cu): ue8m0 scale words (4 scales = one 128-element k-block per uint32), row-major [rows, K / 128]
+  const uint32_t* w_sf; const uint32_t* w2_sf; const uint32_t* x_sf;
+  int sf_ld_w, sf_ld_x;
   int expert_stride;  // > 0: experts live at fixed row stride, expert_offsets[e] is the row COUNT of expert e (scatter layout)
   void* out;
   long long ld_out;
@@ -68,6 +71,8 @@ struct GemmArgs {
   int num_signal_peers = 0;
   // MLX affine-quantised weights (gemm_q_launch): w / w2 point at the packed uint32 codes [rows, k*bits/32];
   // scales / biases are pre-transposed to [k/group, rows] bf16 at load time (TMA-friendly)
+  // block-scaled FP8 (gemm_fp8_launch): w / w2 / x point at e4m3 bytes, *_sf at their ue8m0 scales [rows, k / 32]
+  const void* w_sf = nullptr; const void* w2_sf = nullptr; const void* x_sf = nullptr;
   bool persistent = true;                 // splits == 1: persistent kernel (gemm_persistent.cu)
   bool cluster_splitk = true;             // prefer the DSMEM reduction when it applies (decode shapes)
   int q_bits = 0, q_group = 64;
@@ -81,5 +86,6 @@ cudaError_t gemm_launch(const GemmArgs& a, cudaStream_t stream);
 cudaError_t gemm_persistent_launch(const GemmArgs& a, cudaStream_t stream);
 bool gemm_q_supported(int bits, int group, int k);
 cudaError_t gemm_q_launch(const GemmArgs& a, cudaStream_t stream);
+cudaError_t gemm_fp8_launch(const GemmArgs& a, cudaStream_t stream);   // MXFP8 x MXFP8 -> bf16 / fp32 (gemm_fp8.cu)
 
 }  // namespace b200

@@ -24,6 +24,9 @@ cudaError_t mla_rope_kv_launch(void* q, long long q_ld_t, long long q_ld_h, cons
                                const float* inv_freq, float mscale, int heads, int nope, int rd, int vd, int page, int T,
                                cudaStream_t s);
 
+// bf16 [rows, K] -> MXFP8: e4m3 bytes [rows, K] + ue8m0 scales [rows, K / 32] (one per 32 K-values)
+cudaError_t quant_mxfp8_launch(const void* x, long long ld_x, void* q, void* sf, long long rows, int K, cudaStream_t s);
+
 // ---- attention.cu
 struct PagedAttnArgs {
   const void* q; long long q_ld_t, q_ld_h;       // bf16 [T, q_heads, dk]

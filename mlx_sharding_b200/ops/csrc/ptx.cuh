@@ -140,6 +140,37 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// ---- block-scaled FP8 (kind::mxf8f6f4.block_scale): e4m3 x e4m3, fp32 accumulate, one ue8m0 scale per 32 K-elements.
+// Instruction descriptor (cute::UMMA::InstrDescriptorBlockScaled): [4,6) b_sf_id | [7,10) a_format (0 = e4m3) | [10,13) b_format |
+// 15 a_major | 16 b_major | [17,23) N >> 3 | 23 scale format (1 = ue8m0) | [24,29) M >> 4 | [29,31) a_sf_id.
+// a_sf_id / b_sf_id select the byte (0..3) of the 32-bit scale words in TMEM, i.e. which 32-wide K block of the k-block.
+__host__ __device__ constexpr uint32_t umma_idesc_mxf8(uint32_t M, uint32_t N) {
+  return ((N >> 3) << 17) | (1u << 23) | ((M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_sf(uint32_t idesc, uint32_t a_sf_id, uint32_t b_sf_id) {
+  return idesc | (b_sf_id << 4) | (a_sf_id << 29);
+}
+B200_DEVICE void umma_mxf8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t tmem_sfa, uint32_t tmem_sfb,
+                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%4], [%5], p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(tmem_sfa), "r"(tmem_sfb), "r"(accumulate)
+      : "memory");
+}
+// registers -> TMEM: thread i of the warp writes lane (base_lane + i), consecutive 32-bit columns
+B200_DEVICE void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+               : "memory");
+}
+B200_DEVICE void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+B200_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------- scopes
 B200_DEVICE void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

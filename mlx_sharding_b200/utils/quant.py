@@ -104,3 +104,29 @@ def repack_int4_pairs(wq: torch.Tensor) -> torch.Tensor:
         out |= ((w >> (8 * j + 4)) & 0xF) << (16 + 4 * j)
     out = torch.where(out >= 2 ** 31, out - 2 ** 32, out)
     return out.to(torch.int32)
+
+
+# ------------------------------------------------------------------------------------------------ MXFP8 (OCP microscaling)
+def to_mxfp8(w: torch.Tensor):
+    """``w [..., K]`` (any float dtype, ``K % 32 == 0``) -> ``(q uint8 [..., K], sf uint8 [..., K / 32])``: e4m3 elements with one
+    shared power-of-two scale (ue8m0, ``2^(sf - 127)``) per 32 consecutive ``K`` values, ``scale = 2^ceil(log2(amax / 448))``.
+    The load-time format of weights for ``ops/csrc/gemm_fp8.cu`` (``tcgen05.mma kind::mxf8f6f4.block_scale``); the activation side
+    is produced by ``elementwise.cu::quant_mxfp8_kernel`` with the same rule, bit for bit."""
+    K = w.shape[-1]
+    assert K % 32 == 0
+    wf = w.float().reshape(*w.shape[:-1], K // 32, 32)
+    v = wf.abs().amax(-1) * (1.0 / 448.0)
+    bits = v.contiguous().view(torch.int32)
+    e = ((bits >> 23) & 0xFF) + ((bits & 0x7FFFFF) != 0).to(torch.int32)      # biased exponent of the next power of two >= v
+    e = e.clamp(max=254)
+    inv = ((254 - e) << 23).view(torch.float32)                                # 2^-(e - 127)
+    q = (wf * inv.unsqueeze(-1)).to(torch.float8_e4m3fn).view(torch.uint8).reshape(w.shape)
+    return q.contiguous(), e.to(torch.uint8).contiguous()
+
+
+def from_mxfp8(q: torch.Tensor, sf: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    """Inverse of :func:`to_mxfp8` (exact: every MXFP8 value is representable in fp32)."""
+    K = q.shape[-1]
+    scale = ((sf.to(torch.int32)) << 23).view(torch.float32)                   # 2^(sf - 127); sf == 0 -> 0 (block of zeros)
+    x = q.view(torch.float8_e4m3fn).float().reshape(*q.shape[:-1], K // 32, 32) * scale.unsqueeze(-1)
+    return x.reshape(q.shape).to(dtype)
