@@ -1,0 +1,137 @@
+#!/usr/bin/env python
+"""HTTP-level serving benchmark (BASELINE config 4: Llama-3-8B bf16, 4 pipeline stages, OpenAI ``/v1/chat/completions``).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 bench/http_bench.py \
+        --model synthetic:llama3-8b --concurrency 256 --max-tokens 64
+
+Rank 0 runs the product's HTTP server (``server/openai_api.py``: ``ModelProvider`` -> ``LLMEngine`` -> ``ChainPipeline`` with the
+shared-memory launch ring and the fused P2P hand-off) in a thread; the other ranks are ordinary stage workers
+(``shard_server.serve_chain``).  ``--concurrency`` client threads then POST streaming chat requests with the API's DEFAULT sampling
+parameters (temperature 1.0, top_p 1.0 — the reference's defaults, shard/openai_api.py:206-215), i.e. sampled requests, which replay
+the same CUDA graphs as greedy ones because the sampling parameters travel in the step block.  Reports completion tokens/s over
+the whole run (wall clock, host side — this is an end-to-end number through TCP, JSON and SSE), TTFT percentiles and the engine's
+graph-replay counters.  One untimed warm-up round precedes the measured one (graph capture, allocator warm-up)."""
+import argparse
+import http.client
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def client(port, prompt, max_tokens, out, i, extra):
+    body = dict(messages=[{"role": "user", "content": prompt}], stream=True, max_tokens=max_tokens, **extra)
+    t0 = time.perf_counter()
+    c = http.client.HTTPConnection("127.0.0.1", port, timeout=600)
+    c.request("POST", "/v1/chat/completions", json.dumps(body), {"Content-Type": "application/json"})
+    r = c.getresponse()
+    first, n = None, 0
+    buf = b""
+    while True:
+        chunk = r.read1(65536) if hasattr(r, "read1") else r.read(4096)
+        if not chunk:
+            break
+        buf += chunk
+        while b"\n\n" in buf:
+            ev, buf = buf.split(b"\n\n", 1)
+            if not ev.startswith(b"data: "):
+                continue
+            data = ev[6:]
+            if data == b"[DONE]":
+                continue
+            if first is None:
+                first = time.perf_counter() - t0
+            n += 1
+    c.close()
+    out[i] = (first, n, time.perf_counter() - t0, r.status)
+
+
+def run_round(port, conc, max_tokens, extra):
+    out = [None] * conc
+    prompts = [("Request %03d: write a short note about pipeline parallel inference on NVLink-connected GPUs. " % i) * 1 for i in range(conc)]
+    th = [threading.Thread(target=client, args=(port, prompts[i], max_tokens, out, i, extra)) for i in range(conc)]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    wall = time.perf_counter() - t0
+    ok = [o for o in out if o and o[3] == 200 and o[0] is not None]
+    toks = sum(o[1] for o in ok)
+    ttft = sorted(o[0] for o in ok)
+    pct = lambda p: ttft[min(len(ttft) - 1, int(p * len(ttft)))] if ttft else None
+    return dict(requests=conc, ok=len(ok), sse_chunks=toks, wall_s=round(wall, 3), sse_chunks_per_s=round(toks / wall, 1),
+                ttft_p50_ms=round(pct(0.5) * 1e3, 1) if ttft else None, ttft_p90_ms=round(pct(0.9) * 1e3, 1) if ttft else None)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="synthetic:llama3-8b")
+    ap.add_argument("--concurrency", type=int, default=256)
+    ap.add_argument("--max-tokens", type=int, default=64)
+    ap.add_argument("--max-batch", type=int, default=64)
+    ap.add_argument("--port", type=int, default=18080)
+    ap.add_argument("--greedy", action="store_true", help="temperature 0 instead of the API defaults")
+    a = ap.parse_args()
+
+    import torch
+
+    from mlx_sharding_b200.server import openai_api as api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    argv = ["--model", a.model, "--port", str(a.port), "--max-batch", str(a.max_batch), "--kv-pages", "4096", "--log-level", "WARNING"]
+    if rank != 0:
+        return api.main(argv)                       # stage worker: returns when rank 0 shuts the chain down
+    # rank 0: the same start-up as ``mlx-sharding-api`` (layer split, ModelProvider, HTTP server), but in a thread
+    args = api.build_arg_parser().parse_args(argv)
+    if world > 1:
+        from mlx_sharding_b200.config import ModelConfig
+        from mlx_sharding_b200.parallel.partition import balanced_split
+        from mlx_sharding_b200.parallel.transport import init_distributed
+        from mlx_sharding_b200.utils.checkpoint import get_model_path
+
+        init_distributed(device=args.device)
+        cfg = ModelConfig.from_path(get_model_path(args.model))
+        spec = balanced_split(cfg, world)[0]
+        args.start_layer, args.end_layer = spec.start_layer, spec.end_layer
+    args.static_dir = os.path.join(os.path.dirname(os.path.abspath(api.__file__)), "static")
+    provider = api.ModelProvider(args, [])
+    th = threading.Thread(target=api.run, args=(args.host, args.port, provider, args.static_dir), daemon=True)
+    th.start()
+    for _ in range(600):
+        try:
+            c = http.client.HTTPConnection("127.0.0.1", a.port, timeout=2)
+            c.request("GET", "/health")
+            if c.getresponse().status == 200:
+                break
+        except OSError:
+            time.sleep(0.2)
+    extra = dict(temperature=0.0) if a.greedy else {}
+    warm = run_round(a.port, a.concurrency, min(a.max_tokens, 16), extra)
+    eng = provider.engine
+    st0 = dict(eng.stats)
+    res = run_round(a.port, a.concurrency, a.max_tokens, extra)
+    pipe = eng.pipe
+    gc = getattr(pipe, "gcache", None)
+    out = {"bench": "HTTP /v1/chat/completions, streaming, " + ("temperature 0" if a.greedy else "API default sampling (temperature 1.0)"),
+           "model": a.model, "n_gpus": world, "pipeline": type(pipe).__name__,
+           "hand_off": getattr(getattr(pipe, "plane", None), "name", "local"),
+           "control": type(getattr(pipe, "ctl", None)).__name__ if hasattr(pipe, "ctl") else None,
+           "warmup_round": warm, "measured_round": res,
+           "engine_decode_tokens": eng.stats["decode_tokens"] - st0["decode_tokens"], "engine_steps": eng.stats["steps"] - st0["steps"],
+           "tokens_per_s": round((eng.stats["decode_tokens"] - st0["decode_tokens"] + res["ok"]) / res["wall_s"], 1),
+           "graph_replays_stage0": gc.replays if gc is not None else None, "graph_captures_stage0": gc.captures if gc is not None else None}
+    print(json.dumps(out), flush=True)
+    eng.shutdown()
+    if hasattr(pipe, "shutdown"):
+        pipe.shutdown()
+    os._exit(0)     # the HTTP server thread and the engine thread are daemons; workers have left their loop
+
+
+if __name__ == "__main__":
+    main()

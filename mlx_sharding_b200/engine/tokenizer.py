@@ -33,6 +33,11 @@ class StreamingDetokenizer:
         self._committed = ""             # text of finished segments
         self._window_text = ""           # released text of the current segment
         self.offset = 0                  # how much of .text was already handed out
+        # Context for the next segment: the last token of the previous one.  SentencePiece-style decoders strip the leading
+        # space of the *first* token they are given (Llama-2 / Mistral ``Strip(start=1)``), so a segment decoded on its own loses
+        # indentation after every newline; decoding ``[ctx] + window`` and dropping ``decode([ctx])`` keeps it.
+        self._ctx: List[int] = []
+        self._ctx_text = ""
 
     @property
     def text(self) -> str:
@@ -47,17 +52,25 @@ class StreamingDetokenizer:
     def add_token(self, token: int):
         self.tokens.append(int(token))
         self._window.append(int(token))
-        t = self._decode(self._window)
+        t = self._decode_window()
         if t.endswith(_REPLACEMENT):
             return  # incomplete multi-byte char: hold back
         self._window_text = t
         if t.endswith("\n"):
             self._committed += t
+            self._ctx = self._window[-1:]
+            self._ctx_text = self._decode(self._ctx)
             self._window, self._window_text = [], ""
+
+    def _decode_window(self) -> str:
+        if not self._ctx:
+            return self._decode(self._window)
+        t = self._decode(self._ctx + self._window)
+        return t[len(self._ctx_text):] if t.startswith(self._ctx_text) else self._decode(self._window)
 
     def finalize(self):
         if self._window:
-            self._window_text = self._decode(self._window)
+            self._window_text = self._decode_window()
         self._committed += self._window_text
         self._window, self._window_text = [], ""
 

@@ -230,9 +230,13 @@ class StageModel:
         if not all_logits:
             h = h.index_select(0, meta.last_idx.long()) if meta.num_tokens != meta.num_seqs else h
         hn = O.rmsnorm(h, self.norm_w, self.cfg.rms_norm_eps, self.cfg.model_type == "gemma2")
+        cap = float(self.cfg.final_logit_softcapping) if (self.cfg.model_type == "gemma2" and self.cfg.final_logit_softcapping) else 0.0
+        if cap and self.backend_name == "b200":
+            # final-logit soft-capping (reference gemma2.py:82-83) runs in the LM-head GEMM epilogue: cap * tanh(y / cap)
+            return O.linear(hn, self.lm_head, out_dtype=torch.float32, softcap=cap)
         logits = O.linear(hn, self.lm_head, out_dtype=torch.float32)
-        if self.cfg.model_type == "gemma2" and self.cfg.final_logit_softcapping:
-            logits = O.softcap_(logits, float(self.cfg.final_logit_softcapping))
+        if cap:
+            logits = O.softcap_(logits, cap)
         return logits
 
     @torch.inference_mode()

@@ -73,6 +73,9 @@ def _dense(W: LinearWeight) -> torch.Tensor:
     return _bf16(W.weight)
 
 
+_qpack_warned = []
+
+
 def _qpack(W: LinearWeight):
     """(packed int32 codes [rows, words], scales_t, biases_t [K/g, rows]) for the in-kernel dequant GEMM, or None
     when the layout is not supported by the kernel (then the weight is expanded to bf16 once)."""
@@ -82,6 +85,13 @@ def _qpack(W: LinearWeight):
     if qt is None:
         K = W.in_features
         if not C().gemm_q_supported(W.bits, W.group_size, K) or W.scales.dtype != torch.bfloat16:
+            if W.scales.dtype != torch.bfloat16 and not _qpack_warned:
+                import logging
+
+                logging.getLogger(__name__).warning(
+                    "quantised weights with %s scale tables: the in-kernel dequant GEMM takes bf16 tables, so these weights are "
+                    "dequantised exactly (stored-precision scales) to bf16 once at first use instead", W.scales.dtype)
+                _qpack_warned.append(True)
             W._qt = False
             return None
         rows = W.wq.numel() // W.wq.shape[-1]

@@ -29,8 +29,45 @@ from . import quant
 _LAYER_RE = re.compile(r"^model\.layers\.(\d+)\.")
 
 
+_SYNTH_DIRS: Dict[str, str] = {}
+
+
+def synthetic_model_dir(name: str) -> str:
+    """``synthetic:<name>`` model ids (offline boxes, benchmarks): a directory with the canned ``config.json`` of a known
+    architecture, a self-contained byte-level tokenizer and a ``synthetic.json`` marker — no weight files.  ``utils/loader.py``
+    sees the marker and builds random-init weights of that architecture directly on the device (same key layout / shapes as the
+    mlx-community checkpoint), so ``mlx-sharding-api --model synthetic:llama3-8b`` serves a full-size model without a download."""
+    import tempfile
+
+    from ..config import deepseek_v2_lite_config, gemma2_9b_config, llama3_8b_config
+
+    tiny = lambda: dict(model_type="llama", vocab_size=320, hidden_size=64, intermediate_size=128, num_hidden_layers=4,
+                        num_attention_heads=4, num_key_value_heads=2, rms_norm_eps=1e-5, rope_theta=10000.0,
+                        max_position_embeddings=512, tie_word_embeddings=False)
+    canned = {"deepseek-v2-lite": deepseek_v2_lite_config, "llama3-8b": llama3_8b_config, "gemma2-9b": gemma2_9b_config,
+              "tiny-llama": tiny}
+    if name not in canned:
+        raise FileNotFoundError(f"unknown synthetic model '{name}' (known: {sorted(canned)})")
+    d = _SYNTH_DIRS.get(name)
+    if d is None:
+        from ..engine.tokenizer import write_byte_tokenizer
+
+        d = tempfile.mkdtemp(prefix=f"mlxb200_synth_{name}_")
+        cfg = canned[name]()
+        with open(os.path.join(d, "config.json"), "w") as f:
+            json.dump(cfg, f)
+        with open(os.path.join(d, "synthetic.json"), "w") as f:
+            json.dump({"name": name, "seed": 1}, f)
+        write_byte_tokenizer(d, vocab_size=min(int(cfg["vocab_size"]), 4096))
+        _SYNTH_DIRS[name] = d
+    return d
+
+
 def get_model_path(path_or_hf_repo: str) -> str:
-    """Local directory if it exists, else a HF hub snapshot (reference utils.py:34 via mlx_lm)."""
+    """Local directory if it exists, else a HF hub snapshot (reference utils.py:34 via mlx_lm); ``synthetic:<name>`` -> see
+    :func:`synthetic_model_dir`."""
+    if str(path_or_hf_repo).startswith("synthetic:"):
+        return synthetic_model_dir(str(path_or_hf_repo).split(":", 1)[1])
     if os.path.isdir(path_or_hf_repo):
         return path_or_hf_repo
     try:

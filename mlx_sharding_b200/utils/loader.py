@@ -8,7 +8,9 @@ Reference: ``shard/utils.py:33-68``.  Differences (all deliberate)
 """
 from __future__ import annotations
 
+import json
 import logging
+import os
 from typing import Optional
 
 import torch
@@ -29,6 +31,17 @@ def load_model(path_or_hf_repo: str, start_layer: Optional[int] = None, end_laye
     model_path = get_model_path(path_or_hf_repo)
     cfg = ModelConfig.from_path(model_path)
     spec = spec or cfg.shard(start_layer, end_layer)
+    marker = os.path.join(model_path, "synthetic.json")
+    if os.path.exists(marker):   # ``synthetic:<name>``: random-init weights of that architecture, built on the device
+        with open(os.path.join(model_path, "config.json")) as f:
+            cfgd = json.load(f)
+        with open(marker) as f:
+            seed = int(json.load(f).get("seed", 1))
+        dev = device or ("cuda" if torch.cuda.is_available() else "cpu")
+        dt = dtype or (torch.bfloat16 if torch.device(dev).type == "cuda" else torch.float32)
+        model = random_model(cfgd, dtype=dt, device=dev, backend=backend, seed=seed, spec=spec, expert_shard=expert_shard)
+        log.info("built synthetic %s layers %s (%.2f GB) on %s", cfg.model_type, spec.describe(), model.weight_bytes() / 1e9, dev)
+        return model
     device = device or ("cuda" if torch.cuda.is_available() else "cpu")
     if dtype is None:
         dtype = torch.bfloat16 if torch.device(device).type == "cuda" else torch.float32

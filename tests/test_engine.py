@@ -235,3 +235,41 @@ def test_scheduler_stress_random_traffic_keeps_invariants():
         assert not eng.table.pages and eng.table.alloc.num_free == 40 - 1
         if eng.table.prefix is not None:
             assert all(v == 0 for v in eng.table.prefix.refs.values())
+
+
+def test_streaming_detokenizer_keeps_leading_space_after_newline():
+    """SentencePiece-style decoders drop the leading space of the first token they are given; the streaming detokenizer restarts its
+    window after every newline and must not lose indentation there."""
+    from mlx_sharding_b200.engine.tokenizer import StreamingDetokenizer
+
+    class SpmLike:
+        vocab = {1: "def", 2: "▁f():", 3: "\n", 4: "▁▁▁▁return", 5: "▁1", 6: "\n", 7: "▁x"}
+
+        def decode(self, ids):
+            s = "".join(self.vocab[i] for i in ids).replace("▁", " ")
+            return s[1:] if s.startswith(" ") else s        # Strip(start=1)
+
+    d = StreamingDetokenizer(SpmLike())
+    out = ""
+    for t in [1, 2, 3, 4, 5, 6, 7]:
+        d.add_token(t)
+        out += d.last_segment
+    d.finalize()
+    out += d.last_segment
+    assert out == "def f():\n    return 1\n x", repr(out)
+    assert d.text == out
+
+
+def test_max_tokens_zero_generates_nothing():
+    from helpers import TINY_LLAMA
+    from mlx_sharding_b200.config import ModelConfig
+    from mlx_sharding_b200.models import build_stage
+    from mlx_sharding_b200.parallel.pipeline import LocalPipeline
+    from mlx_sharding_b200.utils.checkpoint import random_state_dict
+
+    cfg = ModelConfig.from_dict(TINY_LLAMA)
+    m = build_stage(cfg, cfg.shard(), torch.float32).load_state(dict(random_state_dict(cfg, dtype=torch.float32)))
+    eng = LLMEngine(LocalPipeline.from_models([m], 16, 16), 16, 16)
+    r = eng.submit([1, 2, 3], SamplingParams(), max_tokens=0)
+    assert r.finished and r.finish_reason == "length" and r.output == [] and list(r) == []
+    assert eng.table.alloc.num_free == 15 and not eng.has_work()
