@@ -137,7 +137,8 @@ Tensor linear(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& w2,
 Tensor grouped_linear(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& w2, const Tensor& expert_offsets,
                       int64_t max_rows, int64_t act, bool out_fp32, const c10::optional<Tensor>& row_dst,
                       const c10::optional<Tensor>& signal_peers, const c10::optional<Tensor>& done_counter, int64_t expected_rows,
-                      int64_t expert_stride) {
+                      int64_t expert_stride, int64_t ep_arrive_ptr, const c10::optional<Tensor>& ep_seq, int64_t ep_error_ptr,
+                      int64_t ep_world, bool ep_zero_other) {
   check_bf16(x, "x"); check_bf16(w, "w"); check_rows(x, "x");
   TORCH_CHECK(w.dim() == 3 && w.is_contiguous(), "w must be contiguous [E, N, K]");
   const c10::cuda::CUDAGuard guard(x.device());
@@ -145,6 +146,8 @@ Tensor grouped_linear(const Tensor& x, const Tensor& w, const c10::optional<Tens
   // expert_stride > 0 (scatter layout): expert e owns rows [e * stride, e * stride + expert_offsets[e]) and the array holds COUNTS
   TORCH_CHECK(w.size(2) == K && expert_offsets.scalar_type() == torch::kInt32 &&
               (expert_stride > 0 ? (expert_offsets.numel() >= E && R >= E * expert_stride) : expert_offsets.numel() == E + 1));
+  TORCH_CHECK(ep_arrive_ptr == 0 || (expert_stride > 0 && ep_seq.has_value() && expert_offsets.numel() >= 2 * E),
+              "EP arrival wait needs the scatter layout with parity-double-buffered counts");
   // EP return path (parallel/ep.py): every output row goes to the address in row_dst[row] (the source rank's return buffer, peer
   // memory) and all `signal_peers` flags are bumped once every tile is stored — the un-fused return kernel disappears
   const bool ep_ret = row_dst.has_value();
@@ -156,6 +159,12 @@ Tensor grouped_linear(const Tensor& x, const Tensor& w, const c10::optional<Tens
   if (w2.has_value()) { check_bf16(*w2, "w2"); TORCH_CHECK(w2->is_contiguous() && w2->sizes() == w.sizes()); a.w2 = w2->data_ptr(); }
   a.m = (int)R; a.n = (int)N; a.k = (int)K; a.max_rows = (int)std::min<int64_t>(max_rows, R);
   a.num_experts = (int)E; a.expert_offsets = expert_offsets.data_ptr<int>(); a.expert_stride = (int)expert_stride;
+  if (ep_arrive_ptr != 0) {
+    a.ep_arrive = reinterpret_cast<const unsigned long long*>(ep_arrive_ptr);
+    a.ep_seq = reinterpret_cast<const uint32_t*>(ep_seq->data_ptr<int>());
+    a.ep_error = reinterpret_cast<uint32_t*>(ep_error_ptr);
+    a.ep_world = (int)ep_world; a.ep_zero_other = ep_zero_other;
+  }
   if (ep_ret) {
     TORCH_CHECK(signal_peers.has_value() && done_counter.has_value() && row_dst->scalar_type() == torch::kInt64 &&
                 signal_peers->scalar_type() == torch::kInt64 && row_dst->numel() >= R && row_dst->is_contiguous(), "bad EP return arguments");
@@ -663,6 +672,23 @@ void ep_dispatch(const Tensor& x, const Tensor& idx, int64_t experts_per_rank, i
                                      ret_expected.has_value() ? reinterpret_cast<uint32_t*>(ret_expected->data_ptr<int>()) : nullptr,
                                      cur_stream()));
 }
+void ep_dispatch_scatter(const Tensor& x, const Tensor& idx, int64_t experts_per_rank, int64_t my_rank, int64_t cap_e,
+                         std::vector<int64_t> recv_x, std::vector<int64_t> recv_dst, std::vector<int64_t> recv_cnt,
+                         std::vector<int64_t> recv_seq, std::vector<int64_t> my_ret, Tensor send_seq, Tensor done_counter,
+                         const c10::optional<Tensor>& ret_expected) {
+  check_bf16(x, "x"); check_rows(x, "x");
+  TORCH_CHECK(idx.scalar_type() == torch::kInt32 && idx.is_contiguous() && idx.dim() == 2);
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int world = (int)recv_x.size();
+  auto a = to_u64(recv_x), b = to_u64(recv_dst), c = to_u64(recv_cnt), d = to_u64(recv_seq), e = to_u64(my_ret);
+  LAUNCH_OK(b200::ep_dispatch_scatter_launch(x.data_ptr(), x.stride(0), idx.data_ptr<int>(), (int)idx.numel(), (int)idx.size(1), (int)x.size(1),
+                                             (int)experts_per_rank, world, (int)my_rank, (int)cap_e, a.data(), b.data(), c.data(), d.data(),
+                                             e.data(), reinterpret_cast<uint32_t*>(send_seq.data_ptr<int>()),
+                                             reinterpret_cast<unsigned int*>(done_counter.data_ptr<int>()),
+                                             ret_expected.has_value() ? reinterpret_cast<uint32_t*>(ret_expected->data_ptr<int>()) : nullptr,
+                                             cur_stream()));
+}
+
 std::vector<Tensor> ep_regroup(int64_t recv_words_ptr, int64_t counter_ptr, int64_t error_ptr, int64_t recv_meta_ptr,
                                int64_t recv_x_ptr, int64_t world, int64_t cap, int64_t E_local, int64_t H, int64_t device,
                                int64_t rows_bound, std::vector<int64_t> ret_y) {
@@ -711,7 +737,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("grouped_linear", &grouped_linear, py::arg("x"), py::arg("w"), py::arg("w2") = py::none(), py::arg("expert_offsets"),
         py::arg("max_rows"), py::arg("act") = 0, py::arg("out_fp32") = false, py::arg("row_dst") = py::none(),
         py::arg("signal_peers") = py::none(), py::arg("done_counter") = py::none(), py::arg("expected_rows") = 0,
-        py::arg("expert_stride") = 0);
+        py::arg("expert_stride") = 0, py::arg("ep_arrive_ptr") = 0, py::arg("ep_seq") = py::none(), py::arg("ep_error_ptr") = 0,
+        py::arg("ep_world") = 0, py::arg("ep_zero_other") = false);
   m.def("linear_q", &linear_q);
   m.def("grouped_linear_q", &grouped_linear_q);
   m.def("gemm_q_supported", &gemm_q_supported);
@@ -757,6 +784,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ep_dispatch", &ep_dispatch, py::arg("x"), py::arg("idx"), py::arg("experts_per_rank"), py::arg("my_rank"), py::arg("cap"),
         py::arg("recv_x"), py::arg("recv_meta"), py::arg("recv_words"), py::arg("send_seq"), py::arg("send_counts"),
         py::arg("done_counter"), py::arg("ret_expected") = py::none());
+  m.def("ep_dispatch_scatter", &ep_dispatch_scatter, py::arg("x"), py::arg("idx"), py::arg("experts_per_rank"), py::arg("my_rank"),
+        py::arg("cap_e"), py::arg("recv_x"), py::arg("recv_dst"), py::arg("recv_cnt"), py::arg("recv_seq"), py::arg("my_ret"),
+        py::arg("send_seq"), py::arg("done_counter"), py::arg("ret_expected") = py::none());
   m.def("ep_regroup", &ep_regroup, py::arg("recv_words_ptr"), py::arg("counter_ptr"), py::arg("error_ptr"),
         py::arg("recv_meta_ptr"), py::arg("recv_x_ptr"), py::arg("world"), py::arg("cap"), py::arg("E_local"), py::arg("H"),
         py::arg("device"), py::arg("rows_bound") = 0, py::arg("ret_y") = std::vector<int64_t>());

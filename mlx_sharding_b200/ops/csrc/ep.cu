@@ -90,6 +90,62 @@ __global__ void ep_dispatch_kernel(const __nv_bfloat16* __restrict__ x, long lon
   }
 }
 
+// ---------------------------------------------------------------------------------------------- dispatch, v2 (scatter)
+// Sender-side slot reservation: each (token, k) pair claims a slot in the *destination's* expert-major receive buffer with one
+// system-scope atomic on the destination's per-expert row counter (counters double-buffered by step parity), so rows land
+// expert-contiguous where the grouped GEMM's TMA reads them — the receiver needs no regroup (counting sort + gather) kernels.
+// Next to the row the sender stores the address of the pair's slot in ITS return buffer *as mapped by the destination* (table
+// exchanged at set-up), which is what the down-projection epilogue stores to.  Publication: the last CTA writes the step's sequence
+// number to every destination (release.sys, after every CTA fenced its rows); the destination's grouped GEMM acquires all of them
+// (gemm_persistent.cu, GemmParams::ep_arrive).
+__global__ void ep_dispatch_scatter_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const int* __restrict__ idx, int npairs,
+                                           int top_k, int H, int experts_per_rank, int world, int my_rank, int cap_e,
+                                           PeerTable recv_x,     // per dst: base of [E_local][cap_e][H] bf16
+                                           PeerTable recv_dst,   // per dst: base of [E_local][cap_e] u64 (return address of each row)
+                                           PeerTable recv_cnt,   // per dst: base of [2][E_local] int32 row counters
+                                           PeerTable recv_seq,   // per dst: base of [world] u64 arrival words
+                                           PeerTable my_ret,     // per dst: base of MY return buffer as mapped by that destination
+                                           uint32_t* __restrict__ send_seq, unsigned int* __restrict__ done_counter,
+                                           uint32_t* __restrict__ ret_expected) {
+  pdl_sync();
+  const int warps_per_cta = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = H / 8;
+  const uint32_t seq = *reinterpret_cast<const volatile uint32_t*>(send_seq) + 1u;   // this step (bumped by the last CTA below)
+  const int par = (int)(seq & 1u);
+  for (int p = blockIdx.x * warps_per_cta + warp; p < npairs; p += gridDim.x * warps_per_cta) {
+    const int e = idx[p];
+    const int dst = e / experts_per_rank, le = e - dst * experts_per_rank;
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd_system(reinterpret_cast<int*>(recv_cnt.p[dst]) + par * experts_per_rank + le, 1);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot < cap_e) {
+      const size_t row = (size_t)le * cap_e + slot;
+      const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)(p / top_k) * ld_x);
+      uint4* drow = reinterpret_cast<uint4*>(recv_x.p[dst]) + row * nvec;
+      for (int v = lane; v < nvec; v += 32) drow[v] = src[v];
+      if (lane == 0)
+        reinterpret_cast<unsigned long long*>(recv_dst.p[dst])[row] = my_ret.p[dst] + (unsigned long long)p * H * sizeof(float);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) + 1u == gridDim.x);
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    for (int r = threadIdx.x; r < world; r += blockDim.x)
+      st_release_sys_u64(reinterpret_cast<unsigned long long*>(recv_seq.p[r]) + my_rank, (unsigned long long)seq);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      *send_seq = seq;
+      *done_counter = 0u;
+      if (ret_expected != nullptr) *ret_expected += (uint32_t)world;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- regroup
 // single CTA: wait for all sources, bucket received rows by local expert
 __global__ void __launch_bounds__(1024)
@@ -239,6 +295,22 @@ cudaError_t ep_dispatch_launch(const void* x, long long ld_x, const int* idx, in
   (void)launch_pdl(ep_dispatch_kernel, dim3(grid), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(x), ld_x, idx, npairs, top_k, H, experts_per_rank, world,
                                           my_rank, cap, make_table(recv_x, world), make_table(recv_meta, world),
                                           make_table(recv_count, world), send_seq, send_counts, done_counter, ret_expected);
+  return cudaGetLastError();
+}
+
+cudaError_t ep_dispatch_scatter_launch(const void* x, long long ld_x, const int* idx, int npairs, int top_k, int H, int experts_per_rank,
+                                       int world, int my_rank, int cap_e, const unsigned long long* recv_x,
+                                       const unsigned long long* recv_dst, const unsigned long long* recv_cnt,
+                                       const unsigned long long* recv_seq, const unsigned long long* my_ret, uint32_t* send_seq,
+                                       unsigned int* done_counter, uint32_t* ret_expected, cudaStream_t s) {
+  if (world > kMaxWorld || (H % 8)) return cudaErrorInvalidValue;
+  int grid = (npairs + 7) / 8;
+  if (grid < 1) grid = 1;
+  if (grid > 592) grid = 592;
+  (void)launch_pdl(ep_dispatch_scatter_kernel, dim3(grid), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(x), ld_x, idx, npairs, top_k, H,
+                   experts_per_rank, world, my_rank, cap_e, make_table(recv_x, world), make_table(recv_dst, world),
+                   make_table(recv_cnt, world), make_table(recv_seq, world), make_table(my_ret, world), send_seq, done_counter,
+                   ret_expected);
   return cudaGetLastError();
 }
 

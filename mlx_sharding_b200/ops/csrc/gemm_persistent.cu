@@ -86,8 +86,9 @@ __device__ __forceinline__ void publish_tiles_done(const GemmParams& p, unsigned
 template <int BN, bool DUAL, typename OutT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_w2,
-                       const __grid_constant__ CUtensorMap tmap_x, const GemmParams p, const int tiles_n, const int tiles_m,
+                       const __grid_constant__ CUtensorMap tmap_x, const GemmParams p_in, const int tiles_n, const int tiles_m,
                        const int num_tiles) {
+  GemmParams p = p_in;
   constexpr int STAGES = p_num_stages(BN, DUAL, sizeof(OutT));
   constexpr int STAGE_BYTES = stage_bytes(BN, DUAL);
   constexpr int ACC_COLS = p_acc_cols(BN, DUAL);
@@ -112,6 +113,33 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   const int lane = threadIdx.x & 31;
   const bool pdl_early = p.expert_offsets != nullptr;
   if (pdl_early) pdl_wait();
+  if (p.ep_arrive != nullptr) {
+    // Expert-parallel receive side: the token rows, their return addresses and the per-expert row counts of this step are written
+    // into this rank's buffers by the *other ranks'* dispatch kernels.  Each source publishes the step's sequence number with
+    // release.sys after its rows; one thread per CTA acquires all of them (bounded spin), then the whole CTA proceeds.  This wait
+    // used to be a separate single-CTA kernel followed by a gather; now the persistent GEMM's CTAs are already resident (PDL).
+    if (threadIdx.x == 0) {
+      const uint32_t expected = *reinterpret_cast<const volatile uint32_t*>(p.ep_seq);   // == my own dispatch count (lock-step ranks)
+      unsigned long long t0;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+      for (int r = 0; r < p.ep_world; ++r) {
+        while (static_cast<uint32_t>(ld_acquire_sys_u64(p.ep_arrive + r)) != expected) {
+          unsigned long long t1;
+          asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+          if (t1 - t0 > 20000000000ull) { if (p.ep_error != nullptr) atomicExch(p.ep_error, 1u); break; }
+          __nanosleep(32);
+        }
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    const uint32_t par = *reinterpret_cast<const volatile uint32_t*>(p.ep_seq) & 1u;
+    const int ne = num_tiles / (tiles_n * tiles_m);      // experts on this rank
+    // counts are double-buffered by step parity; the buffer of the *other* parity (last step's) is reset for the next step
+    if (p.ep_zero_other && blockIdx.x == 0)
+      for (int e = threadIdx.x; e < ne; e += blockDim.x) const_cast<int*>(p.expert_offsets)[(par ^ 1u) * ne + e] = 0;
+    p.expert_offsets += par * ne;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
@@ -393,6 +421,7 @@ cudaError_t gemm_persistent_launch(const GemmArgs& a, cudaStream_t stream) {
 
   GemmParams p;
   p.row_dst = nullptr; p.signal_peers = nullptr; p.num_signal_peers = 0; p.w_sf = p.w2_sf = p.x_sf = nullptr; p.sf_ld_w = p.sf_ld_x = 0;
+  p.ep_arrive = a.ep_arrive; p.ep_seq = a.ep_seq; p.ep_error = a.ep_error; p.ep_world = a.ep_world; p.ep_zero_other = a.ep_zero_other ? 1 : 0;
   p.m = a.m; p.n = a.n; p.k = a.k; p.splits = 1; p.cluster_splitk = 0;
   p.expert_offsets = a.expert_offsets;
   p.expert_stride = a.expert_stride;

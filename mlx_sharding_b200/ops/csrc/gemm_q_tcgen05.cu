@@ -330,7 +330,7 @@ cudaError_t gemm_q_launch(const GemmArgs& a, cudaStream_t stream) {
   if (!q_make_tmap(&t.x, 0, a.x, a.k, a.x_rows, a.ld_x, kBlockK, bn)) return cudaErrorUnknown;
 
   GemmParams p;
-  p.row_dst = nullptr; p.signal_peers = nullptr; p.num_signal_peers = 0; p.w_sf = p.w2_sf = p.x_sf = nullptr; p.sf_ld_w = p.sf_ld_x = 0; p.expert_stride = 0;
+  p.row_dst = nullptr; p.signal_peers = nullptr; p.num_signal_peers = 0; p.w_sf = p.w2_sf = p.x_sf = nullptr; p.sf_ld_w = p.sf_ld_x = 0; p.ep_arrive = nullptr; p.ep_seq = nullptr; p.ep_error = nullptr; p.ep_world = 0; p.ep_zero_other = 0; p.expert_stride = 0;
   p.m = a.m; p.n = a.n; p.k = a.k; p.splits = splits;
   p.cluster_splitk = 0;
   p.expert_offsets = a.expert_offsets;

@@ -16,6 +16,9 @@ struct GemmParams {
   // block-scaled FP8 (gemm_fp8.cu): ue8m0 scale words (4 scales = one 128-element k-block per uint32), row-major [rows, K / 128]
   const uint32_t* w_sf; const uint32_t* w2_sf; const uint32_t* x_sf;
   int sf_ld_w, sf_ld_x;
+  // Expert-parallel receive side (ep.cu v2, gemm_persistent.cu only): before touching tokens / counts the kernel waits until every
+  // source rank has published this step's sequence number (ep_arrive[r], acquire.sys); counts are double-buffered by step parity
+  const unsigned long long* ep_arrive; const uint32_t* ep_seq; uint32_t* ep_error; int ep_world; int ep_zero_other;
   int expert_stride;  // > 0: experts live at fixed row stride, expert_offsets[e] is the row COUNT of expert e (scatter layout)
   void* out;
   long long ld_out;
@@ -49,6 +52,8 @@ struct GemmArgs {
   int max_rows = 0;               // upper bound of rows per (expert) problem: sizes the grid
   int num_experts = 0;            // grouped: number of experts
   const int* expert_offsets = nullptr;  // grouped: int32 [num_experts + 1] row offsets into x / out (device)
+  const unsigned long long* ep_arrive = nullptr; const uint32_t* ep_seq = nullptr; uint32_t* ep_error = nullptr;
+  int ep_world = 0; bool ep_zero_other = false;   // EP receive side: arrival wait fused into the grouped GEMM (see GemmParams)
   int expert_stride = 0;                // > 0: expert e owns rows [e * stride, e * stride + expert_offsets[e]) (counts, not offsets)
   void* out = nullptr;            // bf16 (or fp32 if out_fp32) [rows, n], row stride ld_out; may be a peer pointer
   long long ld_out = 0;

@@ -113,6 +113,12 @@ cudaError_t ep_dispatch_launch(const void* x, long long ld_x, const int* idx, in
                                int world, int my_rank, int cap, const unsigned long long* recv_x, const unsigned long long* recv_meta,
                                const unsigned long long* recv_count, uint32_t* send_seq, int* send_counts,
                                unsigned int* done_counter, uint32_t* ret_expected, cudaStream_t s);
+// v2: sender-side slot reservation into the destination's expert-major buffer (no regroup kernels on the receive side)
+cudaError_t ep_dispatch_scatter_launch(const void* x, long long ld_x, const int* idx, int npairs, int top_k, int H, int experts_per_rank,
+                                       int world, int my_rank, int cap_e, const unsigned long long* recv_x,
+                                       const unsigned long long* recv_dst, const unsigned long long* recv_cnt,
+                                       const unsigned long long* recv_seq, const unsigned long long* my_ret, uint32_t* send_seq,
+                                       unsigned int* done_counter, uint32_t* ret_expected, cudaStream_t s);
 cudaError_t ep_regroup_launch(const unsigned long long* recv_words, uint32_t* local_counter, uint32_t* error_flag, int* recv_count,
                               const void* recv_meta, const void* recv_x, int world, int cap, int E_local, int H, int* expert_offsets,
                               int* row_perm, int* total_rows, void* x_perm, const unsigned long long* ret_y,

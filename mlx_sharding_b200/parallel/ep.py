@@ -25,18 +25,32 @@ from ..ops.weights import LinearWeight
 class EPBuffers:
     """IPC-mapped receive / return buffers of one rank (shared by all MoE layers of that rank)."""
 
-    def __init__(self, hidden: int, max_tokens: int, top_k: int, group=None):
+    def __init__(self, hidden: int, max_tokens: int, top_k: int, group=None, experts_per_rank: int = 0):
+        import os
+
         from ..ops import b200
 
         self.C = b200.load_extension()
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.dev = torch.cuda.current_device()
         self.H, self.top_k = hidden, top_k
+        self.max_tokens = max_tokens
+        # v2 (default): sender-side slot reservation into an expert-major receive buffer, no regroup kernels (ops/csrc/ep.cu)
+        self.v2 = experts_per_rank > 0 and os.environ.get("MLXB200_EP_V2", "1") != "0"
+        self.E_local = experts_per_rank
         self.cap = max_tokens * top_k                      # rows one source can send to one destination
         W, cap, H = self.world, self.cap, hidden
         self.off_recv_x = 0
-        self.off_recv_meta = self.off_recv_x + W * cap * H * 2
-        self.off_recv_count = self.off_recv_meta + W * cap * 8
+        if self.v2:
+            # [E_local][W * max_tokens][H] rows + their return addresses (u64) + [2][E_local] counters; arrival words live in the
+            # recv_count slot
+            rows = experts_per_rank * W * max_tokens
+            self.off_recv_meta = self.off_recv_x + rows * H * 2            # -> row_dst table
+            self.off_cnt = self.off_recv_meta + rows * 8
+            self.off_recv_count = (self.off_cnt + 2 * experts_per_rank * 4 + 255) // 256 * 256
+        else:
+            self.off_recv_meta = self.off_recv_x + W * cap * H * 2
+            self.off_recv_count = self.off_recv_meta + W * cap * 8
         self.off_ret_y = (self.off_recv_count + W * 8 + 255) // 256 * 256     # recv_count: one u64 (count << 32 | step seq) per source
         self.off_flags = self.off_ret_y + cap * H * 4
         total = self.off_flags + 256
@@ -57,6 +71,14 @@ class EPBuffers:
         self.t_recv_count = [p + self.off_recv_count for p in self.peer]
         self.t_ret_y = [p + self.off_ret_y for p in self.peer]
         self.t_ret_flag = [p + self.off_flags + 128 for p in self.peer]
+        if self.v2:
+            self.t_cnt = [p + self.off_cnt for p in self.peer]
+            # my return buffer as mapped by every destination (the address a destination's down-projection epilogue stores to)
+            peers_all: List = [None] * W
+            dist.all_gather_object(peers_all, list(self.peer), group=group)
+            self.t_my_ret = [peers_all[d][self.rank] + self.off_ret_y for d in range(W)]
+            self.cnt = self.C.tensor_from_ptr(self.base + self.off_cnt, [2 * experts_per_rank], "int32", self.dev)
+            self._views = {}
         # device-resident local state: [send_counts(world) | dispatch done ctr | down-GEMM tile ctr | regroup step seq seen |
         #                               return arrivals expected | dispatch step seq | ... | error]
         self.state = torch.zeros(W + 8, dtype=torch.int32, device="cuda")
@@ -66,6 +88,15 @@ class EPBuffers:
 
     def error(self) -> bool:
         return bool(self.state[-1].item())
+
+    def recv_views(self, stride: int):
+        """(rows [E_local * stride, H] bf16, row_dst [E_local * stride] int64) over the v2 receive buffer for this step's stride."""
+        v = self._views.get(stride)
+        if v is None:
+            R = self.E_local * stride
+            v = self._views[stride] = (self.C.tensor_from_ptr(self.base + self.off_recv_x, [R, self.H], "bfloat16", self.dev),
+                                       self.C.tensor_from_ptr(self.base + self.off_recv_meta, [R], "int64", self.dev))
+        return v
 
 
 class ExpertParallelMoE:
@@ -95,6 +126,8 @@ class ExpertParallelMoE:
         W = b.world
         st = b.state
         Tmax = max(T, peer_tokens or getattr(self, "peer_tokens_default", 0) or 0)
+        if b.v2:
+            return self._forward_v2(x, idx, w, residual, out, Tmax, join)
         # 1) dispatch my pairs to the owners of their experts (remote stores + count/flag publication); also advances the
         #    arrival target of this step's combine (st[W+3] += world)
         C.ep_dispatch(x, idx, self.E_local, b.rank, b.cap, b.t_recv_x, b.t_recv_meta, b.t_recv_count, st[W + 4:W + 5],
@@ -113,6 +146,35 @@ class ExpertParallelMoE:
         if join is not None:
             join.wait()  # ``residual`` (shared-expert branch) is produced on the side stream
         return C.ep_combine(b.base + b.off_flags + 128, st[W + 3:W + 4], st[-1:].data_ptr(), b.ret_y, w, residual, out)
+
+
+    # (method of ExpertParallelMoE; placed after forward for readability)
+    pass
+
+
+def _forward_v2(self, x, idx, w, residual, out, Tmax, join):
+    """v2 exchange: 4 launches — dispatch (slot reservation at the sender) -> grouped gate/up GEMM (acquires the arrivals itself) ->
+    grouped down GEMM (epilogue returns the rows) -> combine.  The receive stride of this step is ``world * Tmax`` rows per expert
+    (every rank computes the same value: ranks step in lock-step with equal batch shapes, or pass ``peer_tokens``)."""
+    b, C = self.b, self.b.C
+    T, k = idx.shape
+    W, st = b.world, b.state
+    stride = min(W * b.max_tokens, (W * Tmax + 63) // 64 * 64)
+    rows, row_dst = b.recv_views(stride)
+    C.ep_dispatch_scatter(x, idx, self.E_local, b.rank, stride, b.t_recv_x, b.t_recv_meta, b.t_cnt, b.t_recv_count, b.t_my_ret,
+                          st[W + 4:W + 5], st[W:W + 1], st[W + 3:W + 4])
+    max_rows = min(W * Tmax, stride)
+    exp_rows = T * k
+    arrive, seq, err = b.base + b.off_recv_count, st[W + 4:W + 5], st[-1:].data_ptr()
+    h = C.grouped_linear(rows, self.wg, self.wu, b.cnt, max_rows, self.act, False, None, None, None, exp_rows, stride, arrive, seq, err, W, True)
+    C.grouped_linear(h, self.wd, None, b.cnt, max_rows, 0, True, row_dst, b.ret_flags_dev, st[W + 1:W + 2], exp_rows, stride, arrive, seq, err,
+                     W, False)
+    if join is not None:
+        join.wait()
+    return C.ep_combine(b.base + b.off_flags + 128, st[W + 3:W + 4], st[-1:].data_ptr(), b.ret_y, w, residual, out)
+
+
+ExpertParallelMoE._forward_v2 = _forward_v2
 
 
 class ExpertParallelMoERef:
@@ -188,7 +250,9 @@ def enable_expert_parallel(model, max_tokens: int = 256, group=None):
     if hasattr(model, "unfuse_shared_experts"):
         model.unfuse_shared_experts()     # shared experts were appended to the (un-sharded) routed bank: split them off again
     fused = model.backend_name == "b200"
-    bufs = EPBuffers(cfg.hidden_size, max_tokens, cfg.num_experts_per_tok, group=group) if fused else None
+    world = dist.get_world_size(group)
+    bufs = EPBuffers(cfg.hidden_size, max_tokens, cfg.num_experts_per_tok, group=group,
+                     experts_per_rank=cfg.n_routed_experts // world) if fused else None
     model.ep_layers = {}
     for i, w in model.layer_weights.items():
         if "router" not in w:

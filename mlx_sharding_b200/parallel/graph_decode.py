@@ -129,9 +129,50 @@ def sampling_variant(params) -> Tuple[int, int, int]:
     return C, NB, k
 
 
+def decode_bucket(B: int) -> int:
+    """Batch sizes of captured decode graphs: 1, 2, 4, 8, then multiples of 8 up to 64, then multiples of 16."""
+    if B <= 8:
+        return _pow2_at_least(B, 1)
+    return (B + 7) // 8 * 8 if B <= 64 else (B + 15) // 16 * 16
+
+
+def _pad_decode(meta: BatchMeta, tokens: torch.Tensor, params, contexts, rng, Bp: int):
+    """Pad a pure-decode step to ``Bp`` sequences with dummy rows that read / write the reserved null page (page 0, position 0)."""
+    from ..engine.sampler import SamplingParams
+
+    B, n = meta.num_seqs, Bp - meta.num_seqs
+    z = lambda k: torch.zeros(k, dtype=torch.int32)
+    mb = meta.block_tables.shape[1]
+    meta = BatchMeta(torch.cat([meta.positions, z(n)]), torch.cat([meta.slot_mapping, z(n)]), torch.arange(Bp + 1, dtype=torch.int32),
+                     torch.cat([meta.context_lens, torch.ones(n, dtype=torch.int32)]),
+                     torch.cat([meta.block_tables, torch.zeros(n, mb, dtype=torch.int32)]), torch.arange(Bp, dtype=torch.int32),
+                     Bp, Bp, 1, meta.max_ctx_len, meta.page_size)
+    tokens = torch.cat([tokens, torch.zeros(n, dtype=tokens.dtype)])
+    params = list(params) + [_PAD_PARAMS] * n
+    contexts = (list(contexts) + [[]] * n) if contexts is not None else None
+    rng = (list(rng) + [(0, 0)] * n) if rng is not None else None
+    return meta, tokens, params, contexts, rng
+
+
+_PAD_PARAMS = None
+
+
 def pack_step(seq: int, meta: BatchMeta, tokens: torch.Tensor, params, contexts, rng, is_prefill: bool,
-              pad_blocks_to: int = 0) -> Tuple[np.ndarray, StepLayout]:
-    """Host side (stage 0): one int32 vector ``[header | step block]`` for this step.  ``rng[b]`` = (seed, sampled so far)."""
+              pad_decode: bool = False) -> Tuple[np.ndarray, StepLayout]:
+    """Host side (stage 0): one int32 vector ``[header | step block]`` for this step.  ``rng[b]`` = (seed, sampled so far).
+
+    ``pad_decode``: a pure decode step is padded to the next batch-size bucket (``decode_bucket``) with dummy rows on the null
+    page, so that continuous batching — sequences joining and leaving every few steps — keeps replaying a handful of captured
+    graphs instead of capturing one per distinct batch size (the caller drops the dummy rows of the result)."""
+    global _PAD_PARAMS
+    if pad_decode and meta.max_q_len == 1 and meta.num_tokens == meta.num_seqs:
+        Bp = decode_bucket(meta.num_seqs)
+        if Bp != meta.num_seqs:
+            if _PAD_PARAMS is None:
+                from ..engine.sampler import SamplingParams
+
+                _PAD_PARAMS = SamplingParams()
+            meta, tokens, params, contexts, rng = _pad_decode(meta, tokens, params, contexts, rng, Bp)
     T, B = meta.num_tokens, meta.num_seqs
     mb = meta.block_tables.shape[1]
     C, NB, k = sampling_variant(params)

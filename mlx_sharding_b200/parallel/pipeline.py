@@ -180,6 +180,15 @@ def _fetch(res: torch.Tensor) -> torch.Tensor:
     return host
 
 
+def _step_output(parsed, n_real: int) -> StepOutput:
+    """Result lists -> ``StepOutput`` of the ``n_real`` real sequences (decode steps may carry padding rows, see ``pack_step``)."""
+    toks, lp, ti, tl = parsed
+    if len(toks) != n_real:
+        toks, lp = toks[:n_real], lp[:n_real]
+        ti, tl = (None if ti is None else ti[:n_real]), (None if tl is None else tl[:n_real])
+    return StepOutput(toks, lp, ti, tl)
+
+
 class LocalPipeline:
     """All stages in-process, executed back to back."""
 
@@ -202,14 +211,15 @@ class LocalPipeline:
 
     def submit(self, inp: StepInput) -> StepOutput:
         self._seq += 1
-        wire, lay = pack_step(self._seq, inp.meta, inp.tokens, inp.params, inp.contexts, inp.rng, inp.is_prefill)
+        wire, lay = pack_step(self._seq, inp.meta, inp.tokens, inp.params, inp.contexts, inp.rng, inp.is_prefill,
+                              pad_decode=self.gcache is not None and self.gcache.enabled)
         x = None
         for r in self.runners:
             x = r.run(wire, inp.group, x_local=None if x is None else x.to(r.dev))
         rl = ResultLayout(lay.B, lay.k)
         host = _fetch(x)
         self.d2h_bytes += rl.nbytes
-        return StepOutput(*parse_result(host, rl, self._seq))
+        return _step_output(parse_result(host, rl, self._seq), inp.meta.num_seqs)
 
     def wait(self, handle) -> StepOutput:
         return handle
@@ -480,7 +490,8 @@ class ChainPipeline:
             raise RuntimeError(self._dead)
         self._seq += 1
         seq = self._seq
-        wire, lay = pack_step(seq, inp.meta, inp.tokens, inp.params, inp.contexts, inp.rng, inp.is_prefill)
+        wire, lay = pack_step(seq, inp.meta, inp.tokens, inp.params, inp.contexts, inp.rng, inp.is_prefill,
+                              pad_decode=self.gcache.enabled)
         self.ctl.publish(KIND_STEP, inp.group, wire)
         try:
             self.runner.run(wire, inp.group)
@@ -489,7 +500,7 @@ class ChainPipeline:
             self.ctl.set_error(seq, f"{type(e).__name__}: {e}")
             self.runner.poison(wire, inp.group)
         rl = ResultLayout(lay.B, lay.k)
-        h = (seq, rl, self.plane.recv_result(inp.group, rl.nbytes))
+        h = (seq, rl, self.plane.recv_result(inp.group, rl.nbytes), inp.meta.num_seqs)
         self._outstanding.append(h)
         return h
 
@@ -499,7 +510,7 @@ class ChainPipeline:
             raise RuntimeError(f"stage {err[0]} failed (step {err[1]}): {err[2]}")
 
     def wait(self, handle) -> StepOutput:
-        seq, rl, pending = handle
+        seq, rl, pending, n_real = handle
         host = pending.get()
         try:
             self._outstanding.remove(handle)
@@ -509,13 +520,13 @@ class ChainPipeline:
         if self.plane.failed():
             self._dead = "P2P flag wait timed out: a pipeline stage is not responding"
             raise RuntimeError(self._dead)
-        return StepOutput(*parse_result(host, rl, seq))
+        return _step_output(parse_result(host, rl, seq), n_real)
 
     def reset(self):
         """Called by the engine after a failure, *before* it releases KV pages: wait for every step still in flight (their
         results are discarded — downstream stages may still be writing KV for them), then clear the error state."""
         while self._outstanding:
-            _, _, pending = self._outstanding.popleft()
+            _, _, pending, _ = self._outstanding.popleft()
             try:
                 pending.get()
             except Exception:  # noqa: BLE001

@@ -528,8 +528,11 @@ class APIHandler(BaseHTTPRequestHandler):
 
 # ------------------------------------------------------------------------------------------------ entry
 def make_server(host: str, port: int, model_provider: ModelProvider, static_dir: str) -> ThreadingHTTPServer:
-    ThreadingHTTPServer.daemon_threads = True
-    return ThreadingHTTPServer((host, port), lambda *a, **k: APIHandler(model_provider, static_dir, *a, **k))
+    class _Server(ThreadingHTTPServer):
+        daemon_threads = True
+        request_queue_size = 1024     # listen backlog: hundreds of clients may connect at once (the stdlib default is 5)
+
+    return _Server((host, port), lambda *a, **k: APIHandler(model_provider, static_dir, *a, **k))
 
 
 def run(host: str, port: int, model_provider: ModelProvider, static_dir: str):

@@ -33,9 +33,11 @@ def test_serving_chain_parity(arch, transport, port):
     assert "SERVING_OK" in out, out[-3000:]
 
 
-def test_expert_parallel_moe():
-    out = _torchrun("ep_parity.py", [], port=29574)
-    assert "EP_OK" in out, out[-3000:]
+@pytest.mark.parametrize("version,port", [("v2", 29574), ("v1", 29578)])
+def test_expert_parallel_moe(version, port):
+    """v2: sender-side slot reservation + arrival wait fused into the grouped GEMM; v1: regroup kernels on the receive side."""
+    out = _torchrun("ep_parity.py", [version], port=port)
+    assert "EP_OK " + version in out, out[-3000:]
 
 
 def test_expert_parallel_whole_model():
