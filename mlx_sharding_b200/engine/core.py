@@ -140,10 +140,13 @@ class LLMEngine:
         self._stop = threading.Event()
         self._wake = threading.Event()
         self.stats = dict(steps=0, prefill_tokens=0, decode_tokens=0, finished=0, prefix_cached_tokens=0)
+        self.sinks: list = []      # event sinks of the API worker processes (server/frontend.py): flushed once per scheduler iteration
 
     # -------------------------------------------------------------------------- public API
     def submit(self, prompt: Sequence[int], params: Optional[SamplingParams] = None, max_tokens: int = 100,
-               eos_token_id: Optional[int] = None, stop_id_sequences=None) -> Request:
+               eos_token_id: Optional[int] = None, stop_id_sequences=None, events=None) -> Request:
+        """``events``: optional replacement of the request's event queue (anything with ``put``) — the multi-process API front end
+        (server/frontend.py) passes a per-worker sink so a step's tokens leave the engine process as one message."""
         params = params or SamplingParams()
         params.validate()
         if len(prompt) == 0:
@@ -152,6 +155,9 @@ class LLMEngine:
             raise ValueError(f"prompt ({len(prompt)}) + max_tokens ({max_tokens}) exceeds max_model_len "
                              f"({self.max_model_len})")
         r = Request(prompt, params, max_tokens, eos_token_id, stop_id_sequences)
+        if events is not None:
+            r.events = events
+            events.req = r
         if r.max_tokens <= 0:
             # the reference's ``zip(generate_step(...), range(max_tokens))`` yields nothing (openai_api.py:370-381): no forward pass
             r.finished, r.finish_reason = True, "length"
@@ -200,6 +206,8 @@ class LLMEngine:
             r.events.put(None)
         if any(self.groups) or any(h is not None for h in self.inflight):
             self._fail_all(err)
+        for s in self.sinks:
+            s.flush()
 
     def busy(self) -> bool:
         return self.has_work()
@@ -234,6 +242,8 @@ class LLMEngine:
                 self.table.release(r.id)
                 r.events.put(None)
             self.groups[g] = []
+        for s in self.sinks:
+            s.flush()
 
     def _admit(self):
         while True:
@@ -373,7 +383,13 @@ class LLMEngine:
                 self.inflight[g] = (self.pipe.submit(inp), inp, seqs, q_lens)
                 self.stats["steps"] += 1
                 progressed = True
+        for s in self.sinks:
+            s.flush()
         return progressed
+
+    def metrics_snapshot(self):
+        """(engine counters, free KV pages) — what ``/metrics`` reports; also served to API worker processes."""
+        return dict(self.stats), self.table.alloc.num_free
 
     def drain(self):
         while self.has_work():

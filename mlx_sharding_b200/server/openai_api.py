@@ -304,8 +304,9 @@ class APIHandler(BaseHTTPRequestHandler):
             eng = self.model_provider.engine
             lines = [f"mlx_sharding_{k} {v}" for k, v in m.items()]
             if eng is not None:
-                lines += [f"mlx_sharding_engine_{k} {v}" for k, v in eng.stats.items()]
-                lines.append(f"mlx_sharding_kv_pages_free {eng.table.alloc.num_free}")
+                stats, free_pages = eng.metrics_snapshot()      # RPC to the engine process when this is an API worker
+                lines += [f"mlx_sharding_engine_{k} {v}" for k, v in stats.items()]
+                lines.append(f"mlx_sharding_kv_pages_free {free_pages}")
             data = ("\n".join(lines) + "\n").encode()
             self.send_response(200)
             self.send_header("Content-type", "text/plain; version=0.0.4")
@@ -527,25 +528,49 @@ class APIHandler(BaseHTTPRequestHandler):
 
 
 # ------------------------------------------------------------------------------------------------ entry
-def make_server(host: str, port: int, model_provider: ModelProvider, static_dir: str) -> ThreadingHTTPServer:
+def make_server(host: str, port: int, model_provider, static_dir: str, reuse_port: bool = False) -> ThreadingHTTPServer:
     class _Server(ThreadingHTTPServer):
         daemon_threads = True
         request_queue_size = 1024     # listen backlog: hundreds of clients may connect at once (the stdlib default is 5)
+        allow_reuse_port = reuse_port  # API worker processes all bind the port; the kernel spreads the connections (frontend.py)
 
     return _Server((host, port), lambda *a, **k: APIHandler(model_provider, static_dir, *a, **k))
 
 
-def run(host: str, port: int, model_provider: ModelProvider, static_dir: str):
-    httpd = make_server(host, port, model_provider, static_dir)
+def run(host: str, port: int, model_provider: ModelProvider, static_dir: str, api_workers: int = 0):
+    """Serve until interrupted.  ``api_workers > 0``: the HTTP / SSE / tokenizer work runs in that many worker processes and this
+    process keeps only the engine loop (server/frontend.py); 0: the reference's layout, HTTP threads next to the engine."""
     warnings.warn("this server implements only basic security checks; do not expose it to untrusted networks")
-    log.info("Starting httpd at %s on port %d...", host, port)
+    front = httpd = None
+    if api_workers > 0:
+        from .frontend import FrontEnd
+
+        a = model_provider.cli_args
+        if model_provider.engine is None:
+            raise SystemExit("--api-workers needs --model (the engine is built at start-up; per-request model loading is off)")
+        tok_cfg = {"trust_remote_code": True if getattr(a, "trust_remote_code", False) else None,
+                   "chat_template": getattr(a, "chat_template", "") or None,
+                   "use_default_chat_template": bool(getattr(a, "use_default_chat_template", False))}
+        front = FrontEnd(model_provider.engine, api_workers, host, port, static_dir, a.model, model_provider.model_key or "default_model",
+                         tok_cfg, getattr(a, "log_level", "INFO")).start()
+        log.info("%d API worker processes accepting on %s:%d", api_workers, host, port)
+    else:
+        httpd = make_server(host, port, model_provider, static_dir)
+        log.info("Starting httpd at %s on port %d...", host, port)
     print(f"A web-based UI is available at http://{host}:{port}")
     print("Press Ctrl+C to stop the server.")
     try:
-        httpd.serve_forever()
+        if httpd is not None:
+            httpd.serve_forever()
+        else:
+            while all(p.is_alive() for p in front.procs):
+                time.sleep(0.5)
+            log.error("an API worker exited; shutting down")
     except KeyboardInterrupt:
         pass
     finally:
+        if front is not None:
+            front.stop()
         if model_provider.engine is not None:
             model_provider.engine.shutdown()
 
@@ -581,6 +606,10 @@ def build_arg_parser() -> argparse.ArgumentParser:
     p.add_argument("--prefix-cache", action="store_true",
                    help="automatic prefix caching: full KV pages of prompt prefixes are shared between requests (chat system "
                         "prompts are prefilled once); not available with gRPC reference shards")
+    p.add_argument("--api-workers", type=int, default=0,
+                   help="run the HTTP / SSE / tokenizer front end in this many worker processes (SO_REUSEPORT on --port) and keep only "
+                        "the engine loop in this process — needed to stream to hundreds of clients at GPU speed; 0 = in-process "
+                        "HTTP threads like the reference")
     p.add_argument("--mixed-batches", action="store_true",
                    help="scheduler: prefill chunks and the decode tokens of running sequences share one ragged step, so streams in "
                         "flight keep their inter-token latency while new prompts are prefilled")
@@ -647,7 +676,7 @@ def main(argv=None):
     if args.static_dir is None:
         args.static_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "static")
     provider = ModelProvider(args, stubs)
-    run(args.host, args.port, provider, args.static_dir)
+    run(args.host, args.port, provider, args.static_dir, api_workers=args.api_workers)
 
 
 if __name__ == "__main__":

@@ -19,6 +19,8 @@ int main() {
     {"shared_down 64x2048x2816", 64, 2048, 2816, false, true},
     {"llama_qkv   64x6144x4096", 64, 6144, 4096, false, false},
     {"llama_o     64x4096x4096", 64, 4096, 4096, false, true},
+    {"o_abs       64x2048x8192", 64, 2048, 8192, false, true},
+    {"qkv_abs     64x9792x2048", 64, 9792, 2048, false, false},
     {"o_proj m8    8x2048x2048", 8, 2048, 2048, false, true},
     {"o_proj m256 256x2048x2048", 256, 2048, 2048, false, true},
   };

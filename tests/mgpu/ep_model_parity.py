@@ -30,8 +30,9 @@ if __name__ == "__main__":
     def decode(model, use_loop):
         stage = StageExecutor(model, B * pages_per_seq + 1, PS)
         meta = BatchMeta.build([S] * B, [0] * B, bts, PS, device=dev)
-        toks = stage.forward(prompts.reshape(-1).to(dev), meta).argmax(-1)
-        hist = [toks.clone()]
+        logits = stage.forward(prompts.reshape(-1).to(dev), meta)
+        toks = logits.argmax(-1)
+        hist, lg = [toks.clone()], [logits.float().clone()]
         if use_loop:
             loop = DecodeLoop(stage, 1, B, pages_per_seq, transport="local", standalone=True)
             loop.groups[0].load(torch.full((B,), S, dtype=torch.int32), torch.tensor(bts, dtype=torch.int32), toks, S + steps + 4)
@@ -43,20 +44,36 @@ if __name__ == "__main__":
         else:
             for s in range(steps):
                 meta = BatchMeta.build([1] * B, [S + s] * B, bts, PS, device=dev)
-                toks = stage.forward(toks, meta).argmax(-1)
+                logits = stage.forward(toks, meta)
+                toks = logits.argmax(-1)
                 hist.append(toks.clone())
-        return torch.stack(hist)
+                lg.append(logits.float().clone())
+        return torch.stack(hist), (torch.stack(lg) if not use_loop else None)
 
     model = random_model(GPU_DSV2, device=dev, backend="b200", seed=3)
-    ref = decode(model, False)
+    ref, ref_logits = decode(model, False)
     bufs = enable_expert_parallel(model, max_tokens=B * S)
     assert all(w.get("e_gate") is None for w in model.layer_weights.values() if "router" in w)
-    got = decode(model, True)
+    got, _ = decode(model, True)
+    # Greedy decoding amplifies a single near-tie into a diverged suffix, and the two paths round differently (the un-sharded model
+    # runs the shared experts inside the routed bank with a bf16 combine, the EP path adds them as an fp32 residual).  So: a
+    # sequence may diverge only at a step where the reference's own margin between the two candidate tokens is within rounding
+    # noise (5 % of the logit row's spread), and at most 2 of the 16 sequences may do so.
+    diverged, worst = 0, 0.0
+    for b in range(B):
+        neq = (ref[:, b] != got[:, b]).nonzero()
+        if neq.numel() == 0:
+            continue
+        s0 = int(neq[0])
+        row = ref_logits[s0, b]
+        margin = float((row[ref[s0, b]] - row[got[s0, b]]) / row.std())
+        diverged, worst = diverged + 1, max(worst, margin)
     bad = int((ref != got).sum().item())
-    ok = torch.tensor([1.0 if (bad <= 1 and not bufs.error()) else 0.0], device=dev)
+    ok = torch.tensor([1.0 if (diverged <= 2 and worst < 0.05 and not bufs.error()) else 0.0], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"mismatching tokens on rank 0: {bad} of {ref.numel()}")
+        print(f"mismatching tokens on rank 0: {bad} of {ref.numel()} (per step: {(ref != got).sum(1).tolist()}); "
+              f"{diverged} sequence(s) diverged, worst reference margin at the divergence {worst:.4f} of the logit spread")
         if ok.item() == 1.0:
             print("EP_MODEL_OK")
     dist.barrier()

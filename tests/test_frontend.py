@@ -1,0 +1,117 @@
+"""Multi-process API front end (server/frontend.py): HTTP / SSE / tokenizer in worker processes, engine loop in this one.
+The responses must equal the in-process server's for the same greedy requests; errors, cancellation and /metrics cross the
+process boundary."""
+import http.client
+import json
+import os
+import socket
+import threading
+import time
+
+import pytest
+import torch
+
+from helpers import TINY_LLAMA
+from mlx_sharding_b200.server import openai_api
+from mlx_sharding_b200.server.frontend import FrontEnd
+from mlx_sharding_b200.utils.checkpoint import write_synthetic_checkpoint
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.fixture(scope="module")
+def servers(tmp_path_factory):
+    d = tmp_path_factory.mktemp("ckpt")
+    path = write_synthetic_checkpoint(str(d / "tiny"), TINY_LLAMA, dtype=torch.float32)
+    cwd = os.getcwd()
+    os.chdir(d)
+    args = openai_api.build_arg_parser().parse_args(["--model", path, "--port", "0", "--kv-pages", "128", "--page-size", "16"])
+    args.static_dir = os.path.join(os.path.dirname(openai_api.__file__), "static")
+    provider = openai_api.ModelProvider(args, [])
+    httpd = openai_api.make_server("127.0.0.1", 0, provider, args.static_dir)          # in-process server: the oracle
+    threading.Thread(target=httpd.serve_forever, daemon=True).start()
+    port = _free_port()
+    front = FrontEnd(provider.engine, 2, "127.0.0.1", port, args.static_dir, path, "default_model", {}, "WARNING").start()
+    yield port, httpd.server_address[1], provider
+    front.stop()
+    httpd.shutdown()
+    provider.engine.shutdown()
+    os.chdir(cwd)
+
+
+def _post(port, path, body, raw=False):
+    c = http.client.HTTPConnection("127.0.0.1", port, timeout=120)
+    c.request("POST", path, json.dumps(body), {"Content-Type": "application/json"})
+    r = c.getresponse()
+    data = r.read()
+    c.close()
+    return r, (data if raw else json.loads(data))
+
+
+def test_completion_matches_in_process_server(servers):
+    wport, iport, _ = servers
+    body = {"prompt": "hello world", "max_tokens": 9, "temperature": 0, "logprobs": 3}
+    rw, jw = _post(wport, "/v1/completions", body)
+    ri, ji = _post(iport, "/v1/completions", body)
+    assert rw.status == ri.status == 200
+    assert jw["choices"][0]["logprobs"]["tokens"] == ji["choices"][0]["logprobs"]["tokens"]
+    assert jw["choices"][0]["text"] == ji["choices"][0]["text"] and jw["usage"] == ji["usage"]
+    assert jw["choices"][0]["logprobs"]["top_logprobs"] == ji["choices"][0]["logprobs"]["top_logprobs"]
+
+
+def test_streams_from_many_clients(servers):
+    wport, iport, _ = servers
+    n = 12
+    out = [None] * n
+
+    def one(i):
+        body = {"messages": [{"role": "user", "content": f"request {i}"}], "max_tokens": 6 + i % 3, "temperature": 0, "stream": True}
+        r, raw = _post(wport, "/v1/chat/completions", body, raw=True)
+        ev = [l[6:] for l in raw.decode().split("\n\n") if l.startswith("data: ")]
+        text = "".join(json.loads(e)["choices"][0]["delta"]["content"] for e in ev[:-1])
+        _, j = _post(iport, "/v1/chat/completions", dict(body, stream=False))
+        out[i] = (r.status, ev[-1], text, j["choices"][0]["message"]["content"], json.loads(ev[-2])["choices"][0]["finish_reason"])
+
+    th = [threading.Thread(target=one, args=(i,)) for i in range(n)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for status, last, text, want, reason in out:
+        assert status == 200 and last == "[DONE]" and text == want and reason in ("length", "stop")
+
+
+def test_errors_and_zero_tokens_cross_the_process_boundary(servers):
+    wport, _, _ = servers
+    r, j = _post(wport, "/v1/completions", {"prompt": "x" * 5000, "max_tokens": 100000})      # engine-side validation -> 400
+    assert r.status == 400 and "max_model_len" in j["error"]["message"]
+    r, j = _post(wport, "/v1/completions", {"prompt": "abc", "max_tokens": 0})
+    assert r.status == 200 and j["choices"][0]["text"] == "" and j["usage"]["completion_tokens"] == 0
+    r, j = _post(wport, "/v1/completions", {"prompt": "abc", "max_tokens": 2, "model": "some/other"})   # no hot-swap from a worker
+    assert r.status == 400 and "cannot be switched" in j["error"]["message"]
+    r, j = _post(wport, "/v1/completions", {"prompt": "abc", "temperature": -1})
+    assert r.status == 400
+
+
+def test_metrics_and_client_disconnect(servers):
+    wport, _, provider = servers
+    c = http.client.HTTPConnection("127.0.0.1", wport, timeout=30)
+    c.request("GET", "/metrics")
+    text = c.getresponse().read().decode()
+    assert "mlx_sharding_engine_steps" in text and "mlx_sharding_kv_pages_free" in text
+    free0 = provider.engine.table.alloc.num_free
+    # a client that walks away mid-stream: the worker cancels the request in the engine process, pages come back
+    s = socket.create_connection(("127.0.0.1", wport))
+    body = json.dumps({"prompt": "abc", "max_tokens": 400, "temperature": 0, "stream": True}).encode()
+    s.sendall(b"POST /v1/completions HTTP/1.1\r\nHost: x\r\nContent-Type: application/json\r\nContent-Length: %d\r\n\r\n" % len(body) + body)
+    s.recv(200)
+    s.close()
+    for _ in range(300):
+        if not provider.engine.busy() and provider.engine.table.alloc.num_free == free0:
+            break
+        time.sleep(0.05)
+    assert not provider.engine.busy() and provider.engine.table.alloc.num_free == free0

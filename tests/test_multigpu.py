@@ -40,6 +40,14 @@ def test_expert_parallel_moe(version, port):
     assert "EP_OK " + version in out, out[-3000:]
 
 
+@pytest.mark.parametrize("version,port", [("v2", 29584), ("v1", 29585)])
+def test_expert_parallel_stress(version, port):
+    """Several EP layers sharing one buffer set, called back to back with no host synchronisation, token counts changing from step
+    to step (prefill chunk <-> decode batch), two geometries; every output must equal the local MoE bit for bit."""
+    out = _torchrun("ep_stress.py", [version], port=port)
+    assert "EP_STRESS_OK " + version in out, out[-3000:]
+
+
 def test_expert_parallel_whole_model():
     """Data-parallel attention + expert-parallel MoE for every layer, graph-captured decode loop (bench.py --parallelism ep)."""
     out = _torchrun("ep_model_parity.py", [], port=29576)
