@@ -149,7 +149,25 @@ def main():
     warm2 = round_(a.max_tokens)        # second warm-up at the measured length: every decode bucket / context bucket is captured
     eng = provider.engine
     st0 = dict(eng.stats)
+    # sample the engine's token counter during the measured round: the steady-state rate is the slope over the middle half of the
+    # tokens (a burst of --concurrency simultaneous connections spends its first part in connection set-up, chat templating and
+    # prefill, its last part draining stragglers — neither is the decode rate the device-side bench reports)
+    samples, stop_mon = [], threading.Event()
+
+    def monitor():
+        while not stop_mon.is_set():
+            samples.append((time.perf_counter(), eng.stats["decode_tokens"]))
+            time.sleep(0.02)
+
+    mon = threading.Thread(target=monitor, daemon=True)
+    mon.start()
     res = round_(a.max_tokens)
+    stop_mon.set()
+    mon.join()
+    total = eng.stats["decode_tokens"] - st0["decode_tokens"]
+    lo = next((s_ for s_ in samples if s_[1] - st0["decode_tokens"] >= 0.25 * total), None)
+    hi = next((s_ for s_ in samples if s_[1] - st0["decode_tokens"] >= 0.75 * total), None)
+    steady = round((hi[1] - lo[1]) / (hi[0] - lo[0]), 1) if lo and hi and hi[0] > lo[0] else None
     pipe = eng.pipe
     gc = getattr(pipe, "gcache", None)
     out = {"bench": "HTTP /v1/chat/completions, streaming, " + ("temperature 0" if a.greedy else "API default sampling (temperature 1.0)"),
@@ -158,6 +176,8 @@ def main():
            "control": type(getattr(pipe, "ctl", None)).__name__ if hasattr(pipe, "ctl") else None,
            "warmup_round": warm, "warmup_round_2": warm2, "measured_round": res,
            "engine_decode_tokens": eng.stats["decode_tokens"] - st0["decode_tokens"], "engine_steps": eng.stats["steps"] - st0["steps"],
+           "steady_decode_tokens_per_s": steady,
+           "steady_note": "slope of the engine's decode-token counter between 25 % and 75 % of the round's tokens (all streams active)",
            "tokens_per_s": round((eng.stats["decode_tokens"] - st0["decode_tokens"] + res["ok"]) / res["wall_s"], 1),
            "graph_replays_stage0": gc.replays if gc is not None else None, "graph_captures_stage0": gc.captures if gc is not None else None}
     print(json.dumps(out), flush=True)

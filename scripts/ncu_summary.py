@@ -28,9 +28,13 @@ def short(name):
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
-    if len(sys.argv) > 3:
+    if rep.endswith(".csv"):      # already exported with `ncu -i x.ncu-rep --page raw --csv`
+        raw = open(rep, errors="replace").read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if len(sys.argv) > 3 and not sys.argv[3].startswith("--"):
         open(sys.argv[3], "w").write(raw)
+    title = next((a.split("=", 1)[1] for a in sys.argv[3:] if a.startswith("--title=")), None)
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     iname = hdr.index("Kernel Name")
@@ -38,11 +42,15 @@ def main():
     for r in data:
         n = short(r[iname])
         seen.setdefault(n, []).append(r)
-    md = [f"# ncu --set full: every kernel launched by `__graft_entry__.smoke()` ({len(data)} launches, {len(seen)} distinct kernels)", "",
+    hdr_lines = [f"# ncu --set full: every kernel launched by `__graft_entry__.smoke()` ({len(data)} launches, {len(seen)} distinct kernels)", "",
           "`ncu --set full --clock-control none --import-source on -c 200` under `gpurun` (1 GPU) over the smoke decode of the tiny DeepSeek-V2 flagship",
           "(prefill + graph-free decode steps through `LLMEngine`).  One row per distinct kernel = its first captured launch; the tiny model makes every",
           "kernel latency-bound, so read this table as *coverage* (each hand-written kernel ran on the B200 and was captured with source) — the",
-          "roofline-relevant captures are `ncu_decode_kernels.md` and `ncu_gemm_persistent.md`.  Durations under ncu are not benchmark numbers.", "",
+          "roofline-relevant captures are `ncu_decode_kernels.md` and `ncu_gemm_persistent.md`.  Durations under ncu are not benchmark numbers.", ""]
+    if title is not None:
+        hdr_lines = [f"# {title} ({len(data)} launches, {len(seen)} distinct kernels)", "",
+                     "One row per distinct kernel = its first captured launch.  Durations under ncu are not benchmark numbers.", ""]
+    md = hdr_lines + [
           "| kernel | launches | " + " | ".join(c[1] for c in COLS) + " |", "|---|---:|" + "---:|" * len(COLS)]
     for n, rs in seen.items():
         r = rs[0]
