@@ -156,11 +156,21 @@ class DeepseekV2Stage(StageModel):
         nh, nope, rd, vd, lr = (c.num_attention_heads, c.qk_nope_head_dim, c.qk_rope_head_dim,
                                 c.v_head_dim, c.kv_lora_rank)
         qd = nope + rd
-        normed = O.rmsnorm(h, w["in_ln"], c.rms_norm_eps)
+        pn, self._prenormed = getattr(self, "_prenormed", None), None
+        # the previous layer's MoE combine may already have produced this layer's input norm (ops/b200.py::moe_block, next_norm)
+        normed = pn[1] if (pn is not None and pn[0] is h) else O.rmsnorm(h, w["in_ln"], c.rms_norm_eps)
         if "qkv_abs" in w and meta.max_q_len == 1 and meta.num_tokens == meta.num_seqs and kpool.shape[2] == 64:
             # decode step on the absorbed weights: one GEMM -> [q_abs | q_pe] x 16 heads, c_kv, k_pe; fused prologue (latent norm,
             # both ropes, cache append); tcgen05 multi-query attention over the cached latent; folded output projection
             qkv = O.linear(normed, w["qkv_abs"])
+            if self.backend_name == "b200" and "router" in w and w.get("e_gate") is not None and not w["e_gate"].is_quantized \
+                    and not O.fp8_experts_enabled(w["e_gate"]):
+                nb = O.l2_prefetch_bytes()
+                if nb > 0 and T <= 128:
+                    # forked AFTER the q/kv projection (the chain's bandwidth-hungry kernel): HBM mostly idles from here to the
+                    # expert GEMMs.  Pull the first experts of this layer's gate / up banks into L2 on the side stream (the grouped
+                    # GEMM walks the experts in order, so these are the tiles of its first waves)
+                    O.prefetch_aside([O._dense(w["e_gate"]), O._dense(w["e_up"])], nb)
             qa = qkv[:, : nh * (lr + rd)].unflatten(1, (nh, lr + rd))
             O.mla_absorbed_prologue(qa, qkv[:, nh * (lr + rd): nh * (lr + rd) + lr], qkv[:, nh * (lr + rd) + lr:], w["kv_a_ln"],
                                     c.rms_norm_eps, kpool, meta, self.rope)
@@ -322,6 +332,24 @@ class DeepseekV2Stage(StageModel):
     def mlp_block(self, i, h, meta: BatchMeta):
         O, c, w = self.ops, self.cfg, self.layer_weights[i]
         T = h.shape[0]
+        ep = getattr(self, "ep_layers", None)
+        if "router" in w and "s_gate" not in w and hasattr(O, "moe_block") and not (ep is not None and i in ep):
+            # CUDA backend, whole bank local, shared experts riding in the bank: the block is router -> grouped gate-up -> grouped
+            # down -> combine, with BOTH RMSNorms around it folded in — the pre-MoE norm into the router kernel and the next layer's
+            # input norm into the combine (decode batches; ops/b200.py::moe_block falls back to separate norm kernels otherwise)
+            extra = dict(extra=w["n_fused_shared"]) if "n_fused_shared" in w else {}
+            fk = self._final_kwargs(i, T, "mlp")
+            nxt = self.layer_weights.get(i + 1) if not fk else None
+            nn = dict(next_norm=(nxt["in_ln"], c.rms_norm_eps)) if (nxt is not None and "in_ln" in nxt and self.spec.runs_attn(i + 1)) else {}
+            res = O.moe_block(h, w["router"], dict(top_k=c.num_experts_per_tok, method=c.topk_method, n_group=c.n_group or 1,
+                                                   topk_group=c.topk_group or 1, scaling=c.routed_scaling_factor,
+                                                   norm_topk=c.norm_topk_prob),
+                              w["e_gate"], w["e_up"], w["e_down"], "silu", residual=h, pre_norm=(w["post_ln"], c.rms_norm_eps),
+                              **extra, **nn, **fk)
+            if nn:
+                self._prenormed = res
+                return res[0]
+            return res
         normed = O.rmsnorm(h, w["post_ln"], c.rms_norm_eps)
         if "router" in w:
             join = None

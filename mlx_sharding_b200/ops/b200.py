@@ -227,6 +227,47 @@ def run_aside(fn) -> _Join:
     return _Join(done)
 
 
+_aside_last = {}
+
+
+def prefetch_aside(tensors, nbytes_each: int):
+    """Start pulling the first ``nbytes_each`` bytes of every tensor into L2 on the side stream (forked from the current stream at
+    this point, NOT joined here: nothing depends on a prefetch — :func:`join_aside` ties the side stream back once per forward so
+    a graph capture ends with all its branches joined).  The main stream's kernel chain keeps its programmatic (PDL) edges."""
+    cur = torch.cuda.current_stream()
+    dev = cur.device.index
+    side = _side_streams.get(dev)
+    if side is None:
+        side = _side_streams[dev] = torch.cuda.Stream(device=cur.device)
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    side.wait_event(fork)
+    with torch.cuda.stream(side):
+        for t in tensors:
+            C().l2_prefetch(t, 0, min(int(nbytes_each), t.numel() * t.element_size()) // 16 * 16)
+        done = torch.cuda.Event()
+        done.record(side)
+    _aside_last[dev] = done
+
+
+def join_aside():
+    """Join the side stream's outstanding prefetches into the current stream (end of a forward pass)."""
+    cur = torch.cuda.current_stream()
+    ev = _aside_last.pop(cur.device.index, None)
+    if ev is not None:
+        cur.wait_event(ev)
+        C().pdl_skip_next()
+
+
+def l2_prefetch_bytes() -> int:
+    """Bytes of the next MoE block's gate / up banks (each) to prefetch into L2 during a decode layer's attention chain
+    (``MLXB200_L2_PREFETCH_MB``, total across both banks; 0 = off)."""
+    try:
+        return int(float(os.environ.get("MLXB200_L2_PREFETCH_MB", "0")) * (1 << 20)) // 2
+    except ValueError:
+        return 0
+
+
 def moe_experts(x, idx, w, Wg: LinearWeight, Wu: LinearWeight, Wd: LinearWeight, act: str = "silu",
                 extra: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
                 out: Optional[torch.Tensor] = None, signal: Optional[Tuple[int, int]] = None, join: Optional[_Join] = None):
@@ -308,8 +349,15 @@ SCATTER_MAX_TOKENS = 128
 
 def moe_block(x, gate_w, route_kw: dict, Wg: LinearWeight, Wu: LinearWeight, Wd: LinearWeight, act: str = "silu",
               residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, signal: Optional[Tuple[int, int]] = None,
-              extra: int = 0):
-    """Router + routed (and appended shared) experts of one MoE block.  Decode-sized batches with bf16 banks take the *scatter*
+              extra: int = 0, pre_norm: Optional[Tuple[torch.Tensor, float]] = None,
+              next_norm: Optional[Tuple[torch.Tensor, float]] = None):
+    """Router + routed (and appended shared) experts of one MoE block.
+
+    ``pre_norm = (weight, eps)``: ``x`` is the un-normalised residual stream and the block starts with ``rmsnorm(x) * weight`` — on
+    the scatter path the router kernel normalises the row in shared memory (no norm kernel).  ``next_norm = (weight, eps)``: the
+    block also returns ``rmsnorm(result) * weight`` (the next layer's input norm), fused into the combine kernel on the scatter
+    path; the return value is then ``(result, normed)``.
+  Decode-sized batches with bf16 banks take the *scatter*
     path: the router kernel claims a slot per (token, expert) pair in the expert's fixed-stride segment and copies the token row
     there itself, the grouped GEMMs read per-expert row counts — route / counting sort / gather are ONE launch, the block is
     router -> grouped gate-up -> grouped down -> combine.  Larger batches (prefill) keep the compact counting-sort permutation."""
@@ -318,8 +366,14 @@ def moe_block(x, gate_w, route_kw: dict, Wg: LinearWeight, Wu: LinearWeight, Wd:
     fp8 = fp8_experts_enabled(Wg) and x.shape[1] % 128 == 0
     quant = (Wg.is_quantized or Wu.is_quantized or Wd.is_quantized) and not fp8
     if quant or T > SCATTER_MAX_TOKENS or os.environ.get("MLXB200_MOE_SCATTER", "1") == "0":
+        if pre_norm is not None:
+            x = rmsnorm(x, pre_norm[0], pre_norm[1])
         idx, wts = moe_route(x, gate_w, extra=extra, **route_kw)
-        return moe_experts(x, idx, wts, Wg, Wu, Wd, act, residual=residual, out=out, signal=signal)
+        res = moe_experts(x, idx, wts, Wg, Wu, Wd, act, residual=residual, out=out, signal=signal)
+        return res if next_norm is None else (res, rmsnorm(res, next_norm[0], next_norm[1]))
+    fuse_norms = os.environ.get("MLXB200_FUSE_NORMS", "1") != "0"
+    if pre_norm is not None and not fuse_norms:
+        x, pre_norm = rmsnorm(x, pre_norm[0], pre_norm[1]), None
     if fp8:
         (gq, gs), (uq, us), (dq, ds) = _fp8pack(Wg), _fp8pack(Wu), _fp8pack(Wd)
         E, H = gq.shape[0], x.shape[1]
@@ -338,8 +392,9 @@ def moe_block(x, gate_w, route_kw: dict, Wg: LinearWeight, Wu: LinearWeight, Wd:
     method = rk.pop("method", "greedy")
     if method != "group_limited_greedy":
         rk["n_group"], rk["topk_group"] = 1, 1
+    nw, ne = (_bf16(pre_norm[0]), float(pre_norm[1])) if pre_norm is not None else (None, 1e-6)
     idx, wts, pair_row = c.moe_route(x, _bf16(gate_w), int(rk["top_k"]), int(rk["n_group"]), int(rk["topk_group"]), float(rk["scaling"]),
-                                     bool(rk["norm_topk"]), int(extra), counts, stride, xs)
+                                     bool(rk["norm_topk"]), int(extra), counts, stride, xs, nw, ne)
     k = idx.shape[1]
     if fp8:
         # block-scaled FP8 experts: activations are quantised per 32-wide K block right before each GEMM (garbage rows beyond an
@@ -352,7 +407,12 @@ def moe_block(x, gate_w, route_kw: dict, Wg: LinearWeight, Wu: LinearWeight, Wd:
         h = c.grouped_linear(xs, wg, wu, counts, stride, ACT_IDS[act], False, None, None, None, T * k, stride)
         y = c.grouped_linear(h, wd, None, counts, stride, 0, True, None, None, None, T * k, stride)
     flag, val = signal if signal is not None else (0, 0)
-    return c.moe_combine(y, pair_row, wts, residual, out, int(k), int(flag), int(val), counts)
+    if next_norm is not None and signal is None and fuse_norms and H <= 8192:
+        normed = torch.empty(T, H, dtype=torch.bfloat16, device=x.device)
+        res = c.moe_combine(y, pair_row, wts, residual, out, int(k), 0, 0, counts, _bf16(next_norm[0]), float(next_norm[1]), normed)
+        return res, normed
+    res = c.moe_combine(y, pair_row, wts, residual, out, int(k), int(flag), int(val), counts)
+    return res if next_norm is None else (res, rmsnorm(res, next_norm[0], next_norm[1]))
 
 
 def softcap_(logits, cap: float):

@@ -286,6 +286,12 @@ void rope_(Tensor x, const Tensor& positions, const Tensor& inv_freq, int64_t ro
                             (int)rot_off, (int)rot_dim, interleaved, (float)mscale, (int)x.size(0), cur_stream()));
 }
 
+void l2_prefetch(const Tensor& t, int64_t offset_bytes, int64_t nbytes) {
+  TORCH_CHECK(t.is_cuda() && t.is_contiguous() && offset_bytes >= 0 && nbytes >= 0 && offset_bytes + nbytes <= (int64_t)t.nbytes(), "bad prefetch range");
+  const c10::cuda::CUDAGuard guard(t.device());
+  LAUNCH_OK(b200::l2_prefetch_launch(static_cast<const char*>(t.data_ptr()) + offset_bytes, (unsigned long long)nbytes, cur_stream()));
+}
+
 Tensor embed(const Tensor& ids, const Tensor& table, const c10::optional<Tensor>& scales, const c10::optional<Tensor>& biases,
              int64_t bits, int64_t group, double scale) {
   TORCH_CHECK(ids.is_cuda() && ids.scalar_type() == torch::kInt64 && ids.is_contiguous(), "ids must be contiguous int64 CUDA");
@@ -484,9 +490,10 @@ Tensor mla_decode(const Tensor& q, const Tensor& pool, const Tensor& block_table
 // ---- MoE --------------------------------------------------------------------------------------------------------
 std::vector<Tensor> moe_route(const Tensor& x, const Tensor& gate_w, int64_t top_k, int64_t n_group, int64_t topk_group, double scaling,
                               bool norm_topk, int64_t extra, const c10::optional<Tensor>& sc_counts, int64_t sc_stride,
-                              const c10::optional<Tensor>& sc_x) {
+                              const c10::optional<Tensor>& sc_x, const c10::optional<Tensor>& norm_w, double norm_eps) {
   check_bf16(x, "x"); check_bf16(gate_w, "gate_w"); check_rows(x, "x");
   TORCH_CHECK(gate_w.is_contiguous());
+  if (norm_w.has_value()) { check_bf16(*norm_w, "norm_w"); TORCH_CHECK(norm_w->is_contiguous() && norm_w->numel() == x.size(1), "bad norm weight"); }
   const c10::cuda::CUDAGuard guard(x.device());
   const int T = (int)x.size(0);
   Tensor idx = torch::empty({T, top_k + extra}, torch::dtype(torch::kInt32).device(x.device()));
@@ -502,7 +509,8 @@ std::vector<Tensor> moe_route(const Tensor& x, const Tensor& gate_w, int64_t top
   LAUNCH_OK(b200::moe_route_launch(x.data_ptr(), x.stride(0), gate_w.data_ptr(), T, (int)x.size(1), (int)gate_w.size(0), (int)top_k,
                                  (int)n_group, (int)topk_group, (float)scaling, norm_topk, (int)extra, idx.data_ptr<int>(), w.data_ptr<float>(),
                                  scatter ? sc_counts->data_ptr<int>() : nullptr, (int)sc_stride, scatter ? pair_row.data_ptr<int>() : nullptr,
-                                 scatter ? sc_x->data_ptr() : nullptr, cur_stream()));
+                                 scatter ? sc_x->data_ptr() : nullptr, norm_w.has_value() ? norm_w->data_ptr() : nullptr, (float)norm_eps,
+                                 cur_stream()));
   if (scatter) return {idx, w, pair_row};
   return {idx, w};
 }
@@ -523,7 +531,8 @@ std::vector<Tensor> moe_permute(const Tensor& idx, const Tensor& x, int64_t E) {
 
 Tensor moe_combine(const Tensor& y_perm, const Tensor& pair_row, const Tensor& wts, const c10::optional<Tensor>& residual,
                    const c10::optional<Tensor>& out_, int64_t top_k, int64_t signal_flag_ptr, int64_t signal_value,
-                   const c10::optional<Tensor>& zero_counts) {
+                   const c10::optional<Tensor>& zero_counts, const c10::optional<Tensor>& norm_w, double norm_eps,
+                   const c10::optional<Tensor>& normed) {
   TORCH_CHECK(y_perm.is_cuda() && y_perm.scalar_type() == torch::kFloat32 && y_perm.is_contiguous());
   TORCH_CHECK(!zero_counts.has_value() || zero_counts->scalar_type() == torch::kInt32);
   TORCH_CHECK(wts.scalar_type() == torch::kFloat32 && wts.is_contiguous() && pair_row.scalar_type() == torch::kInt32);
@@ -533,12 +542,19 @@ Tensor moe_combine(const Tensor& y_perm, const Tensor& pair_row, const Tensor& w
   TORCH_CHECK(out.scalar_type() == torch::kBFloat16 && out.stride(1) == 1);
   const void* res = nullptr; long long ldr = 0;
   if (residual.has_value()) { check_bf16(*residual, "residual"); check_rows(*residual, "residual"); res = residual->data_ptr(); ldr = residual->stride(0); }
+  if (norm_w.has_value()) {
+    check_bf16(*norm_w, "norm_w");
+    TORCH_CHECK(normed.has_value() && normed->scalar_type() == torch::kBFloat16 && normed->stride(1) == 1 && normed->size(0) >= T &&
+                normed->size(1) == H && norm_w->is_contiguous() && norm_w->numel() == H, "bad fused-norm arguments");
+  }
   unsigned int* done = nullptr;
   if (signal_flag_ptr != 0) done = reinterpret_cast<unsigned int*>(scratch().get_counters(y_perm.device()).data_ptr<int>()) + 65534;
   LAUNCH_OK(b200::moe_combine_launch(y_perm.data_ptr(), pair_row.data_ptr<int>(), wts.data_ptr<float>(), res, ldr, out.data_ptr(),
                                    out.stride(0), T, (int)top_k, H, reinterpret_cast<uint32_t*>(signal_flag_ptr), (uint32_t)signal_value,
                                    done, zero_counts.has_value() ? zero_counts->data_ptr<int>() : nullptr,
-                                   zero_counts.has_value() ? (int)zero_counts->numel() : 0, cur_stream()));
+                                   zero_counts.has_value() ? (int)zero_counts->numel() : 0,
+                                   norm_w.has_value() ? norm_w->data_ptr() : nullptr, (float)norm_eps,
+                                   normed.has_value() ? normed->data_ptr() : nullptr, normed.has_value() ? normed->stride(0) : 0, cur_stream()));
   return out;
 }
 
@@ -744,6 +760,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_q_supported", &gemm_q_supported);
   m.def("rmsnorm", &rmsnorm, py::arg("x"), py::arg("w"), py::arg("eps"), py::arg("gemma") = false, py::arg("residual") = py::none());
   m.def("rope_", &rope_);
+  m.def("l2_prefetch", &l2_prefetch, py::arg("t"), py::arg("offset_bytes"), py::arg("nbytes"));
   m.def("embed", &embed, py::arg("ids"), py::arg("table"), py::arg("scales") = py::none(), py::arg("biases") = py::none(),
         py::arg("bits") = 0, py::arg("group") = 64, py::arg("scale") = 1.0);
   m.def("kv_write", &kv_write);
@@ -761,11 +778,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("act") = 0, py::arg("out_fp32") = false, py::arg("expected_rows") = 0, py::arg("expert_stride") = 0);
   m.def("moe_route", &moe_route, py::arg("x"), py::arg("gate_w"), py::arg("top_k"), py::arg("n_group"), py::arg("topk_group"),
         py::arg("scaling"), py::arg("norm_topk"), py::arg("extra") = 0, py::arg("sc_counts") = py::none(), py::arg("sc_stride") = 0,
-        py::arg("sc_x") = py::none());
+        py::arg("sc_x") = py::none(), py::arg("norm_w") = py::none(), py::arg("norm_eps") = 1e-6);
   m.def("moe_permute", &moe_permute);
   m.def("moe_combine", &moe_combine, py::arg("y_perm"), py::arg("pair_row"), py::arg("wts"), py::arg("residual") = py::none(),
         py::arg("out") = py::none(), py::arg("top_k"), py::arg("signal_flag_ptr") = 0, py::arg("signal_value") = 0,
-        py::arg("zero_counts") = py::none());
+        py::arg("zero_counts") = py::none(), py::arg("norm_w") = py::none(), py::arg("norm_eps") = 1e-6, py::arg("normed") = py::none());
   m.def("apply_penalties_", &apply_penalties_);
   m.def("sample", &sample);
   m.def("sample_into", &sample_into, py::arg("logits"), py::arg("temperature"), py::arg("top_p"), py::arg("row_rng"), py::arg("top_k"),

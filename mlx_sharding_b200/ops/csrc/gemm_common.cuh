@@ -97,97 +97,54 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint8_t* smem,
       if (do_epilogue) __threadfence();
     }
 
-    if (do_epilogue && p.splits > 1) {
-      // ---- split-K finish by the last-arriving CTA.  The partials are [token][128 features] fp32, so a warp reads one token row of
-      // one split as 32 x float4 (512 contiguous bytes) and already holds 4 *adjacent features of one token*: bias, activation,
-      // residual and the coalesced 8 B store happen straight from registers — no shared-memory transpose, no extra barrier.  The
-      // reduction is L2-latency bound, so every round keeps kTok tokens x up to 4 splits of independent 16 B loads in flight
-      // (16 per thread); splits are always summed in ascending order (deterministic, batch-invariant).
-      constexpr int kTok = DUAL ? 2 : 4;
-      constexpr size_t kPart = static_cast<size_t>(BN) * (DUAL ? 2 : 1) * kTileM;       // floats per split partial
-      const int wq = et >> 5;
-      const int f0 = n0 + 4 * lane;
-      const float* ws0 = p.workspace + static_cast<size_t>((blockIdx.y * gridDim.x + blockIdx.x) * (gridDim.z / p.splits) + mt) *
-                                           p.splits * kPart + 4 * lane;
-      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.bias != nullptr && f0 < p.n) {
-        const uint2 bb = *reinterpret_cast<const uint2*>(p.bias + f0);
-        bias4 = make_float4(bf16_lo(bb.x), bf16_hi(bb.x), bf16_lo(bb.y), bf16_hi(bb.y));
-      }
-      if (f0 < p.n) {
-#pragma unroll 1
-        for (int r0 = wq; r0 < rows_valid; r0 += 4 * kTok) {
-          float4 g[kTok], u[kTok];
-#pragma unroll
-          for (int t = 0; t < kTok; ++t) { g[t] = make_float4(0.f, 0.f, 0.f, 0.f); u[t] = g[t]; }
-#pragma unroll 1
-          for (int s0 = 0; s0 < p.splits; s0 += 4) {
-            float4 a[kTok][4], b[kTok][4];
-#pragma unroll
-            for (int t = 0; t < kTok; ++t) {
-              const int r = r0 + 4 * t;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const bool on = (r < rows_valid) && (s0 + j < p.splits);
-                const float* src = ws0 + static_cast<size_t>(s0 + j) * kPart + static_cast<size_t>(r) * kTileM;
-                a[t][j] = on ? __ldcg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (DUAL) b[t][j] = on ? __ldcg(reinterpret_cast<const float4*>(src + static_cast<size_t>(BN) * kTileM)) : make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-            }
-#pragma unroll
-            for (int t = 0; t < kTok; ++t) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                g[t].x += a[t][j].x; g[t].y += a[t][j].y; g[t].z += a[t][j].z; g[t].w += a[t][j].w;
-                if (DUAL) { u[t].x += b[t][j].x; u[t].y += b[t][j].y; u[t].z += b[t][j].z; u[t].w += b[t][j].w; }
-              }
-            }
-          }
-#pragma unroll
-          for (int t = 0; t < kTok; ++t) {
-            const int r = r0 + 4 * t;
-            if (r >= rows_valid) break;
-            float y[4] = {g[t].x + bias4.x, g[t].y + bias4.y, g[t].z + bias4.z, g[t].w + bias4.w};
-            const float uu[4] = {u[t].x, u[t].y, u[t].z, u[t].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (DUAL) y[j] = apply_act(p.act, y[j]) * uu[j];
-              if (p.softcap > 0.f) y[j] = p.softcap * tanhf(y[j] / p.softcap);
-              // the un-split path rounds to the output type before the residual is added (staging buffer): keep the same numerics
-              if (sizeof(OutT) == 2) y[j] = __bfloat162float(__float2bfloat16_rn(y[j]));
-            }
-            const size_t row = static_cast<size_t>(row_base + r);
-            if (p.residual != nullptr) {
-              const uint2 rr = *reinterpret_cast<const uint2*>(p.residual + row * p.ld_res + f0);
-              y[0] += bf16_lo(rr.x); y[1] += bf16_hi(rr.x); y[2] += bf16_lo(rr.y); y[3] += bf16_hi(rr.y);
-            }
-            if (sizeof(OutT) == 2) {
-              uint2 o;
-              o.x = pack_bf16(y[0], y[1]); o.y = pack_bf16(y[2], y[3]);
-              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ld_out + f0) = o;
-            } else {
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ld_out + f0) = make_float4(y[0], y[1], y[2], y[3]);
-            }
-          }
-        }
-      }
-    } else if (do_epilogue) {
+    if (do_epilogue) {
       OutT* stg = reinterpret_cast<OutT*>(smem);  // aliases the idle stage ring: [BN][128]
       const float bias = (p.bias != nullptr && f_glob < p.n) ? __bfloat162float(p.bias[f_glob]) : 0.0f;
+      const float* ws0 = nullptr;
+      if (p.splits > 1)
+        ws0 = p.workspace + static_cast<size_t>((blockIdx.y * gridDim.x + blockIdx.x) * (gridDim.z / p.splits) + mt) *
+                                p.splits * (BN * (DUAL ? 2 : 1) * kTileM);
 #pragma unroll 1
       for (int c = 0; c < BN; c += 16) {
         if (c >= rows_valid) break;
         float g[16], u[16];
-        uint32_t v[16];
-        tmem_ld16(taddr + c, v);
-        tmem_ld_wait();
+        if (p.splits > 1) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) g[j] = __uint_as_float(v[j]);
-        if (DUAL) {
-          tmem_ld16(taddr + BN + c, v);
+          for (int j = 0; j < 16; ++j) { g[j] = 0.f; u[j] = 0.f; }
+          // deterministic split order, but 2 splits x 16 columns of independent L2 loads are in flight
+          // per thread before they are consumed (the reduction is latency-, not bandwidth-bound)
+          for (int s = 0; s < p.splits; s += 2) {
+            const float* w0 = ws0 + static_cast<size_t>(s) * (BN * (DUAL ? 2 : 1) * kTileM);
+            const bool two = (s + 1) < p.splits;
+            const float* w1 = two ? w0 + (BN * (DUAL ? 2 : 1) * kTileM) : w0;
+            float a0[16], a1[16], b0[16], b1[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              a0[j] = __ldcg(&w0[(c + j) * kTileM + f_local]);
+              a1[j] = two ? __ldcg(&w1[(c + j) * kTileM + f_local]) : 0.f;
+              if (DUAL) {
+                b0[j] = __ldcg(&w0[(BN + c + j) * kTileM + f_local]);
+                b1[j] = two ? __ldcg(&w1[(BN + c + j) * kTileM + f_local]) : 0.f;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              g[j] = (g[j] + a0[j]) + a1[j];
+              if (DUAL) u[j] = (u[j] + b0[j]) + b1[j];
+            }
+          }
+        } else {
+          uint32_t v[16];
+          tmem_ld16(taddr + c, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) u[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 16; ++j) g[j] = __uint_as_float(v[j]);
+          if (DUAL) {
+            tmem_ld16(taddr + BN + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) u[j] = __uint_as_float(v[j]);
+          }
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {

@@ -11,6 +11,8 @@ cudaError_t rmsnorm_launch(const void* x, long long ld_x, const void* w, const v
                            void* out, long long ld_out, int rows, int H, float eps, bool gemma, cudaStream_t s);
 cudaError_t rope_launch(void* x, long long ld_t, long long ld_h, int heads, const int* positions, const float* inv_freq,
                         int rot_off, int rot_dim, bool interleaved, float mscale, int T, cudaStream_t s);
+// bulk L2 prefetch of [p, p + bytes) (16 B aligned), a few threads, no PDL: meant for a side stream
+cudaError_t l2_prefetch_launch(const void* p, unsigned long long bytes, cudaStream_t s);
 cudaError_t embed_launch(const long long* ids, const void* table, const void* scales, const void* biases, int bits, int group,
                          void* out, int H, float scale, int T, cudaStream_t s);
 cudaError_t kv_write_launch(const void* k, long long k_ld_t, long long k_ld_h, const void* v, long long v_ld_t,
@@ -70,7 +72,10 @@ cudaError_t mla_decode_launch(const void* q, long long q_ld_t, int B, const void
 // `extra`: always-on experts appended after the routed ones (ids E .. E+extra-1, weight 1); idx / wts rows are top_k + extra wide
 cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, int T, int H, int E, int top_k,
                              int n_group, int topk_group, float scaling, bool norm_topk, int extra, int* idx, float* wts,
-                             int* sc_counts, int sc_stride, int* sc_pair_row, void* sc_x, cudaStream_t s);
+                             int* sc_counts, int sc_stride, int* sc_pair_row, void* sc_x, const void* norm_w, float norm_eps,
+                             cudaStream_t s);
+// (norm_w != nullptr: `x` is the un-normalised residual stream; the router normalises the row in shared memory first — the fused
+//  pre-MoE RMSNorm — so logits and scattered expert inputs equal what a separate norm kernel would have produced)
 // (sc_*: scatter mode for decode batches — every (token, k) pair claims slot `atomicAdd(sc_counts[e])` of expert e's fixed-stride
 //  segment, its row index goes to sc_pair_row and the token row is copied to sc_x[row]: no separate permutation kernels)
 // permutation: counts/offsets per expert, destination row of every (token, k) pair, gathered rows
@@ -81,7 +86,8 @@ cudaError_t moe_permute_launch(const int* idx, int T, int top_k, int E, int* exp
 cudaError_t moe_combine_launch(const void* y_perm, const int* pair_row, const float* wts, const void* residual,
                                long long ld_res, void* out, long long ld_out, int T, int top_k, int H,
                                uint32_t* signal_flag, uint32_t signal_value, unsigned int* done_counter, int* zero_counts,
-                               int n_zero, cudaStream_t s);
+                               int n_zero, const void* norm_w, float norm_eps, void* normed, long long ld_normed, cudaStream_t s);
+// (norm_w != nullptr: additionally writes normed = rmsnorm(out) * norm_w — the next layer's input norm fused into the combine)
 
 // ---- sampler.cu
 cudaError_t apply_penalties_launch(float* logits, int B, int V, const int* rep_ctx, int C, const float* penalty,

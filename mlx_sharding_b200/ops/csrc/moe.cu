@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(kRouteToks == 1 ? 1024 : kRouteThreads)
 moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv_bfloat16* __restrict__ gw, int T, int H,
                  int E, int top_k, int n_group, int topk_group, float scaling, int norm_topk, int extra, int* __restrict__ idx,
                  float* __restrict__ wts, int* __restrict__ sc_counts, int sc_stride, int* __restrict__ sc_pair_row,
-                 __nv_bfloat16* __restrict__ sc_x) {
+                 __nv_bfloat16* __restrict__ sc_x, const __nv_bfloat16* __restrict__ norm_w, float norm_eps) {
   pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   extern __shared__ __align__(16) uint8_t smem[];
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem);                 // [kRouteToks][H]
@@ -55,6 +55,33 @@ moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv
     reinterpret_cast<uint4*>(xs + (size_t)tk * H)[v] = r;
   }
   __syncthreads();
+  if (norm_w != nullptr) {
+    // Fused pre-MoE RMSNorm: `x` is the un-normalised residual stream; warp `tk` normalises token `tk` in shared memory (same
+    // arithmetic as rmsnorm_kernel: fp32 statistics, x * inv * w rounded to bf16), so the router logits AND the scattered expert
+    // inputs below see exactly what a separate norm kernel would have written — without its launch and its HBM round trip.
+    if (warp < kRouteToks) {
+      uint4* row = reinterpret_cast<uint4*>(xs + (size_t)warp * H);
+      float ss = 0.f;
+      for (int v = lane; v < nvec; v += 32) {
+        const uint4 r = row[v];
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float a = bf16_lo(rr[j]), b = bf16_hi(rr[j]); ss += a * a + b * b; }
+      }
+      ss = warp_sum(ss);
+      const float inv = rsqrtf(ss / (float)H + norm_eps);
+      for (int v = lane; v < nvec; v += 32) {
+        const uint4 r = row[v];
+        const uint4 g = __ldg(reinterpret_cast<const uint4*>(norm_w) + v);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w}, gg[4] = {g.x, g.y, g.z, g.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = pack_bf16(bf16_lo(rr[j]) * inv * bf16_lo(gg[j]), bf16_hi(rr[j]) * inv * bf16_hi(gg[j]));
+        row[v] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    __syncthreads();
+  }
   for (int e = warp; e < E; e += blockDim.x / 32) {
     float acc[kRouteToks];
 #pragma unroll
@@ -288,11 +315,89 @@ __global__ void moe_combine_kernel(const float* __restrict__ y_perm, const int* 
   }
 }
 
+// Combine + the NEXT layer's input RMSNorm, one CTA per token: the combined row is rounded to bf16 (that is the residual stream the
+// un-fused graph stores), kept in registers, reduced to its mean square and written a second time normalised — the attention
+// block of the next layer starts from `normed` without a norm kernel (launch + 2 x row traffic + one dependent-kernel gap saved).
+constexpr int kCombThreads = 256;
+constexpr int kCombMaxV = 4;   // H <= 256 * 8 * 4 = 8192
+__global__ void __launch_bounds__(kCombThreads)
+moe_combine_norm_kernel(const float* __restrict__ y_perm, const int* __restrict__ pair_row, const float* __restrict__ wts,
+                        const __nv_bfloat16* __restrict__ residual, long long ld_res, __nv_bfloat16* __restrict__ out,
+                        long long ld_out, int top_k, int H, int* __restrict__ zero_counts, int n_zero,
+                        const __nv_bfloat16* __restrict__ norm_w, float norm_eps, __nv_bfloat16* __restrict__ normed,
+                        long long ld_normed) {
+  pdl_sync();
+  if (zero_counts != nullptr && blockIdx.x == 0)
+    for (int e = threadIdx.x; e < n_zero; e += blockDim.x) zero_counts[e] = 0;
+  const int t = blockIdx.x;
+  const int nvec = H / 8;
+  __shared__ float s_w[32];
+  __shared__ int s_row[32];
+  __shared__ float red[kCombThreads / 32];
+  if (threadIdx.x < top_k) {
+    s_w[threadIdx.x] = wts[(size_t)t * top_k + threadIdx.x];
+    s_row[threadIdx.x] = pair_row[(size_t)t * top_k + threadIdx.x];
+  }
+  __syncthreads();
+  uint4 keep[kCombMaxV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kCombMaxV; ++i) {
+    const int v = threadIdx.x + i * kCombThreads;
+    if (v < nvec) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int k = 0; k < top_k; ++k) {
+        const float w = s_w[k];
+        const float* src = y_perm + (size_t)s_row[k] * H + v * 8;
+        const float4 a = *reinterpret_cast<const float4*>(src);
+        const float4 b = *reinterpret_cast<const float4*>(src + 4);
+        acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
+        acc[4] += w * b.x; acc[5] += w * b.y; acc[6] += w * b.z; acc[7] += w * b.w;
+      }
+      if (residual != nullptr) {
+        const uint4 r = reinterpret_cast<const uint4*>(residual + (size_t)t * ld_res)[v];
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[2 * j] += bf16_lo(rr[j]); acc[2 * j + 1] += bf16_hi(rr[j]); }
+      }
+      uint4 o;
+      o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+      o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+      reinterpret_cast<uint4*>(out + (size_t)t * ld_out)[v] = o;
+      keep[i] = o;
+      const uint32_t oo[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float a = bf16_lo(oo[j]), b = bf16_hi(oo[j]); ss += a * a + b * b; }
+    }
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < kCombThreads / 32; ++i) tot += red[i];
+  const float inv = rsqrtf(tot / (float)H + norm_eps);
+#pragma unroll
+  for (int i = 0; i < kCombMaxV; ++i) {
+    const int v = threadIdx.x + i * kCombThreads;
+    if (v < nvec) {
+      const uint4 g = __ldg(reinterpret_cast<const uint4*>(norm_w) + v);
+      const uint32_t oo[4] = {keep[i].x, keep[i].y, keep[i].z, keep[i].w}, gg[4] = {g.x, g.y, g.z, g.w};
+      uint32_t n[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) n[j] = pack_bf16(bf16_lo(oo[j]) * inv * bf16_lo(gg[j]), bf16_hi(oo[j]) * inv * bf16_hi(gg[j]));
+      reinterpret_cast<uint4*>(normed + (size_t)t * ld_normed)[v] = make_uint4(n[0], n[1], n[2], n[3]);
+    }
+  }
+}
+
 }  // namespace
 
 cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, int T, int H, int E, int top_k, int n_group,
                              int topk_group, float scaling, bool norm_topk, int extra, int* idx, float* wts, int* sc_counts,
-                             int sc_stride, int* sc_pair_row, void* sc_x, cudaStream_t s) {
+                             int sc_stride, int* sc_pair_row, void* sc_x, const void* norm_w, float norm_eps, cudaStream_t s) {
   if (T == 0) return cudaSuccess;
   if (sc_counts != nullptr && (T > 1024 || sc_stride < T)) return cudaErrorInvalidValue;   // scatter: one-token-per-CTA variant only
   if (E > 32 * kMaxEPerLane || top_k + extra > 32 || extra < 0 || (H % 8) || n_group > 32 || (n_group > 1 && E % n_group)) return cudaErrorInvalidValue;
@@ -303,7 +408,8 @@ cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, 
     if (smem > 48 * 1024) return cudaErrorInvalidValue;
     // one token per CTA, 32 warps: each warp owns <= 2 experts, so the whole router row set costs two L2 round trips
     (void)launch_pdl(moe_route_kernel<1>, dim3(T), dim3(E >= 64 ? 1024 : (E >= 32 ? 512 : kRouteThreads)), smem, s, xx, ld_x, gw, T, H, E, top_k, n_group, topk_group, scaling,
-                                                       norm_topk ? 1 : 0, extra, idx, wts, sc_counts, sc_stride, sc_pair_row, static_cast<__nv_bfloat16*>(sc_x));
+                                                       norm_topk ? 1 : 0, extra, idx, wts, sc_counts, sc_stride, sc_pair_row, static_cast<__nv_bfloat16*>(sc_x),
+                                                       static_cast<const __nv_bfloat16*>(norm_w), norm_eps);
   } else {
     constexpr int TOKS = 8;
     const size_t smem = (size_t)TOKS * H * 2 + (size_t)TOKS * E * 4;
@@ -314,7 +420,8 @@ cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, 
       configured = smem;
     }
     (void)launch_pdl(moe_route_kernel<TOKS>, dim3((T + TOKS - 1) / TOKS), dim3(kRouteThreads), smem, s, xx, ld_x, gw, T, H, E, top_k, n_group, topk_group,
-                                                                           scaling, norm_topk ? 1 : 0, extra, idx, wts, sc_counts, sc_stride, sc_pair_row, static_cast<__nv_bfloat16*>(sc_x));
+                                                                           scaling, norm_topk ? 1 : 0, extra, idx, wts, sc_counts, sc_stride, sc_pair_row, static_cast<__nv_bfloat16*>(sc_x),
+                                                                           static_cast<const __nv_bfloat16*>(norm_w), norm_eps);
   }
   return cudaGetLastError();
 }
@@ -336,9 +443,17 @@ cudaError_t moe_permute_launch(const int* idx, int T, int top_k, int E, int* exp
 cudaError_t moe_combine_launch(const void* y_perm, const int* pair_row, const float* wts, const void* residual,
                                long long ld_res, void* out, long long ld_out, int T, int top_k, int H,
                                uint32_t* signal_flag, uint32_t signal_value, unsigned int* done_counter, int* zero_counts,
-                               int n_zero, cudaStream_t s) {
+                               int n_zero, const void* norm_w, float norm_eps, void* normed, long long ld_normed, cudaStream_t s) {
   if (T == 0) return cudaSuccess;
   if (H % 8) return cudaErrorInvalidValue;
+  if (norm_w != nullptr) {
+    // fused next-layer RMSNorm (never together with a stage hand-off: the last layer of a stage has no next layer to norm for)
+    if (signal_flag != nullptr || normed == nullptr || top_k > 32 || H > kCombThreads * 8 * kCombMaxV) return cudaErrorInvalidValue;
+    (void)launch_pdl(moe_combine_norm_kernel, dim3(T), dim3(kCombThreads), 0, s, static_cast<const float*>(y_perm), pair_row, wts,
+                     static_cast<const __nv_bfloat16*>(residual), ld_res, static_cast<__nv_bfloat16*>(out), ld_out, top_k, H, zero_counts,
+                     n_zero, static_cast<const __nv_bfloat16*>(norm_w), norm_eps, static_cast<__nv_bfloat16*>(normed), ld_normed);
+    return cudaGetLastError();
+  }
   const long long total = (long long)T * (H / 8);
   (void)launch_pdl(moe_combine_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, 
       static_cast<const float*>(y_perm), pair_row, wts, static_cast<const __nv_bfloat16*>(residual), ld_res,

@@ -548,6 +548,8 @@ def run(host: str, port: int, model_provider: ModelProvider, static_dir: str, ap
         a = model_provider.cli_args
         if model_provider.engine is None:
             raise SystemExit("--api-workers needs --model (the engine is built at start-up; per-request model loading is off)")
+        if not hasattr(model_provider.engine, "sinks"):
+            raise SystemExit("--api-workers is not available with --expert-parallel (the lockstep group owns the request routing)")
         tok_cfg = {"trust_remote_code": True if getattr(a, "trust_remote_code", False) else None,
                    "chat_template": getattr(a, "chat_template", "") or None,
                    "use_default_chat_template": bool(getattr(a, "use_default_chat_template", False))}

@@ -198,6 +198,35 @@ def test_moe_block_scatter_matches_permutation_path(B, T, extra):
     assert all(int(c.sum()) == 0 for c, _ in B._scatter_bufs.values())
 
 
+@pytest.mark.parametrize("T,extra", [(1, 0), (64, 2), (37, 2), (200, 2)])
+def test_moe_block_fused_norms(B, T, extra, monkeypatch):
+    """RMSNorm folded into the router kernel (pre-MoE norm) and into the combine kernel (next layer's input norm) == separate norm
+    kernels around the same block; T = 200 takes the permutation fallback (norms run as kernels there)."""
+    H, I, E, k = 2048, 1408, 64, 6
+    Et = E + extra
+    h = rnd(T, H, scale=2.0)
+    gw = rnd(E, H, scale=0.05)
+    Wg = LinearWeight(weight=rnd(Et, I, H, scale=0.03, seed=1))
+    Wu = LinearWeight(weight=rnd(Et, I, H, scale=0.03, seed=2))
+    Wd = LinearWeight(weight=rnd(Et, H, I, scale=0.03, seed=3))
+    n1, n2 = (1.0 + rnd(H, scale=0.1, seed=7)), (1.0 + rnd(H, scale=0.1, seed=8))
+    rk = dict(top_k=k, method="greedy", n_group=1, topk_group=1, scaling=1.0, norm_topk=False)
+    ref = B.moe_block(B.rmsnorm(h, n1, 1e-6), gw, rk, Wg, Wu, Wd, "silu", residual=h, extra=extra)
+    ref_n = B.rmsnorm(ref, n2, 1e-6)
+    for _ in range(2):
+        got, got_n = B.moe_block(h, gw, rk, Wg, Wu, Wd, "silu", residual=h, extra=extra, pre_norm=(n1, 1e-6), next_norm=(n2, 1e-6))
+        # the statistics are summed in a different order than rmsnorm_kernel's: a normalised value may land on the neighbouring bf16
+        close(got, ref, 2e-2, 1e-2)
+        close(got_n, ref_n, 2e-2, 2e-2)
+    only_pre = B.moe_block(h, gw, rk, Wg, Wu, Wd, "silu", residual=h, extra=extra, pre_norm=(n1, 1e-6))
+    close(only_pre, ref, 2e-2, 1e-2)
+    monkeypatch.setenv("MLXB200_FUSE_NORMS", "0")
+    got, got_n = B.moe_block(h, gw, rk, Wg, Wu, Wd, "silu", residual=h, extra=extra, pre_norm=(n1, 1e-6), next_norm=(n2, 1e-6))
+    assert torch.equal(got, ref) and torch.equal(got_n, ref_n)
+    torch.cuda.synchronize()
+    assert all(int(c.sum()) == 0 for c, _ in B._scatter_bufs.values())
+
+
 def test_sampler_greedy_logprobs_topk(B):
     Bn, V = 5, 102400
     logits = rnd(Bn, V, scale=3.0, dtype=torch.float32)

@@ -77,3 +77,94 @@ def test_generate_cli_expert_parallel(tmp_path):
     text = lambda out: "".join(l for l in out.split("==========")[0].splitlines(True) if not l.startswith("NCCL version"))
     assert "Generation:" in ep.stdout
     assert text(one.stdout) == text(ep.stdout) and len(text(one.stdout)) > 0
+
+
+# ---------------------------------------------------------------------------------------------- HTTP serving on GPUs
+def _serve_and_ask(tmp_path, ckpt, nproc, extra, bodies, master_port):
+    """Start ``mlx-sharding-api`` (plain or under torchrun), POST ``bodies`` concurrently, return (answers, /metrics text)."""
+    import concurrent.futures
+    import http.client
+    import json
+    import signal
+    import socket
+    import time
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        http_port = s.getsockname()[1]
+    root = os.path.dirname(HERE)
+    cmd = [sys.executable, "-m", "shard.openai_api"] if nproc == 1 else \
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+         "--master-port", str(master_port), "-m", "shard.openai_api"]
+    cmd += ["--model", ckpt, "--port", str(http_port), "--kv-pages", "256", "--page-size", "64", "--log-level", "WARNING"] + extra
+    env = dict(os.environ, PYTHONPATH=root)
+    if nproc == 1:
+        env["CUDA_VISIBLE_DEVICES"] = "0"
+    proc = subprocess.Popen(cmd, cwd=str(tmp_path), env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, start_new_session=True)
+
+    def post(body):
+        c = http.client.HTTPConnection("127.0.0.1", http_port, timeout=180)
+        c.request("POST", "/v1/chat/completions", json.dumps(body), {"Content-Type": "application/json"})
+        r = c.getresponse()
+        data = r.read()
+        c.close()
+        return r.status, json.loads(data)
+
+    try:
+        t0 = time.time()
+        while True:
+            assert proc.poll() is None, "server exited early: " + proc.stdout.read().decode(errors="replace")[-3000:]
+            assert time.time() - t0 < 300, "server did not come up"
+            try:
+                c = http.client.HTTPConnection("127.0.0.1", http_port, timeout=2)
+                c.request("GET", "/health")
+                if c.getresponse().status == 200:
+                    break
+            except OSError:
+                time.sleep(0.5)
+        with concurrent.futures.ThreadPoolExecutor(len(bodies)) as ex:
+            res = list(ex.map(post, bodies))
+        c = http.client.HTTPConnection("127.0.0.1", http_port, timeout=10)
+        c.request("GET", "/metrics")
+        metrics = c.getresponse().read().decode()
+        return res, metrics
+    finally:
+        os.killpg(proc.pid, signal.SIGTERM)      # the exact process group started above
+        try:
+            proc.wait(timeout=30)
+        except subprocess.TimeoutExpired:
+            os.killpg(proc.pid, signal.SIGKILL)
+
+
+def _agree(a, b):
+    """Greedy answers of two numerically different executions of the same model: equal lengths, equal first token, and at most one
+    request diverging later (a near-tie flips the rest of that stream)."""
+    assert [len(x) for x in a] == [len(x) for x in b]
+    assert all(x[0] == y[0] for x, y in zip(a, b))
+    assert sum(x != y for x, y in zip(a, b)) <= 1, (a, b)
+
+
+@pytest.mark.timeout(900)
+def test_http_serving_on_gpus(tmp_path):
+    """``mlx-sharding-api`` on real GPUs, the three layouts a user can start: one GPU; a 2-stage chain under torchrun with the HTTP
+    front end in worker processes (``--api-workers``); a 2-rank expert-parallel lockstep group.  Same greedy answers."""
+    import torch
+
+    sys.path.insert(0, HERE)
+    from helpers import GPU_DSV2
+    from mlx_sharding_b200.utils.checkpoint import write_synthetic_checkpoint
+
+    ckpt = write_synthetic_checkpoint(str(tmp_path / "dsv2"), GPU_DSV2, dtype=torch.bfloat16, seed=11)
+    bodies = [{"messages": [{"role": "user", "content": f"hello gpus {i}"}], "max_tokens": 6 + i, "temperature": 0, "logprobs": 1}
+              for i in range(4)]
+    toks = lambda res: [j["choices"][0]["logprobs"]["tokens"] for _, j in res]
+    one, _ = _serve_and_ask(tmp_path, ckpt, 1, [], bodies, 0)
+    assert all(st == 200 for st, _ in one) and [len(t) for t in toks(one)] == [6, 7, 8, 9]
+    chain, m = _serve_and_ask(tmp_path, ckpt, 2, ["--api-workers", "2"], bodies, 29591)
+    assert all(st == 200 for st, _ in chain), chain
+    _agree(toks(one), toks(chain))
+    assert "mlx_sharding_engine_steps" in m
+    ep, m = _serve_and_ask(tmp_path, ckpt, 2, ["--expert-parallel"], bodies, 29592)
+    assert all(st == 200 for st, _ in ep), ep
+    _agree(toks(one), toks(ep))
+    assert "lockstep_assigned_rank0 2" in m and "lockstep_assigned_rank1 2" in m, m
