@@ -113,6 +113,10 @@ class LockstepGroup:
         d.update({f"lockstep_assigned_rank{r}": n for r, n in enumerate(self._assigned)})
         return d
 
+    def metrics_snapshot(self):
+        """(counters, free KV pages of this rank) — the ``/metrics`` surface shared with ``LLMEngine``."""
+        return self.stats, self.engine.table.alloc.num_free
+
     def submit(self, prompt, params: Optional[SamplingParams] = None, max_tokens: int = 100, eos_token_id: Optional[int] = None,
                stop_id_sequences=None) -> Request:
         assert self.rank == 0, "requests enter the group on rank 0"
@@ -258,6 +262,13 @@ def build_lockstep_group(model, num_pages: int, page_size: int = 64, max_seqs: i
     enable_expert_parallel(model, max_tokens=bound)
     for layer in model.ep_layers.values():
         layer.peer_tokens_default = bound                       # ranks run different batch sizes: size temporaries for the bound
-    engine = LockstepEngine(LocalPipeline([StageExecutor(model, num_pages, page_size)]), num_pages, page_size, ctrl_group=ctrl,
+    pipe = LocalPipeline([StageExecutor(model, num_pages, page_size)])
+    if pipe.gcache is not None:
+        # No CUDA-graph replay in the lockstep group: a rank *capturing* a decode graph launches nothing for real while its peers
+        # execute the same iteration eagerly and wait for its expert dispatch — the ranks' batches (hence their capture points)
+        # differ, so captures cannot be aligned without making every rank capture every other rank's bucket.  The graph-resident
+        # expert-parallel loop is the symmetric one (parallel/decode_loop.py: bench.py --parallelism ep, generate.py --expert_parallel).
+        pipe.gcache.enabled = False
+    engine = LockstepEngine(pipe, num_pages, page_size, ctrl_group=ctrl,
                             max_seqs_per_group=max_seqs, max_prefill_tokens=max_prefill_tokens, prefix_cache=prefix_cache)
     return LockstepGroup(engine, ctrl)

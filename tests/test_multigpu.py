@@ -100,7 +100,10 @@ def _serve_and_ask(tmp_path, ckpt, nproc, extra, bodies, master_port):
     env = dict(os.environ, PYTHONPATH=root)
     if nproc == 1:
         env["CUDA_VISIBLE_DEVICES"] = "0"
-    proc = subprocess.Popen(cmd, cwd=str(tmp_path), env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, start_new_session=True)
+    log_path = os.path.join(str(tmp_path), f"server_{nproc}_{'_'.join(e.strip('-') for e in extra) or 'plain'}.log")
+    log_f = open(log_path, "wb")
+    proc = subprocess.Popen(cmd, cwd=str(tmp_path), env=env, stdout=log_f, stderr=subprocess.STDOUT, start_new_session=True)
+    tail = lambda: open(log_path, errors="replace").read()[-4000:]
 
     def post(body):
         c = http.client.HTTPConnection("127.0.0.1", http_port, timeout=180)
@@ -113,7 +116,7 @@ def _serve_and_ask(tmp_path, ckpt, nproc, extra, bodies, master_port):
     try:
         t0 = time.time()
         while True:
-            assert proc.poll() is None, "server exited early: " + proc.stdout.read().decode(errors="replace")[-3000:]
+            assert proc.poll() is None, "server exited early: " + tail()
             assert time.time() - t0 < 300, "server did not come up"
             try:
                 c = http.client.HTTPConnection("127.0.0.1", http_port, timeout=2)
@@ -122,8 +125,12 @@ def _serve_and_ask(tmp_path, ckpt, nproc, extra, bodies, master_port):
                     break
             except OSError:
                 time.sleep(0.5)
-        with concurrent.futures.ThreadPoolExecutor(len(bodies)) as ex:
-            res = list(ex.map(post, bodies))
+        try:
+            with concurrent.futures.ThreadPoolExecutor(len(bodies)) as ex:
+                res = list(ex.map(post, bodies))
+        except Exception as e:  # noqa: BLE001 — show what the server printed
+            time.sleep(1.0)
+            raise AssertionError(f"request failed ({type(e).__name__}: {e}); server log tail:\n" + tail()) from e
         c = http.client.HTTPConnection("127.0.0.1", http_port, timeout=10)
         c.request("GET", "/metrics")
         metrics = c.getresponse().read().decode()
@@ -134,6 +141,7 @@ def _serve_and_ask(tmp_path, ckpt, nproc, extra, bodies, master_port):
             proc.wait(timeout=30)
         except subprocess.TimeoutExpired:
             os.killpg(proc.pid, signal.SIGKILL)
+        log_f.close()
 
 
 def _agree(a, b):
