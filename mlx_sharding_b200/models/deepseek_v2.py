@@ -350,6 +350,29 @@ class DeepseekV2Stage(StageModel):
                 self._prenormed = res
                 return res[0]
             return res
+        if ("router" in w and ep is not None and i in ep and hasattr(ep[i], "route_forward") and getattr(ep[i].b, "v2", False)
+                and 1 <= T <= 1024 and os.environ.get("MLXB200_EP_FUSED_ROUTE", "1") != "0"):
+            # expert-parallel block as four kernels (parallel/ep.py::route_forward): [pre-MoE norm + router + dispatch] -> grouped
+            # gate/up -> grouped down (+ return) -> [combine + next layer's input norm]; the shared experts fork onto the side
+            # stream right behind the router (they consume the normalised rows it stores)
+            def shared_branch(normed):
+                if "s_gate" not in w:
+                    return h, None
+                if self.overlap_shared_experts and hasattr(O, "run_aside"):
+                    hs = torch.empty_like(h)
+                    return hs, O.run_aside(lambda: O.linear(O.gated_up(normed, w["s_gate"], w["s_up"], "silu"), w["s_down"], residual=h, out=hs))
+                return O.linear(O.gated_up(normed, w["s_gate"], w["s_up"], "silu"), w["s_down"], residual=h), None
+
+            nxt = self.layer_weights.get(i + 1)
+            nn = (nxt["in_ln"], c.rms_norm_eps) if (nxt is not None and "in_ln" in nxt and self.spec.runs_attn(i + 1)) else None
+            res = ep[i].route_forward(h, w["router"], dict(top_k=c.num_experts_per_tok, method=c.topk_method, n_group=c.n_group or 1,
+                                                           topk_group=c.topk_group or 1, scaling=c.routed_scaling_factor,
+                                                           norm_topk=c.norm_topk_prob),
+                                      (w["post_ln"], c.rms_norm_eps), shared_branch, next_norm=nn)
+            if nn is not None:
+                self._prenormed = res
+                return res[0]
+            return res
         normed = O.rmsnorm(h, w["post_ln"], c.rms_norm_eps)
         if "router" in w:
             join = None

@@ -705,6 +705,40 @@ void ep_dispatch_scatter(const Tensor& x, const Tensor& idx, int64_t experts_per
                                              cur_stream()));
 }
 
+// Router + expert-parallel dispatch in one kernel (v2 exchange): returns {idx, wts}; optionally normalises `x` first (norm_w) and
+// stores the normalised rows (normed_out) for the shared-expert branch.
+std::vector<Tensor> ep_route_dispatch(const Tensor& x, const Tensor& gate_w, int64_t top_k, int64_t n_group, int64_t topk_group, double scaling,
+                                      bool norm_topk, int64_t experts_per_rank, int64_t my_rank, int64_t cap_e, std::vector<int64_t> recv_x,
+                                      std::vector<int64_t> recv_dst, std::vector<int64_t> recv_cnt, std::vector<int64_t> recv_seq,
+                                      std::vector<int64_t> my_ret, Tensor send_seq, Tensor done_counter, const c10::optional<Tensor>& ret_expected,
+                                      const c10::optional<Tensor>& norm_w, double norm_eps, const c10::optional<Tensor>& normed_out) {
+  check_bf16(x, "x"); check_bf16(gate_w, "gate_w"); check_rows(x, "x");
+  TORCH_CHECK(gate_w.is_contiguous());
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int T = (int)x.size(0), world = (int)recv_x.size();
+  TORCH_CHECK(T >= 1 && T <= 1024 && world <= b200::kEpMaxWorld, "fused route + dispatch needs 1 <= T <= 1024");
+  if (norm_w.has_value()) { check_bf16(*norm_w, "norm_w"); TORCH_CHECK(norm_w->is_contiguous() && norm_w->numel() == x.size(1)); }
+  if (normed_out.has_value()) { check_bf16(*normed_out, "normed_out"); check_rows(*normed_out, "normed_out"); TORCH_CHECK(normed_out->size(0) >= T && normed_out->size(1) == x.size(1)); }
+  Tensor idx = torch::empty({T, top_k}, torch::dtype(torch::kInt32).device(x.device()));
+  Tensor w = torch::empty({T, top_k}, torch::dtype(torch::kFloat32).device(x.device()));
+  b200::RouteEP ep;
+  ep.enabled = 1; ep.experts_per_rank = (int)experts_per_rank; ep.world = world; ep.my_rank = (int)my_rank; ep.cap_e = (int)cap_e;
+  auto fill = [&](b200::EpPeerTable& t, const std::vector<int64_t>& v) {
+    for (int i = 0; i < b200::kEpMaxWorld; ++i) t.p[i] = i < world ? (unsigned long long)v[i] : 0ull;
+  };
+  TORCH_CHECK((int)recv_dst.size() == world && (int)recv_cnt.size() == world && (int)recv_seq.size() == world && (int)my_ret.size() == world);
+  fill(ep.recv_x, recv_x); fill(ep.recv_dst, recv_dst); fill(ep.recv_cnt, recv_cnt); fill(ep.recv_seq, recv_seq); fill(ep.my_ret, my_ret);
+  ep.send_seq = reinterpret_cast<uint32_t*>(send_seq.data_ptr<int>());
+  ep.done_counter = reinterpret_cast<unsigned int*>(done_counter.data_ptr<int>());
+  ep.ret_expected = ret_expected.has_value() ? reinterpret_cast<uint32_t*>(ret_expected->data_ptr<int>()) : nullptr;
+  LAUNCH_OK(b200::moe_route_launch(x.data_ptr(), x.stride(0), gate_w.data_ptr(), T, (int)x.size(1), (int)gate_w.size(0), (int)top_k,
+                                   (int)n_group, (int)topk_group, (float)scaling, norm_topk, 0, idx.data_ptr<int>(), w.data_ptr<float>(),
+                                   nullptr, 0, nullptr, nullptr, norm_w.has_value() ? norm_w->data_ptr() : nullptr, (float)norm_eps,
+                                   cur_stream(), &ep, normed_out.has_value() ? normed_out->data_ptr() : nullptr,
+                                   normed_out.has_value() ? normed_out->stride(0) : 0));
+  return {idx, w};
+}
+
 std::vector<Tensor> ep_regroup(int64_t recv_words_ptr, int64_t counter_ptr, int64_t error_ptr, int64_t recv_meta_ptr,
                                int64_t recv_x_ptr, int64_t world, int64_t cap, int64_t E_local, int64_t H, int64_t device,
                                int64_t rows_bound, std::vector<int64_t> ret_y) {
@@ -730,17 +764,25 @@ std::vector<Tensor> ep_regroup(int64_t recv_words_ptr, int64_t counter_ptr, int6
   return {offs, total, x_perm, row_dst};
 }
 Tensor ep_combine(int64_t flag_ptr, const Tensor& expected, int64_t error_ptr, const Tensor& ret_y, const Tensor& wts,
-                  const c10::optional<Tensor>& residual, const c10::optional<Tensor>& out_) {
+                  const c10::optional<Tensor>& residual, const c10::optional<Tensor>& out_, const c10::optional<Tensor>& norm_w,
+                  double norm_eps, const c10::optional<Tensor>& normed) {
   TORCH_CHECK(ret_y.scalar_type() == torch::kFloat32 && ret_y.is_contiguous() && wts.scalar_type() == torch::kFloat32 && wts.is_contiguous());
   const c10::cuda::CUDAGuard guard(ret_y.device());
   const int64_t T = wts.size(0), k = wts.size(1), H = ret_y.size(1);
   Tensor out = out_.has_value() ? *out_ : torch::empty({T, H}, ret_y.options().dtype(torch::kBFloat16));
   TORCH_CHECK(out.stride(1) == 1 && out.size(0) >= T && T * k <= ret_y.size(0));
   if (residual.has_value()) { check_bf16(*residual, "residual"); check_rows(*residual, "residual"); }
+  if (norm_w.has_value()) {
+    check_bf16(*norm_w, "norm_w");
+    TORCH_CHECK(normed.has_value() && normed->scalar_type() == torch::kBFloat16 && normed->stride(1) == 1 && normed->size(0) >= T &&
+                normed->size(1) == H && norm_w->is_contiguous() && norm_w->numel() == H, "bad fused-norm arguments");
+  }
   LAUNCH_OK(b200::ep_combine_launch(reinterpret_cast<const uint32_t*>(flag_ptr), reinterpret_cast<const uint32_t*>(expected.data_ptr<int>()),
                                     reinterpret_cast<uint32_t*>(error_ptr), ret_y.data_ptr<float>(), wts.data_ptr<float>(),
                                     residual.has_value() ? residual->data_ptr() : nullptr, residual.has_value() ? residual->stride(0) : 0,
-                                    out.data_ptr(), out.stride(0), (int)T, (int)k, (int)H, cur_stream()));
+                                    out.data_ptr(), out.stride(0), (int)T, (int)k, (int)H, cur_stream(),
+                                    norm_w.has_value() ? norm_w->data_ptr() : nullptr, (float)norm_eps,
+                                    normed.has_value() ? normed->data_ptr() : nullptr, normed.has_value() ? normed->stride(0) : 0));
   return out;
 }
 }  // namespace
@@ -808,7 +850,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("recv_meta_ptr"), py::arg("recv_x_ptr"), py::arg("world"), py::arg("cap"), py::arg("E_local"), py::arg("H"),
         py::arg("device"), py::arg("rows_bound") = 0, py::arg("ret_y") = std::vector<int64_t>());
   m.def("ep_combine", &ep_combine, py::arg("flag_ptr"), py::arg("expected"), py::arg("error_ptr"), py::arg("ret_y"), py::arg("wts"),
-        py::arg("residual") = py::none(), py::arg("out") = py::none());
+        py::arg("residual") = py::none(), py::arg("out") = py::none(), py::arg("norm_w") = py::none(), py::arg("norm_eps") = 1e-6,
+        py::arg("normed") = py::none());
+  m.def("ep_route_dispatch", &ep_route_dispatch, py::arg("x"), py::arg("gate_w"), py::arg("top_k"), py::arg("n_group"), py::arg("topk_group"),
+        py::arg("scaling"), py::arg("norm_topk"), py::arg("experts_per_rank"), py::arg("my_rank"), py::arg("cap_e"), py::arg("recv_x"),
+        py::arg("recv_dst"), py::arg("recv_cnt"), py::arg("recv_seq"), py::arg("my_ret"), py::arg("send_seq"), py::arg("done_counter"),
+        py::arg("ret_expected") = py::none(), py::arg("norm_w") = py::none(), py::arg("norm_eps") = 1e-6, py::arg("normed_out") = py::none());
   m.def("init_scratch", &init_scratch);
   m.def("launch_count", []() { return g_launches; });
   m.def("pdl_skip_next", []() { b200::pdl_skip_next(); });

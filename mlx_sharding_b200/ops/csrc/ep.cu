@@ -27,11 +27,8 @@ namespace b200 {
 
 namespace {
 
-constexpr int kMaxWorld = 16;
-
-struct PeerTable {
-  unsigned long long p[kMaxWorld];
-};
+constexpr int kMaxWorld = kEpMaxWorld;
+using PeerTable = EpPeerTable;
 
 // ---------------------------------------------------------------------------------------------- dispatch
 // one warp per (token, k) pair
@@ -274,6 +271,89 @@ __global__ void ep_combine_kernel(const uint32_t* flag, const uint32_t* __restri
   reinterpret_cast<uint4*>(out + (size_t)t * ld_out)[v] = o;
 }
 
+// Combine + the next layer's input RMSNorm (one CTA per token; same fusion as moe_combine_norm_kernel for the local MoE block)
+constexpr int kEpCombThreads = 256;
+constexpr int kEpCombMaxV = 4;   // H <= 8192
+__global__ void __launch_bounds__(kEpCombThreads)
+ep_combine_norm_kernel(const uint32_t* flag, const uint32_t* __restrict__ expected_ptr, uint32_t* error_flag, unsigned long long timeout_ns,
+                       const float* __restrict__ ret_y, const float* __restrict__ wts, const __nv_bfloat16* __restrict__ residual,
+                       long long ld_res, __nv_bfloat16* __restrict__ out, long long ld_out, int top_k, int H,
+                       const __nv_bfloat16* __restrict__ norm_w, float norm_eps, __nv_bfloat16* __restrict__ normed, long long ld_normed) {
+  pdl_sync();
+  if (threadIdx.x == 0) {
+    const uint32_t expected = *reinterpret_cast<const volatile uint32_t*>(expected_ptr);
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    while (true) {
+      const uint32_t v = ld_acquire_sys(flag);
+      if ((int32_t)(v - expected) >= 0) break;
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) { if (error_flag) atomicExch(error_flag, 1u); break; }
+      __nanosleep(32);
+    }
+    __threadfence_system();
+  }
+  __shared__ float s_w[32];
+  __shared__ float red[kEpCombThreads / 32];
+  const int t = blockIdx.x;
+  if (threadIdx.x < top_k) s_w[threadIdx.x] = wts[(size_t)t * top_k + threadIdx.x];
+  __syncthreads();
+  const int nvec = H / 8;
+  uint4 keep[kEpCombMaxV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kEpCombMaxV; ++i) {
+    const int v = threadIdx.x + i * kEpCombThreads;
+    if (v < nvec) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int k = 0; k < top_k; ++k) {
+        const float w = s_w[k];
+        const float4* src = reinterpret_cast<const float4*>(ret_y + ((size_t)t * top_k + k) * H + v * 8);
+        const float4 a = __ldcv(src), b = __ldcv(src + 1);
+        acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
+        acc[4] += w * b.x; acc[5] += w * b.y; acc[6] += w * b.z; acc[7] += w * b.w;
+      }
+      if (residual != nullptr) {
+        const uint4 r = reinterpret_cast<const uint4*>(residual + (size_t)t * ld_res)[v];
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[2 * j] += bf16_lo(rr[j]); acc[2 * j + 1] += bf16_hi(rr[j]); }
+      }
+      uint4 o;
+      o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+      o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+      reinterpret_cast<uint4*>(out + (size_t)t * ld_out)[v] = o;
+      keep[i] = o;
+      const uint32_t oo[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float a = bf16_lo(oo[j]), b = bf16_hi(oo[j]); ss += a * a + b * b; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < kEpCombThreads / 32; ++i) tot += red[i];
+  const float inv = rsqrtf(tot / (float)H + norm_eps);
+#pragma unroll
+  for (int i = 0; i < kEpCombMaxV; ++i) {
+    const int v = threadIdx.x + i * kEpCombThreads;
+    if (v < nvec) {
+      const uint4 g = __ldg(reinterpret_cast<const uint4*>(norm_w) + v);
+      const uint32_t oo[4] = {keep[i].x, keep[i].y, keep[i].z, keep[i].w}, gg[4] = {g.x, g.y, g.z, g.w};
+      uint32_t n[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) n[j] = pack_bf16(bf16_lo(oo[j]) * inv * bf16_lo(gg[j]), bf16_hi(oo[j]) * inv * bf16_hi(gg[j]));
+      reinterpret_cast<uint4*>(normed + (size_t)t * ld_normed)[v] = make_uint4(n[0], n[1], n[2], n[3]);
+    }
+  }
+}
+
 constexpr unsigned long long kTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
 
 PeerTable make_table(const unsigned long long* v, int world) {
@@ -333,9 +413,16 @@ cudaError_t ep_regroup_launch(const unsigned long long* recv_words, uint32_t* lo
 
 cudaError_t ep_combine_launch(const uint32_t* flag, const uint32_t* expected_ptr, uint32_t* error_flag, const float* ret_y,
                               const float* wts, const void* residual, long long ld_res, void* out, long long ld_out, int T, int top_k,
-                              int H, cudaStream_t s) {
+                              int H, cudaStream_t s, const void* norm_w, float norm_eps, void* normed, long long ld_normed) {
   if (T == 0) return cudaSuccess;
   if (H % 8) return cudaErrorInvalidValue;
+  if (norm_w != nullptr) {
+    if (normed == nullptr || top_k > 32 || H > kEpCombThreads * 8 * kEpCombMaxV) return cudaErrorInvalidValue;
+    (void)launch_pdl(ep_combine_norm_kernel, dim3(T), dim3(kEpCombThreads), 0, s, flag, expected_ptr, error_flag, kTimeoutNs, ret_y, wts,
+                     static_cast<const __nv_bfloat16*>(residual), ld_res, static_cast<__nv_bfloat16*>(out), ld_out, top_k, H,
+                     static_cast<const __nv_bfloat16*>(norm_w), norm_eps, static_cast<__nv_bfloat16*>(normed), ld_normed);
+    return cudaGetLastError();
+  }
   const long long total = (long long)T * (H / 8);
   (void)launch_pdl(ep_combine_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, flag, expected_ptr, error_flag, kTimeoutNs,
                    ret_y, wts, static_cast<const __nv_bfloat16*>(residual), ld_res, static_cast<__nv_bfloat16*>(out), ld_out, T, top_k, H);

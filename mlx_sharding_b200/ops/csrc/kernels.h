@@ -67,13 +67,30 @@ cudaError_t mla_decode_launch(const void* q, long long q_ld_t, int B, const void
                               const int* block_tables, int max_blocks, const int* context_lens, int max_ctx, float scale,
                               int nsplit, float* workspace, void* out, long long o_ld_t, long long* dbg, cudaStream_t s);
 
+// ---- expert-parallel peer tables (ep.cu, and the router's fused dispatch in moe.cu)
+constexpr int kEpMaxWorld = 16;
+struct EpPeerTable {
+  unsigned long long p[kEpMaxWorld];
+};
+// Fused router + expert-parallel dispatch (v2 exchange, see ep.cu): the router CTA of a token reserves the slots of its top-k pairs
+// in the owners' expert-major receive buffers (remote atomics), stores the (normalised) row there and takes part in the
+// publication protocol of ep_dispatch_scatter_kernel — one kernel instead of norm + route + dispatch.
+struct RouteEP {
+  int enabled = 0, experts_per_rank = 0, world = 0, my_rank = 0, cap_e = 0;
+  EpPeerTable recv_x, recv_dst, recv_cnt, recv_seq, my_ret;
+  uint32_t* send_seq = nullptr;
+  unsigned int* done_counter = nullptr;
+  uint32_t* ret_expected = nullptr;
+};
+
 // ---- moe.cu
 // router: fp32 softmax(x W^T) -> top-k (optionally group limited) -> weights * scaling (or normalised)
 // `extra`: always-on experts appended after the routed ones (ids E .. E+extra-1, weight 1); idx / wts rows are top_k + extra wide
 cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, int T, int H, int E, int top_k,
                              int n_group, int topk_group, float scaling, bool norm_topk, int extra, int* idx, float* wts,
                              int* sc_counts, int sc_stride, int* sc_pair_row, void* sc_x, const void* norm_w, float norm_eps,
-                             cudaStream_t s);
+                             cudaStream_t s, const RouteEP* ep = nullptr, void* normed_out = nullptr, long long ld_normed = 0);
+// (normed_out: also store the normalised row — the shared-expert branch of an expert-parallel block consumes it)
 // (norm_w != nullptr: `x` is the un-normalised residual stream; the router normalises the row in shared memory first — the fused
 //  pre-MoE RMSNorm — so logits and scattered expert inputs equal what a separate norm kernel would have produced)
 // (sc_*: scatter mode for decode batches — every (token, k) pair claims slot `atomicAdd(sc_counts[e])` of expert e's fixed-stride
@@ -131,6 +148,7 @@ cudaError_t ep_regroup_launch(const unsigned long long* recv_words, uint32_t* lo
                               unsigned long long* row_dst, cudaStream_t s);
 cudaError_t ep_combine_launch(const uint32_t* flag, const uint32_t* expected_ptr, uint32_t* error_flag, const float* ret_y,
                               const float* wts, const void* residual, long long ld_res, void* out, long long ld_out, int T, int top_k,
-                              int H, cudaStream_t s);
+                              int H, cudaStream_t s, const void* norm_w = nullptr, float norm_eps = 0.f,
+                              void* normed = nullptr, long long ld_normed = 0);
 
 }  // namespace b200

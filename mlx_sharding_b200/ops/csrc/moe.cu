@@ -40,8 +40,12 @@ __global__ void __launch_bounds__(kRouteToks == 1 ? 1024 : kRouteThreads)
 moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv_bfloat16* __restrict__ gw, int T, int H,
                  int E, int top_k, int n_group, int topk_group, float scaling, int norm_topk, int extra, int* __restrict__ idx,
                  float* __restrict__ wts, int* __restrict__ sc_counts, int sc_stride, int* __restrict__ sc_pair_row,
-                 __nv_bfloat16* __restrict__ sc_x, const __nv_bfloat16* __restrict__ norm_w, float norm_eps) {
+                 __nv_bfloat16* __restrict__ sc_x, const __nv_bfloat16* __restrict__ norm_w, float norm_eps, const RouteEP ep,
+                 __nv_bfloat16* __restrict__ normed_out, long long ld_normed) {
   pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
+  // expert-parallel dispatch fused into the router: this step's sequence number (bumped by the last CTA at the very end, after
+  // every CTA has read it here)
+  const uint32_t ep_seq = ep.enabled ? *reinterpret_cast<const volatile uint32_t*>(ep.send_seq) + 1u : 0u;
   extern __shared__ __align__(16) uint8_t smem[];
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem);                 // [kRouteToks][H]
   float* logits = reinterpret_cast<float*>(smem + (size_t)kRouteToks * H * 2);  // [kRouteToks][E]
@@ -81,6 +85,12 @@ moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv
       }
     }
     __syncthreads();
+  }
+  if (normed_out != nullptr) {
+    for (int i = threadIdx.x; i < kRouteToks * nvec; i += blockDim.x) {
+      const int tk = i / nvec, v = i % nvec;
+      if (t0 + tk < T) reinterpret_cast<uint4*>(normed_out + (size_t)(t0 + tk) * ld_normed)[v] = reinterpret_cast<const uint4*>(xs + (size_t)tk * H)[v];
+    }
   }
   for (int e = warp; e < E; e += blockDim.x / 32) {
     float acc[kRouteToks];
@@ -124,6 +134,7 @@ moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv
   const int tk = warp;
   const int t = t0 + tk;
   __shared__ int s_rows[32];
+  __shared__ int s_dst[32];
   if (tk < kRouteToks && t < T) {
   float sc[kMaxEPerLane], sel[kMaxEPerLane];
   float mx = -INFINITY;
@@ -214,6 +225,17 @@ moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv
     sc_pair_row[(size_t)t * row + lane] = r;
     s_rows[lane] = r;
   }
+  if (kRouteToks == 1 && ep.enabled && lane < top_k) {
+    // sender-side slot reservation in the owner's expert-major receive buffer (counters double-buffered by step parity) + the
+    // address the owner's down-projection epilogue returns this pair's output row to (my return buffer as mapped by the owner)
+    const int dst = my_i / ep.experts_per_rank, le = my_i - dst * ep.experts_per_rank;
+    const int slot = atomicAdd_system(reinterpret_cast<int*>(ep.recv_cnt.p[dst]) + (int)(ep_seq & 1u) * ep.experts_per_rank + le, 1);
+    const int r = slot < ep.cap_e ? le * ep.cap_e + slot : -1;
+    s_rows[lane] = r;
+    s_dst[lane] = dst;
+    if (r >= 0)
+      reinterpret_cast<unsigned long long*>(ep.recv_dst.p[dst])[r] = ep.my_ret.p[dst] + ((unsigned long long)t * top_k + lane) * H * sizeof(float);
+  }
   }
   if (kRouteToks == 1 && sc_counts != nullptr) {
     __syncthreads();
@@ -222,6 +244,34 @@ moe_route_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv
       for (int i = threadIdx.x; i < row * nvec; i += blockDim.x) {
         const int k = i / nvec, v = i % nvec;
         reinterpret_cast<uint4*>(sc_x + (size_t)s_rows[k] * H)[v] = reinterpret_cast<const uint4*>(xs)[v];
+      }
+    }
+  }
+  if (kRouteToks == 1 && ep.enabled) {
+    __syncthreads();
+    if (t0 < T) {
+      for (int i = threadIdx.x; i < top_k * nvec; i += blockDim.x) {
+        const int k = i / nvec, v = i % nvec;
+        if (s_rows[k] >= 0)
+          reinterpret_cast<uint4*>(ep.recv_x.p[s_dst[k]])[(size_t)s_rows[k] * nvec + v] = reinterpret_cast<const uint4*>(xs)[v];
+      }
+    }
+    // publication (same protocol as ep_dispatch_scatter_kernel): every CTA fences its remote stores, the last one writes the
+    // step's sequence number to every destination with release.sys and advances the local step state
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = (atomicAdd(ep.done_counter, 1u) + 1u == gridDim.x);
+    __syncthreads();
+    if (last) {
+      __threadfence_system();
+      for (int r = threadIdx.x; r < ep.world; r += blockDim.x)
+        st_release_sys_u64(reinterpret_cast<unsigned long long*>(ep.recv_seq.p[r]) + ep.my_rank, (unsigned long long)ep_seq);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        *ep.send_seq = ep_seq;
+        *ep.done_counter = 0u;
+        if (ep.ret_expected != nullptr) *ep.ret_expected += (uint32_t)ep.world;
       }
     }
   }
@@ -397,7 +447,11 @@ moe_combine_norm_kernel(const float* __restrict__ y_perm, const int* __restrict_
 
 cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, int T, int H, int E, int top_k, int n_group,
                              int topk_group, float scaling, bool norm_topk, int extra, int* idx, float* wts, int* sc_counts,
-                             int sc_stride, int* sc_pair_row, void* sc_x, const void* norm_w, float norm_eps, cudaStream_t s) {
+                             int sc_stride, int* sc_pair_row, void* sc_x, const void* norm_w, float norm_eps, cudaStream_t s,
+                             const RouteEP* ep_in, void* normed_out, long long ld_normed) {
+  RouteEP ep;
+  if (ep_in != nullptr) ep = *ep_in;
+  if (ep.enabled && (T == 0 || T > 1024 || ep.world > kEpMaxWorld || sc_counts != nullptr)) return cudaErrorInvalidValue;   // one-token-per-CTA variant only
   if (T == 0) return cudaSuccess;
   if (sc_counts != nullptr && (T > 1024 || sc_stride < T)) return cudaErrorInvalidValue;   // scatter: one-token-per-CTA variant only
   if (E > 32 * kMaxEPerLane || top_k + extra > 32 || extra < 0 || (H % 8) || n_group > 32 || (n_group > 1 && E % n_group)) return cudaErrorInvalidValue;
@@ -409,7 +463,8 @@ cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, 
     // one token per CTA, 32 warps: each warp owns <= 2 experts, so the whole router row set costs two L2 round trips
     (void)launch_pdl(moe_route_kernel<1>, dim3(T), dim3(E >= 64 ? 1024 : (E >= 32 ? 512 : kRouteThreads)), smem, s, xx, ld_x, gw, T, H, E, top_k, n_group, topk_group, scaling,
                                                        norm_topk ? 1 : 0, extra, idx, wts, sc_counts, sc_stride, sc_pair_row, static_cast<__nv_bfloat16*>(sc_x),
-                                                       static_cast<const __nv_bfloat16*>(norm_w), norm_eps);
+                                                       static_cast<const __nv_bfloat16*>(norm_w), norm_eps, ep,
+                                                       static_cast<__nv_bfloat16*>(normed_out), ld_normed);
   } else {
     constexpr int TOKS = 8;
     const size_t smem = (size_t)TOKS * H * 2 + (size_t)TOKS * E * 4;
@@ -421,7 +476,8 @@ cudaError_t moe_route_launch(const void* x, long long ld_x, const void* gate_w, 
     }
     (void)launch_pdl(moe_route_kernel<TOKS>, dim3((T + TOKS - 1) / TOKS), dim3(kRouteThreads), smem, s, xx, ld_x, gw, T, H, E, top_k, n_group, topk_group,
                                                                            scaling, norm_topk ? 1 : 0, extra, idx, wts, sc_counts, sc_stride, sc_pair_row, static_cast<__nv_bfloat16*>(sc_x),
-                                                                           static_cast<const __nv_bfloat16*>(norm_w), norm_eps);
+                                                                           static_cast<const __nv_bfloat16*>(norm_w), norm_eps, ep,
+                                                                           static_cast<__nv_bfloat16*>(normed_out), ld_normed);
   }
   return cudaGetLastError();
 }

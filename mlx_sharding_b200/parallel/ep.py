@@ -177,6 +177,54 @@ def _forward_v2(self, x, idx, w, residual, out, Tmax, join):
 ExpertParallelMoE._forward_v2 = _forward_v2
 
 
+def _route_forward(self, h, gate_w, route_kw: dict, pre_norm, residual_fn, out=None, next_norm=None):
+    """The whole expert-parallel block as FOUR kernels (v2 exchange, 1 <= T <= 1024): router with the pre-MoE RMSNorm and the
+    dispatch folded in (``moe.cu``: the token's CTA reserves its pairs' slots on the owners with remote atomics, stores the
+    normalised row there and takes part in the publication) -> grouped gate/up GEMM (acquires the arrivals) -> grouped down GEMM
+    (epilogue returns the rows) -> combine with the next layer's input norm folded in.
+
+    ``h``: un-normalised residual stream; ``pre_norm = (weight, eps)``; ``residual_fn(normed)`` -> ``(residual, join)``: called
+    right after the router so the shared-expert branch (which consumes ``normed``) forks onto the side stream behind it;
+    ``next_norm = (weight, eps)`` or None.  Returns ``out`` or ``(out, normed_next)``."""
+    b, C = self.b, self.b.C
+    from ..ops import b200 as O
+
+    T = h.shape[0]
+    k = int(route_kw["top_k"])
+    assert b.v2 and 1 <= T <= 1024 and T * k <= b.cap
+    W, st = b.world, b.state
+    Tmax = max(T, getattr(self, "peer_tokens_default", 0) or 0)
+    stride = min(W * b.max_tokens, (W * Tmax + 63) // 64 * 64)
+    rows, row_dst = b.recv_views(stride)
+    rk = dict(route_kw)
+    if rk.pop("method", "greedy") != "group_limited_greedy":
+        rk["n_group"], rk["topk_group"] = 1, 1
+    normed = torch.empty_like(h)
+    idx, w = C.ep_route_dispatch(h, O._bf16(gate_w), k, int(rk["n_group"]), int(rk["topk_group"]), float(rk["scaling"]),
+                                 bool(rk["norm_topk"]), self.E_local, b.rank, stride, b.t_recv_x, b.t_recv_meta, b.t_cnt,
+                                 b.t_recv_count, b.t_my_ret, st[W + 4:W + 5], st[W:W + 1], st[W + 3:W + 4],
+                                 O._bf16(pre_norm[0]), float(pre_norm[1]), normed)
+    residual, join = residual_fn(normed)
+    max_rows = min(W * Tmax, stride)
+    exp_rows = T * k
+    arrive, seq, err = b.base + b.off_recv_count, st[W + 4:W + 5], st[-1:].data_ptr()
+    hmid = C.grouped_linear(rows, self.wg, self.wu, b.cnt, max_rows, self.act, False, None, None, None, exp_rows, stride, arrive, seq, err, W, True)
+    C.grouped_linear(hmid, self.wd, None, b.cnt, max_rows, 0, True, row_dst, b.ret_flags_dev, st[W + 1:W + 2], exp_rows, stride, arrive, seq, err,
+                     W, False)
+    if join is not None:
+        join.wait()
+    flag, exp, errp = b.base + b.off_flags + 128, st[W + 3:W + 4], st[-1:].data_ptr()
+    if next_norm is not None and h.shape[1] <= 8192:
+        nxt = torch.empty_like(h)
+        res = C.ep_combine(flag, exp, errp, b.ret_y, w, residual, out, O._bf16(next_norm[0]), float(next_norm[1]), nxt)
+        return res, nxt
+    res = C.ep_combine(flag, exp, errp, b.ret_y, w, residual, out)
+    return res if next_norm is None else (res, O.rmsnorm(res, next_norm[0], next_norm[1]))
+
+
+ExpertParallelMoE.route_forward = _route_forward
+
+
 class ExpertParallelMoERef:
     """Backend-agnostic expert parallelism: the same exchange expressed with ``torch.distributed.all_to_all_single`` (gloo on
     CPU, NCCL on GPU) and the ``ops.reference`` expert math.  It is the CPU path of ``enable_expert_parallel`` (tests, plumbing

@@ -15,6 +15,45 @@ from mlx_sharding_b200.ops.weights import LinearWeight  # noqa: E402
 from mlx_sharding_b200.parallel.ep import EPBuffers, ExpertParallelMoE  # noqa: E402
 
 
+def run_fused(H, I, E, k, Ts, layers, rank, world):
+    """``route_forward``: [norm + router + dispatch] -> GEMMs -> [combine + next norm], against separate norm / route / local experts."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    mk = lambda *s, sc=0.03: (torch.randn(*s, device="cuda", generator=g) * sc).to(torch.bfloat16)
+    banks = [(LinearWeight(weight=mk(E, I, H)), LinearWeight(weight=mk(E, I, H)), LinearWeight(weight=mk(E, H, I)), mk(E, H, sc=0.05),
+              (1.0 + mk(H, sc=3.0)).contiguous(), (1.0 + mk(H, sc=3.0)).contiguous()) for _ in range(layers)]
+    maxT = max(Ts)
+    bufs = EPBuffers(H, maxT, k, experts_per_rank=E // world)
+    eps = [ExpertParallelMoE(bufs, b[0], b[1], b[2], E) for b in banks]
+    rk = dict(top_k=k, method="greedy", n_group=1, topk_group=1, scaling=1.0, norm_topk=False)
+    g2 = torch.Generator(device="cuda").manual_seed(200 + rank)
+    ok = True
+    for step, T in enumerate(Ts):
+        hs = [(torch.randn(T, H, device="cuda", generator=g2) * 2.0).to(torch.bfloat16) for _ in range(layers)]
+        torch.cuda.synchronize()
+        outs = [ep.route_forward(h, b[3], rk, (b[4], 1e-6), (lambda h_: (lambda normed: (h_, None)))(h), next_norm=(b[5], 1e-6))
+                for ep, h, b in zip(eps, hs, banks)]                                                         # back to back
+        torch.cuda.synchronize()
+        worst, badrows, rows = 0.0, 0, 0
+        for (Wg, Wu, Wd, gate, n1, n2), h, (got, got_n) in zip(banks, hs, outs):
+            normed = b200.rmsnorm(h, n1, 1e-6)
+            idx, w = b200.moe_route(normed, gate, k)
+            ref = b200.moe_experts(normed, idx, w, Wg, Wu, Wd, "silu", residual=h)
+            ref_n = b200.rmsnorm(ref, n2, 1e-6)
+            # per-row error relative to the row's magnitude (the test's norm weights make the values large: one bf16 ulp of an
+            # output near 32 is 0.25)
+            rel = lambda a, b_: (a.float() - b_.float()).abs().amax(-1) / (b_.float().abs().amax(-1) + 1.0)
+            d = torch.maximum(rel(got, ref), rel(got_n, ref_n))
+            worst = max(worst, d.max().item())
+            badrows += int((d > 2e-2).sum().item())
+            rows += T
+        # a normalised value may land on the neighbouring bf16 (statistics summed in a different order), which can flip a near-tie
+        # of the router for a rare token: tolerate one such row per step, nothing systematic
+        good = badrows <= 1 and not bufs.error()
+        ok = ok and good
+        print(f"[rank {rank}] fused H={H} E={E} step {step} T={T}: max rel err {worst:.4g}, bad rows {badrows}/{rows}, error flag {bufs.error()}", flush=True)
+    return ok
+
+
 def run(H, I, E, k, Ts, layers, v1, rank, world):
     g = torch.Generator(device="cuda").manual_seed(5)
     mk = lambda *s, sc=0.03: (torch.randn(*s, device="cuda", generator=g) * sc).to(torch.bfloat16)
@@ -78,6 +117,16 @@ if __name__ == "__main__":
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     rank, world = dist.get_rank(), dist.get_world_size()
     v1 = len(sys.argv) > 1 and sys.argv[1] == "v1"
+    if len(sys.argv) > 1 and sys.argv[1] == "fused":
+        ok = run_fused(256, 128, 8, 3, [384, 16, 16, 48, 384, 16], 3, rank, world)
+        ok = run_fused(2048, 1408, 64, 6, [256, 64, 64, 48, 256, 64], 5, rank, world) and ok
+        flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0 and flag.item() == 1.0:
+            print("EP_STRESS_OK fused")
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(0)
     ok = run(256, 128, 8, 3, [384, 16, 16, 48, 384, 16], 3, v1, rank, world)
     ok = run(2048, 1408, 64, 6, [256, 64, 64, 48, 256, 64], 5, v1, rank, world) and ok
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")

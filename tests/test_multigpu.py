@@ -40,10 +40,11 @@ def test_expert_parallel_moe(version, port):
     assert "EP_OK " + version in out, out[-3000:]
 
 
-@pytest.mark.parametrize("version,port", [("v2", 29584), ("v1", 29585)])
+@pytest.mark.parametrize("version,port", [("v2", 29584), ("v1", 29585), ("fused", 29586)])
 def test_expert_parallel_stress(version, port):
     """Several EP layers sharing one buffer set, called back to back with no host synchronisation, token counts changing from step
-    to step (prefill chunk <-> decode batch), two geometries; every output must equal the local MoE bit for bit."""
+    to step (prefill chunk <-> decode batch), two geometries; every output must equal the local MoE bit for bit.  ``fused``: the
+    four-kernel block (norm + router + dispatch in one kernel, combine + next norm in one) against separate kernels."""
     out = _torchrun("ep_stress.py", [version], port=port)
     assert "EP_STRESS_OK " + version in out, out[-3000:]
 
