@@ -39,7 +39,8 @@ class Gemma2Stage(LlamaStage):
         normed = O.rmsnorm(h, w["in_ln"], eps, True)
         attn = self._attention(w, normed, meta, kpool, vpool)
         a = O.linear(attn, w["o"])
-        return O.rmsnorm(a, w["post_ln"], eps, True, residual=h)
+        # a stage may end here (half-layer boundary): the norm's epilogue is then the fused P2P hand-off (ops/b200.py::rmsnorm)
+        return O.rmsnorm(a, w["post_ln"], eps, True, residual=h, **self._final_kwargs(i, h.shape[0], "attn"))
 
     def mlp_block(self, i, h, meta):
         O, c, w = self.ops, self.cfg, self.layer_weights[i]
@@ -47,7 +48,8 @@ class Gemma2Stage(LlamaStage):
         normed = O.rmsnorm(h, w["mlp_ln"], eps, True)
         act = O.gated_up(normed, w["gate"], w["up"], self.act)
         m = O.linear(act, w["down"])
-        return O.rmsnorm(m, w["post_ffn_ln"], eps, True, residual=h)
+        # Gemma-2's stage-final kernel is this norm, not a GEMM: it stores into the next stage's inbox and raises its flag itself
+        return O.rmsnorm(m, w["post_ffn_ln"], eps, True, residual=h, **self._final_kwargs(i, h.shape[0], "mlp"))
 
 
 Model = Gemma2Stage

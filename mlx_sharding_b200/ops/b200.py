@@ -118,8 +118,12 @@ def embed(ids: torch.Tensor, emb: LinearWeight, scale: float = 1.0, dtype: torch
     return C().embed(ids, _bf16(emb.weight), None, None, 0, 64, float(scale))
 
 
-def rmsnorm(x, w, eps: float, gemma: bool = False, residual: Optional[torch.Tensor] = None):
-    return C().rmsnorm(x, w, float(eps), bool(gemma), residual)
+def rmsnorm(x, w, eps: float, gemma: bool = False, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+            signal: Optional[Tuple[int, int]] = None):
+    """``out`` / ``signal``: fused stage boundary — the norm stores straight into the next stage's inbox (peer memory) and the
+    last CTA raises its flag (Gemma-2 stages end in a norm, not in a GEMM)."""
+    flag, val = signal if signal is not None else (0, 0)
+    return C().rmsnorm(x, w, float(eps), bool(gemma), residual, out, int(flag), int(val))
 
 
 def add_rmsnorm(x, residual, w, eps, gemma=False):

@@ -266,14 +266,19 @@ Tensor grouped_linear_q(const Tensor& x, const Tensor& wq, const Tensor& scales_
 bool gemm_q_supported(int64_t bits, int64_t group, int64_t k) { return b200::gemm_q_supported((int)bits, (int)group, (int)k); }
 
 // ---- elementwise ------------------------------------------------------------------------------------------------
-Tensor rmsnorm(const Tensor& x, const Tensor& w, double eps, bool gemma, const c10::optional<Tensor>& residual) {
+Tensor rmsnorm(const Tensor& x, const Tensor& w, double eps, bool gemma, const c10::optional<Tensor>& residual,
+               const c10::optional<Tensor>& out_, int64_t signal_flag_ptr, int64_t signal_value) {
   check_bf16(x, "x"); check_bf16(w, "w"); check_rows(x, "x");
   const c10::cuda::CUDAGuard guard(x.device());
-  Tensor out = torch::empty({x.size(0), x.size(1)}, x.options());
+  Tensor out = out_.has_value() ? *out_ : torch::empty({x.size(0), x.size(1)}, x.options());
+  TORCH_CHECK(out.scalar_type() == torch::kBFloat16 && out.stride(1) == 1 && out.size(0) >= x.size(0) && out.size(1) == x.size(1), "bad out tensor");
+  unsigned int* done = nullptr;
+  if (signal_flag_ptr != 0) done = reinterpret_cast<unsigned int*>(scratch().get_counters(x.device()).data_ptr<int>()) + 65532;
   const void* res = nullptr; long long ldr = 0;
   if (residual.has_value()) { check_bf16(*residual, "residual"); check_rows(*residual, "residual"); res = residual->data_ptr(); ldr = residual->stride(0); }
   LAUNCH_OK(b200::rmsnorm_launch(x.data_ptr(), x.stride(0), w.data_ptr(), res, ldr, out.data_ptr(), out.stride(0), (int)x.size(0),
-                               (int)x.size(1), (float)eps, gemma, cur_stream()));
+                               (int)x.size(1), (float)eps, gemma, cur_stream(), reinterpret_cast<uint32_t*>(signal_flag_ptr),
+                               (uint32_t)signal_value, done));
   return out;
 }
 
@@ -800,7 +805,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("linear_q", &linear_q);
   m.def("grouped_linear_q", &grouped_linear_q);
   m.def("gemm_q_supported", &gemm_q_supported);
-  m.def("rmsnorm", &rmsnorm, py::arg("x"), py::arg("w"), py::arg("eps"), py::arg("gemma") = false, py::arg("residual") = py::none());
+  m.def("rmsnorm", &rmsnorm, py::arg("x"), py::arg("w"), py::arg("eps"), py::arg("gemma") = false, py::arg("residual") = py::none(),
+        py::arg("out") = py::none(), py::arg("signal_flag_ptr") = 0, py::arg("signal_value") = 0);
   m.def("rope_", &rope_);
   m.def("l2_prefetch", &l2_prefetch, py::arg("t"), py::arg("offset_bytes"), py::arg("nbytes"));
   m.def("embed", &embed, py::arg("ids"), py::arg("table"), py::arg("scales") = py::none(), py::arg("biases") = py::none(),

@@ -88,7 +88,8 @@ constexpr int kNormMaxV = 8;
 __global__ void __launch_bounds__(kNormThreads)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv_bfloat16* __restrict__ w,
                const __nv_bfloat16* __restrict__ residual, long long ld_res, __nv_bfloat16* __restrict__ out,
-               long long ld_out, int H, float eps, int gemma) {
+               long long ld_out, int H, float eps, int gemma, uint32_t* signal_flag, uint32_t signal_value,
+               unsigned int* done_counter) {
   pdl_sync();  // PDL: predecessor's writes visible; let the successor start its prologue
   const int row = blockIdx.x;
   const int nvec = H / 8;
@@ -138,16 +139,33 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv_b
       orow[v] = pack8(f);
     }
   }
+  if (signal_flag != nullptr) {
+    // fused stage boundary (Gemma-2: a stage's last kernel is the post-feed-forward norm + residual): `out` is the next stage's
+    // inbox in peer memory; every CTA fences its row, the last one raises the consumer's flag with system scope
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int done = atomicAdd(done_counter, 1u) + 1u;
+      if (done == gridDim.x) {
+        *done_counter = 0u;
+        __threadfence_system();
+        if (signal_value == 0u) atomicAdd_system(signal_flag, 1u);
+        else st_release_sys(signal_flag, signal_value);
+      }
+    }
+  }
 }
 
 cudaError_t rmsnorm_launch(const void* x, long long ld_x, const void* w, const void* residual, long long ld_res,
-                           void* out, long long ld_out, int rows, int H, float eps, bool gemma, cudaStream_t s) {
+                           void* out, long long ld_out, int rows, int H, float eps, bool gemma, cudaStream_t s,
+                           uint32_t* signal_flag, uint32_t signal_value, unsigned int* done_counter) {
   if (H % 8 != 0 || H > kNormThreads * 8 * kNormMaxV || (ld_x % 8) || (ld_out % 8)) return cudaErrorInvalidValue;
   if (rows == 0) return cudaSuccess;
   (void)launch_pdl(rmsnorm_kernel, dim3(rows), dim3(kNormThreads), 0, s, static_cast<const __nv_bfloat16*>(x), ld_x,
                                                  static_cast<const __nv_bfloat16*>(w),
                                                  static_cast<const __nv_bfloat16*>(residual), ld_res,
-                                                 static_cast<__nv_bfloat16*>(out), ld_out, H, eps, gemma ? 1 : 0);
+                                                 static_cast<__nv_bfloat16*>(out), ld_out, H, eps, gemma ? 1 : 0, signal_flag, signal_value,
+                                                 done_counter);
   return cudaGetLastError();
 }
 

@@ -8,7 +8,8 @@ namespace b200 {
 
 // ---- elementwise.cu
 cudaError_t rmsnorm_launch(const void* x, long long ld_x, const void* w, const void* residual, long long ld_res,
-                           void* out, long long ld_out, int rows, int H, float eps, bool gemma, cudaStream_t s);
+                           void* out, long long ld_out, int rows, int H, float eps, bool gemma, cudaStream_t s, uint32_t* signal_flag = nullptr,
+                           uint32_t signal_value = 0, unsigned int* done_counter = nullptr);
 cudaError_t rope_launch(void* x, long long ld_t, long long ld_h, int heads, const int* positions, const float* inv_freq,
                         int rot_off, int rot_dim, bool interleaved, float mscale, int T, cudaStream_t s);
 // bulk L2 prefetch of [p, p + bytes) (16 B aligned), a few threads, no PDL: meant for a side stream

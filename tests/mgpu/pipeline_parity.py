@@ -9,7 +9,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-from helpers import GPU_DSV2, GPU_LLAMA  # noqa: E402
+from helpers import GPU_DSV2, GPU_GEMMA2, GPU_LLAMA  # noqa: E402
 from mlx_sharding_b200.config import ModelConfig, ShardSpec  # noqa: E402
 from mlx_sharding_b200.ops.meta import BatchMeta  # noqa: E402
 from mlx_sharding_b200.parallel.decode_loop import DecodeLoop  # noqa: E402
@@ -109,7 +109,7 @@ if __name__ == "__main__":
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
     arch, transport = sys.argv[1], sys.argv[2]
-    cfgd = GPU_DSV2 if arch == "dsv2" else GPU_LLAMA
+    cfgd = {"dsv2": GPU_DSV2, "gemma2": GPU_GEMMA2}.get(arch, GPU_LLAMA)
     steps, B, S = 6, 16, 24
     prompts, hist = run(cfgd, transport, steps, B, S, half=len(sys.argv) > 3 and sys.argv[3] == "half")
     if dist.get_rank() == 0:

@@ -18,7 +18,7 @@ def _torchrun(script, args, nproc=2, port=29571, timeout=420):
 
 
 @pytest.mark.parametrize("arch,transport,port", [("dsv2", "fused", 29571), ("llama", "fused", 29572), ("dsv2", "nccl", 29573),
-                                                 ("dsv2", "fused,half", 29575)])
+                                                 ("dsv2", "fused,half", 29575), ("gemma2", "fused", 29579)])
 def test_pipeline_parity(arch, transport, port):
     """``fused,half``: the stage boundary sits between the attention and the MLP block (o-proj epilogue does the P2P store)."""
     out = _torchrun("pipeline_parity.py", [arch] + transport.split(","), port=port)
