@@ -246,12 +246,23 @@ __global__ void ep_combine_kernel(const uint32_t* flag, const uint32_t* __restri
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int k = 0; k < top_k; ++k) {
-    const float w = wts[(size_t)t * top_k + k];
-    const float4* src = reinterpret_cast<const float4*>(ret_y + ((size_t)t * top_k + k) * H + v * 8);
-    const float4 a = __ldcv(src), b = __ldcv(src + 1);   // rows were written by peers: never from a stale L1 line
-    acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
-    acc[4] += w * b.x; acc[5] += w * b.y; acc[6] += w * b.z; acc[7] += w * b.w;
+  for (int k0 = 0; k0 < top_k; k0 += 4) {   // four pairs' loads in flight before any is used; accumulation order unchanged
+    float4 a[4], b[4];
+    float w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u < top_k ? k0 + u : top_k - 1;
+      w[u] = k0 + u < top_k ? wts[(size_t)t * top_k + k] : 0.f;
+      const float4* src = reinterpret_cast<const float4*>(ret_y + ((size_t)t * top_k + k) * H + v * 8);
+      a[u] = __ldcv(src); b[u] = __ldcv(src + 1);   // rows were written by peers: never from a stale L1 line
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (k0 + u < top_k) {
+        acc[0] += w[u] * a[u].x; acc[1] += w[u] * a[u].y; acc[2] += w[u] * a[u].z; acc[3] += w[u] * a[u].w;
+        acc[4] += w[u] * b[u].x; acc[5] += w[u] * b[u].y; acc[6] += w[u] * b[u].z; acc[7] += w[u] * b[u].w;
+      }
+    }
   }
   if (residual != nullptr) {
     const uint4 r = reinterpret_cast<const uint4*>(residual + (size_t)t * ld_res)[v];
@@ -309,12 +320,23 @@ ep_combine_norm_kernel(const uint32_t* flag, const uint32_t* __restrict__ expect
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-      for (int k = 0; k < top_k; ++k) {
-        const float w = s_w[k];
-        const float4* src = reinterpret_cast<const float4*>(ret_y + ((size_t)t * top_k + k) * H + v * 8);
-        const float4 a = __ldcv(src), b = __ldcv(src + 1);
-        acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
-        acc[4] += w * b.x; acc[5] += w * b.y; acc[6] += w * b.z; acc[7] += w * b.w;
+      for (int k0 = 0; k0 < top_k; k0 += 4) {
+        float4 a[4], b[4];
+        float w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u < top_k ? k0 + u : top_k - 1;
+          w[u] = k0 + u < top_k ? s_w[k] : 0.f;
+          const float4* src = reinterpret_cast<const float4*>(ret_y + ((size_t)t * top_k + k) * H + v * 8);
+          a[u] = __ldcv(src); b[u] = __ldcv(src + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (k0 + u < top_k) {
+            acc[0] += w[u] * a[u].x; acc[1] += w[u] * a[u].y; acc[2] += w[u] * a[u].z; acc[3] += w[u] * a[u].w;
+            acc[4] += w[u] * b[u].x; acc[5] += w[u] * b[u].y; acc[6] += w[u] * b[u].z; acc[7] += w[u] * b[u].w;
+          }
+        }
       }
       if (residual != nullptr) {
         const uint4 r = reinterpret_cast<const uint4*>(residual + (size_t)t * ld_res)[v];

@@ -330,13 +330,26 @@ __global__ void moe_combine_kernel(const float* __restrict__ y_perm, const int* 
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int k = 0; k < top_k; ++k) {
-      const float w = wts[(size_t)t * top_k + k];
-      const float* src = y_perm + (size_t)pair_row[(size_t)t * top_k + k] * H + v * 8;
-      const float4 a = *reinterpret_cast<const float4*>(src);
-      const float4 b = *reinterpret_cast<const float4*>(src + 4);
-      acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
-      acc[4] += w * b.x; acc[5] += w * b.y; acc[6] += w * b.z; acc[7] += w * b.w;
+    // the expert rows come from L2 / HBM: issue the loads of four pairs before using any (a plain k-loop serialises one round trip
+    // per pair — 8 round trips for top-6 + 2 shared experts); the accumulation order stays k = 0, 1, 2, ...
+    for (int k0 = 0; k0 < top_k; k0 += 4) {
+      float4 a[4], b[4];
+      float w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u < top_k ? k0 + u : top_k - 1;
+        w[u] = k0 + u < top_k ? wts[(size_t)t * top_k + k] : 0.f;
+        const float* src = y_perm + (size_t)pair_row[(size_t)t * top_k + k] * H + v * 8;
+        a[u] = *reinterpret_cast<const float4*>(src);
+        b[u] = *reinterpret_cast<const float4*>(src + 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (k0 + u < top_k) {
+          acc[0] += w[u] * a[u].x; acc[1] += w[u] * a[u].y; acc[2] += w[u] * a[u].z; acc[3] += w[u] * a[u].w;
+          acc[4] += w[u] * b[u].x; acc[5] += w[u] * b[u].y; acc[6] += w[u] * b[u].z; acc[7] += w[u] * b[u].w;
+        }
+      }
     }
     if (residual != nullptr) {
       const uint4 r = reinterpret_cast<const uint4*>(residual + (size_t)t * ld_res)[v];
@@ -398,13 +411,24 @@ moe_combine_norm_kernel(const float* __restrict__ y_perm, const int* __restrict_
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-      for (int k = 0; k < top_k; ++k) {
-        const float w = s_w[k];
-        const float* src = y_perm + (size_t)s_row[k] * H + v * 8;
-        const float4 a = *reinterpret_cast<const float4*>(src);
-        const float4 b = *reinterpret_cast<const float4*>(src + 4);
-        acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
-        acc[4] += w * b.x; acc[5] += w * b.y; acc[6] += w * b.z; acc[7] += w * b.w;
+      for (int k0 = 0; k0 < top_k; k0 += 4) {   // four pairs' loads in flight (see moe_combine_kernel)
+        float4 a[4], b[4];
+        float w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u < top_k ? k0 + u : top_k - 1;
+          w[u] = k0 + u < top_k ? s_w[k] : 0.f;
+          const float* src = y_perm + (size_t)s_row[k] * H + v * 8;
+          a[u] = *reinterpret_cast<const float4*>(src);
+          b[u] = *reinterpret_cast<const float4*>(src + 4);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (k0 + u < top_k) {
+            acc[0] += w[u] * a[u].x; acc[1] += w[u] * a[u].y; acc[2] += w[u] * a[u].z; acc[3] += w[u] * a[u].w;
+            acc[4] += w[u] * b[u].x; acc[5] += w[u] * b[u].y; acc[6] += w[u] * b[u].z; acc[7] += w[u] * b[u].w;
+          }
+        }
       }
       if (residual != nullptr) {
         const uint4 r = reinterpret_cast<const uint4*>(residual + (size_t)t * ld_res)[v];
