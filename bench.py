@@ -157,6 +157,9 @@ def main(argv=None):
             base = None
         gc.collect()
         torch.cuda.empty_cache()
+        settle = float(os.environ.get("MLXB200_BENCH_SETTLE_S", "0") or 0)
+        if settle > 0:
+            time.sleep(settle)
         if world > 1:
             dist.barrier()
 

@@ -477,9 +477,13 @@ Tensor mla_decode(const Tensor& q, const Tensor& pool, const Tensor& block_table
   if (B == 0) return out;
   const int tiles = (int)((max_ctx + 63) / 64);
   int nsplit = (int)nsplit_req;
-  if (nsplit <= 0) {   // flash-decoding split: until one wave of CTAs exists, keeping >= 2 tiles per split
+  if (nsplit <= 0) {
+    // flash-decoding split: until one wave of CTAs exists, keeping >= 8 tiles (512 tokens) per split.  A split costs a second
+    // kernel (the LSE combine) and a partial round trip: measured (bench/mla_bench.py sweep) 64 x 128 tokens 14.4 us un-split vs
+    // 19.5 us in two splits, 64 x 1024 best at 2, 64 x 4096 at 2-4, 8 x 16 k at 16 — i.e. ~8+ tiles per split.  `max_ctx` is
+    // the *bound* the caller's block tables allow (serving pads them to 8 pages), so short contexts must not split on it.
     nsplit = 1;
-    while (B * nsplit < sm_count() && tiles / (nsplit * 2) >= 2 && nsplit < 64) nsplit *= 2;
+    while (B * nsplit < sm_count() && tiles / (nsplit * 2) >= 8 && nsplit < 64) nsplit *= 2;
   }
   if (nsplit > tiles) nsplit = tiles > 0 ? tiles : 1;
   float* ws = nullptr;
