@@ -71,6 +71,7 @@ def parse_request_params(body: dict) -> dict:
         repetition_context_size=body.get("repetition_context_size", 20),
         logit_bias=body.get("logit_bias", None),
         logprobs=body.get("logprobs", -1),
+        seed=body.get("seed", None),      # OpenAI's `seed`: the request's own random stream (the reference has no such field)
     )
     if not isinstance(p["stream"], bool):
         raise RequestError("stream must be a boolean")
@@ -101,6 +102,8 @@ def parse_request_params(body: dict) -> dict:
             raise RequestError("logit_bias must be a dict of int to float")
     if not isinstance(p["model"], str):
         raise RequestError("model must be a string")
+    if p["seed"] is not None and (not isinstance(p["seed"], int) or isinstance(p["seed"], bool)):
+        raise RequestError("seed must be an integer")
     return p
 
 
@@ -372,7 +375,7 @@ class APIHandler(BaseHTTPRequestHandler):
             params = SamplingParams(temperature=float(prm["temperature"]), top_p=float(prm["top_p"]),
                                     repetition_penalty=float(prm["repetition_penalty"]),
                                     repetition_context_size=prm["repetition_context_size"],
-                                    logit_bias=prm["logit_bias"], logprobs=max(prm["logprobs"], 0))
+                                    logit_bias=prm["logit_bias"], logprobs=max(prm["logprobs"], 0), seed=prm["seed"])
             req = self.engine.submit(prompt, params, max_tokens=prm["max_tokens"],
                                      eos_token_id=self.tokenizer.eos_token_id, stop_id_sequences=stop_ids)
         except (RequestError, ValueError, AssertionError, KeyError) as e:

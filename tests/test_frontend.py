@@ -115,3 +115,24 @@ def test_metrics_and_client_disconnect(servers):
             break
         time.sleep(0.05)
     assert not provider.engine.busy() and provider.engine.table.alloc.num_free == free0
+
+
+def test_stop_sequences_logit_bias_and_seeded_sampling_through_workers(servers):
+    """Request features that live on both sides of the pipe: stop sequences (engine stops, handler trims / holds text back),
+    logit bias + top-logprobs (sampling block), per-request seeds (same seed -> same tokens, from either front end)."""
+    wport, iport, _ = servers
+    body = {"prompt": "abc", "max_tokens": 10, "temperature": 0, "logit_bias": {"65": 100.0}, "stop": "AA", "logprobs": 2}
+    rw, jw = _post(wport, "/v1/completions", body)
+    ri, ji = _post(iport, "/v1/completions", body)
+    assert jw["choices"][0]["finish_reason"] == "stop" and jw["choices"][0]["text"] == "" and jw["choices"][0] == ji["choices"][0]
+    # streaming with a stop sequence: held-back text never reaches the client
+    r, raw = _post(wport, "/v1/completions", dict(body, stream=True), raw=True)
+    ev = [json.loads(l[6:]) for l in raw.decode().split("\n\n") if l.startswith("data: ") and l[6:] != "[DONE]"]
+    assert "".join(e["choices"][0]["text"] for e in ev) == "" and ev[-1]["choices"][0]["finish_reason"] == "stop"
+    # sampled requests: reproducible per seed, identical from a worker and from the in-process server
+    samp = {"prompt": "seeded", "max_tokens": 12, "temperature": 1.0, "top_p": 0.9, "seed": 1234}
+    a = _post(wport, "/v1/completions", samp)[1]["choices"][0]["logprobs"]["tokens"]
+    b = _post(wport, "/v1/completions", samp)[1]["choices"][0]["logprobs"]["tokens"]
+    c = _post(iport, "/v1/completions", samp)[1]["choices"][0]["logprobs"]["tokens"]
+    d = _post(wport, "/v1/completions", dict(samp, seed=99))[1]["choices"][0]["logprobs"]["tokens"]
+    assert a == b == c and len(a) == 12 and d != a
