@@ -312,6 +312,31 @@ class DeepseekV2Stage(StageModel):
         nh, nope, rd, vd, lr = c.num_attention_heads, c.qk_nope_head_dim, c.qk_rope_head_dim, c.v_head_dim, c.kv_lora_rank
         page = kpool.shape[2]
         lat = O.rmsnorm(ckv, w["kv_a_ln"], c.rms_norm_eps)                                      # [T, lr]
+        if getattr(meta, "fresh", False) and self.rope.interleaved and os.environ.get("MLXB200_PREFILL_FAST", "1") != "0":
+            # Fresh prompts (no cached context; the TTFT case): everything the batch attends to is this chunk itself, so the
+            # per-head K / V come straight from the chunk's own latents — no gather of cached pages, no concatenate / transpose
+            # passes.  kv_b on the T rows, then ONE fused launch ropes q_pe in place and writes K = [k_nope | rope(k_pe)] and V
+            # into temporary paged pools addressed by an identity block table; flash prefill runs on those.
+            B = meta.num_seqs
+            mb = max(1, (meta.max_ctx_len + page - 1) // page)
+            tmp = getattr(meta, "_fresh_tmp", None)
+            if tmp is None or tmp[0] != (page, mb):
+                seq = torch.bucketize(torch.arange(T, device=h.device), meta.cu_seqlens[1:].long().contiguous(), right=True)
+                pos = meta.positions.long()
+                tslots = ((seq * mb + pos // page) * page + pos % page).to(torch.int32)
+                tbt = torch.arange(B * mb, dtype=torch.int32, device=h.device).view(B, mb)
+                tmp = meta._fresh_tmp = ((page, mb), BatchMeta(meta.positions, tslots, meta.cu_seqlens, meta.context_lens, tbt, meta.last_idx,
+                                                               meta.num_tokens, B, meta.max_q_len, meta.max_ctx_len, page))
+            tmp_meta = tmp[1]
+            kv = O.linear(lat, w["kv_b"]).view(T, nh, nope + vd)
+            kpe = k_pe.reshape(T, 1, rd).clone()
+            O.rope_(kpe, meta.positions, self.rope, 0)
+            kpool.view(-1, lr + rd).index_copy_(0, meta.slot_mapping.long(), torch.cat([lat, kpe.view(T, rd)], 1))   # latent cache
+            ktmp = torch.empty(B * mb, nh, page, nope + rd, dtype=lat.dtype, device=h.device)
+            vtmp = torch.empty(B * mb, nh, page, vd, dtype=lat.dtype, device=h.device)
+            O.mla_rope_kv_write(q, k_pe, kv, ktmp, vtmp, tmp_meta, self.rope, nope, vd)
+            attn = O.paged_attention(q, ktmp, vtmp, tmp_meta, c.attn_scale, 0.0)
+            return O.linear(attn.reshape(T, nh * vd), w["o"], residual=h, **self._final_kwargs(i, T, "attn"))
         O.rope_(q, meta.positions, self.rope, nope)                                              # q_pe in place
         kpe = k_pe.reshape(T, 1, rd).clone()
         O.rope_(kpe, meta.positions, self.rope, 0)

@@ -31,6 +31,7 @@ class BatchMeta:
     max_q_len: int
     max_ctx_len: int
     page_size: int
+    fresh: bool = False          # host-side hint: no sequence of this step has cached context (every prompt starts at position 0)
 
     @property
     def is_decode(self) -> bool:
@@ -40,7 +41,7 @@ class BatchMeta:
         mv = lambda t: t.to(device, non_blocking=non_blocking)
         return BatchMeta(mv(self.positions), mv(self.slot_mapping), mv(self.cu_seqlens), mv(self.context_lens),
                          mv(self.block_tables), mv(self.last_idx), self.num_tokens, self.num_seqs,
-                         self.max_q_len, self.max_ctx_len, self.page_size)
+                         self.max_q_len, self.max_ctx_len, self.page_size, self.fresh)
 
     # ------------------------------------------------------------------ wire format
     def pack(self) -> torch.Tensor:
@@ -98,7 +99,9 @@ class BatchMeta:
             cu.append(cu[-1] + ql)
             last.append(cu[-1] - 1)
             ctx_after.append(c0 + ql)
-        return BatchMeta._finish_build(pos, slots, cu, ctx_after, last, q_lens, block_tables, page_size, device, pad_blocks_to)
+        m = BatchMeta._finish_build(pos, slots, cu, ctx_after, last, q_lens, block_tables, page_size, device, pad_blocks_to)
+        m.fresh = B > 0 and all(int(c) == 0 for c in ctx_before)
+        return m
 
     @staticmethod
     def _finish_build(pos, slots, cu, ctx_after, last, q_lens, block_tables, page_size, device, pad_blocks_to) -> "BatchMeta":

@@ -148,6 +148,11 @@ class StepRunner:
             flat = torch.empty(lay.size, dtype=torch.int32, device=self.dev)
             self._h2d(flat, blk)
             sv = StepViews(flat, lay, self.stage.kv.page_size, mctx, mq)
+            # host-side hint for the models (the block is still in host memory here): every sequence of this step starts at position
+            # 0, i.e. context length == query length — prefill of fresh prompts can skip gathering cached context
+            o = lay.meta + 6 + 2 * lay.T
+            cu, ctx = blk[o:o + lay.B + 1], blk[o + lay.B + 1:o + 2 * lay.B + 1]
+            sv.meta.fresh = bool(lay.B > 0 and np.array_equal(ctx, cu[1:] - cu[:-1]))
             rl = ResultLayout(lay.B, lay.k)
             res = torch.zeros(rl.nbytes, dtype=torch.uint8, device=self.dev) if self.last else None
             return self._device_step(sv, group, res, rl)
