@@ -136,3 +136,26 @@ def test_page_allocator_never_double_books(ops, page):
     for sid in list(live):
         table.release(sid)
     assert alloc.num_free == free0
+
+
+def test_batchmeta_fresh_flag_and_its_host_side_recomputation():
+    """``BatchMeta.fresh`` (no sequence has cached context) is set by ``build`` and recomputed by every pipeline stage from the packed
+    step block (context length == query length for all sequences) — the hint the DeepSeek prefill fast path keys on."""
+    import numpy as np
+
+    from mlx_sharding_b200.engine.sampler import SamplingParams
+    from mlx_sharding_b200.ops.meta import BatchMeta
+    from mlx_sharding_b200.parallel.graph_decode import HEADER_WORDS, pack_step, unpack_header
+
+    bts = [[1, 2], [3, 4], [5, 6]]
+    cases = [([5, 7, 3], [0, 0, 0], True), ([5, 7, 3], [0, 4, 0], False), ([1, 1, 1], [9, 2, 5], False), ([4], [0], True)]
+    for q, c0, want in cases:
+        m = BatchMeta.build(q, c0, bts[:len(q)], 16)
+        assert m.fresh is want and m.to("cpu").fresh is want
+        toks = torch.arange(sum(q), dtype=torch.int64)
+        wire, lay = pack_step(1, m, toks, [SamplingParams(temperature=0.0)] * len(q), [[]] * len(q), None, max(q) > 1)
+        lay2, _ = unpack_header(wire)
+        blk = wire[HEADER_WORDS:HEADER_WORDS + lay2.size]
+        o = lay2.meta + 6 + 2 * lay2.T
+        cu, ctx = blk[o:o + lay2.B + 1], blk[o + lay2.B + 1:o + 2 * lay2.B + 1]
+        assert bool(np.array_equal(ctx, cu[1:] - cu[:-1])) is want
