@@ -50,7 +50,8 @@ class _WorkerSink:
             return
         with self.lock:
             buf, self.buf = self.buf, []
-        self.out.put(("events", buf))
+        if self.alive:      # a dead worker's requests were cancelled; their last events have nowhere to go
+            self.out.put(("events", buf))
 
     def _send_loop(self):
         while True:
