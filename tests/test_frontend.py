@@ -136,3 +136,71 @@ def test_stop_sequences_logit_bias_and_seeded_sampling_through_workers(servers):
     c = _post(iport, "/v1/completions", samp)[1]["choices"][0]["logprobs"]["tokens"]
     d = _post(wport, "/v1/completions", dict(samp, seed=99))[1]["choices"][0]["logprobs"]["tokens"]
     assert a == b == c and len(a) == 12 and d != a
+
+
+def test_engine_bridge_under_load_without_http():
+    """RemoteEngine <-> _WorkerSink over a pipe inside one process, stub pipeline (no model): many concurrent requests with different
+    lengths, a few cancelled mid-stream — every stream ends exactly once with the right number of tokens, nothing is left behind."""
+    import multiprocessing as mp
+    import random
+
+    from mlx_sharding_b200.engine.core import LLMEngine, StepOutput
+    from mlx_sharding_b200.engine.sampler import SamplingParams
+    from mlx_sharding_b200.server.frontend import RemoteEngine, _WorkerSink
+
+    class Stub:
+        num_stages = 2
+
+        def submit(self, inp):
+            n = inp.meta.num_seqs
+            return StepOutput(tokens=[7] * n, logprobs=[0.0] * n)
+
+        def wait(self, h):
+            return h
+
+        def reset(self):
+            pass
+
+    eng = LLMEngine(Stub(), 4096, 16, num_groups=2, max_seqs_per_group=16, max_prefill_tokens=256).start()
+    free0 = eng.table.alloc.num_free
+    a, b = mp.Pipe(duplex=True)
+    sink = _WorkerSink(a, eng)
+    eng.sinks.append(sink)
+    remote = RemoteEngine(b)
+    rnd = random.Random(3)
+    plan = [(rnd.randint(1, 40), rnd.random() < 0.15) for _ in range(120)]
+    results = [None] * len(plan)
+
+    def run(i):
+        n, cancel = plan[i]
+        r = remote.submit(list(range(3, 3 + rnd.randint(1, 30))), SamplingParams(temperature=0.0), max_tokens=n, eos_token_id=None)
+        got, reason = 0, None
+        for ev in r:
+            if ev.token < 0:
+                reason = ev.finish_reason
+                break
+            got += 1
+            if cancel and got == 1:
+                r.cancel()
+            if ev.finished:
+                reason = ev.finish_reason
+        results[i] = (got, reason)
+
+    th = [threading.Thread(target=run, args=(i,)) for i in range(len(plan))]
+    [t.start() for t in th]
+    [t.join(timeout=120) for t in th]
+    assert all(not t.is_alive() for t in th)
+    for (n, cancel), (got, reason) in zip(plan, results):
+        if cancel and n > 2:
+            assert reason in ("cancelled", "length") and 1 <= got <= n       # the cancel races with the engine: it may finish first
+        else:
+            assert got == n and reason == "length"
+    for _ in range(100):
+        if not eng.busy() and not sink.requests and not remote.reqs:
+            break
+        time.sleep(0.05)
+    assert not eng.busy() and not sink.requests and not remote.reqs
+    assert eng.table.alloc.num_free == free0
+    eng.shutdown()
+    a.close()
+    b.close()
